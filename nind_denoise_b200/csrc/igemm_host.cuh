@@ -1,0 +1,255 @@
+// Host side of the implicit-GEMM kernel: tensor-map encoding, tiling/pipeline choices, launch.
+#pragma once
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include "igemm.cuh"
+
+namespace nind {
+
+// NHWC bf16 activation buffer as stored (halo frames included in hs/ws).
+struct ActBuf {
+  __nv_bfloat16* ptr = nullptr;
+  int b = 0, hs = 0, ws = 0, c = 0;
+  size_t elems() const { return (size_t)b * hs * ws * c; }
+};
+
+struct ConvSpec {
+  ActBuf in;
+  int in_coff = 0, cin = 0;  // channels [in_coff, in_coff + cin) of `in`
+  int taps = 9;              // 9: 3x3 valid conv over the stored buffer; 1: per-pixel GEMM
+  const __nv_bfloat16* w = nullptr;  // packed [taps][n_total][cin], cin contiguous
+  int n_total = 0;
+  const float* bias = nullptr;
+  int act = ACT_NONE;
+  float slope = 0.f;
+  int epi_mode = EPI_STORE;
+  ActBuf out;  // EPI_STORE / EPI_D2S destination
+  int out_coff = 0, out_halo = 0;
+  int d2s_cout = 0;
+  // EPI_HEAD
+  const float* head_w = nullptr;
+  const float* head_b = nullptr;
+  float* head_out = nullptr;  // [B][3][hy][hx] fp32
+  int head_unpad = 0, head_hy = 0, head_hx = 0, head_sigmoid = 0;
+  // tuning / probing
+  int a_mode = 0, a_bo_mode = 0;
+  int n_tile = 0;     // 0 = auto
+  int force_ws = -1;  // -1 = auto
+  int max_ctas = 0;   // 0 = number of SMs
+};
+
+struct IgemmLaunch {
+  CUtensorMap tmA, tmB;
+  IgemmParams p;
+  int n_tile = 0;
+  size_t smem = 0;
+  int grid = 0;
+  double flops = 0;  // algorithmic 2*MAC actually useful (valid outputs only)
+};
+
+typedef CUresult (*PFN_tmapEncodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
+                                        const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                        const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                        CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+inline PFN_tmapEncodeTiled tmap_encoder() {
+  static PFN_tmapEncodeTiled fn = nullptr;
+  if (!fn) {
+    void* f = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<PFN_tmapEncodeTiled>(f);
+  }
+  return fn;
+}
+
+// bf16 tensor map, 128-byte swizzle, zero OOB fill.  dims/strides innermost first.
+inline bool encode_tmap_bf16(CUtensorMap* m, const void* base, int rank, const uint64_t* dims,
+                             const uint64_t* strides_bytes /* rank-1 */, const uint32_t* box,
+                             std::string* why) {
+  PFN_tmapEncodeTiled enc = tmap_encoder();
+  if (!enc) {
+    if (why) *why = "cuTensorMapEncodeTiled entry point not available";
+    return false;
+  }
+  cuuint64_t gd[5], gs[5];
+  cuuint32_t bx[5], es[5];
+  for (int i = 0; i < rank; ++i) {
+    gd[i] = dims[i];
+    bx[i] = box[i];
+    es[i] = 1;
+    if (i + 1 < rank) gs[i] = strides_bytes[i];
+  }
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), gd, gs,
+                   bx, es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    if (why) {
+      char buf[256];
+      snprintf(buf, sizeof buf, "cuTensorMapEncodeTiled failed: %d (rank %d dims %llu %llu %llu box %u %u %u)",
+               (int)r, rank, (unsigned long long)dims[0], (unsigned long long)(rank > 1 ? dims[1] : 0),
+               (unsigned long long)(rank > 2 ? dims[2] : 0), box[0], rank > 1 ? box[1] : 0,
+               rank > 2 ? box[2] : 0);
+      *why = buf;
+    }
+    return false;
+  }
+  return true;
+}
+
+constexpr size_t IG_SMEM_LIMIT = 227 * 1024;
+
+inline int device_sm_count() {
+  static int n = 0;
+  if (!n) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    if (n <= 0) n = 148;
+  }
+  return n;
+}
+
+inline bool build_igemm(const ConvSpec& s, IgemmLaunch* L, std::string* why) {
+  auto fail = [&](const char* m) {
+    if (why) *why = m;
+    return false;
+  };
+  if (s.taps != 9 && s.taps != 1) return fail("taps must be 1 or 9");
+  if (s.cin % 64 != 0 || s.cin <= 0) return fail("input channels must be a multiple of 64");
+  if (s.n_total % 32 != 0) return fail("output columns must be a multiple of 32");
+  if (s.in.c % 8 != 0) return fail("buffer channel count must be a multiple of 8");
+  const int shrink = s.taps == 9 ? 2 : 0;
+  IgemmParams& p = L->p;
+  memset(&p, 0, sizeof p);
+
+  int n_tile = s.n_tile;
+  if (n_tile == 0) n_tile = s.n_total >= 256 ? 256 : (s.n_total >= 128 ? 128 : 64);
+  if (n_tile != 64 && n_tile != 128 && n_tile != 256) return fail("n_tile must be 64/128/256");
+  if (s.epi_mode == EPI_HEAD && (n_tile != 64 || s.n_total != 64)) return fail("head needs N=64");
+  L->n_tile = n_tile;
+
+  p.w_valid = s.in.ws - shrink;
+  p.h_valid = s.in.hs - shrink;
+  p.hs_in = s.in.hs;
+  p.rows_total = s.in.b * s.in.hs;
+  p.tiles_x = (p.w_valid + IG_TILE_W - 1) / IG_TILE_W;
+  p.tiles_y = (p.rows_total - shrink + IG_TILE_H - 1) / IG_TILE_H;
+  p.tiles_n = (s.n_total + n_tile - 1) / n_tile;
+  p.total_tiles = p.tiles_x * p.tiles_y * p.tiles_n;
+  p.kchunks = s.cin / 64;
+  p.taps = s.taps;
+  p.a_mode = s.taps == 9 ? s.a_mode : 0;
+  p.a_bo_mode = s.a_bo_mode;
+
+  uint32_t boxA[3];
+  if (s.taps == 1) {
+    boxA[0] = 64; boxA[1] = 8; boxA[2] = 16;
+    p.a_tx_bytes = 16384; p.a_stage_bytes = 16384; p.a_sbo = 1024;
+    p.tap_off[0] = 0;
+  } else if (p.a_mode == 0) {
+    boxA[0] = 64; boxA[1] = 10; boxA[2] = 18;
+    p.a_tx_bytes = 10 * 18 * 128; p.a_stage_bytes = 23552; p.a_sbo = 1280;
+    for (int t = 0; t < 9; ++t) p.tap_off[t] = ((t / 3) * 10 + (t % 3)) * 128;
+  } else {
+    boxA[0] = 64; boxA[1] = 8; boxA[2] = 18;
+    p.a_box_bytes = 8 * 18 * 128; p.a_copy_bytes = 8 * 18 * 128;
+    p.a_tx_bytes = 3 * p.a_box_bytes; p.a_stage_bytes = 3 * p.a_copy_bytes; p.a_sbo = 1024;
+    for (int t = 0; t < 9; ++t) p.tap_off[t] = (t % 3) * p.a_copy_bytes + (t / 3) * 8 * 128;
+  }
+
+  // pipeline depth / weights-stationary decision
+  const uint32_t b_bytes = n_tile * 128;
+  const int kt = p.kchunks * p.taps;
+  bool ws = false;
+  if (s.force_ws != 0 && p.tiles_n == 1 && kt <= IG_MAX_STAGES &&
+      igemm_smem_bytes(n_tile, 2, p.a_stage_bytes, kt) <= IG_SMEM_LIMIT)
+    ws = true;
+  if (s.force_ws == 1 && !ws) return fail("weights do not fit in shared memory");
+  if (ws) {
+    p.sb = kt;
+    p.sa = 2;
+    while (p.sa < 6 && igemm_smem_bytes(n_tile, p.sa + 1, p.a_stage_bytes, p.sb) <= IG_SMEM_LIMIT) ++p.sa;
+  } else {
+    p.sb = 4;
+    p.sa = 2;
+    while (p.sa < 4 && igemm_smem_bytes(n_tile, p.sa + 1, p.a_stage_bytes, p.sb) <= IG_SMEM_LIMIT) ++p.sa;
+    while (p.sb < 8 && igemm_smem_bytes(n_tile, p.sa, p.a_stage_bytes, p.sb + 1) <= IG_SMEM_LIMIT) ++p.sb;
+    if (igemm_smem_bytes(n_tile, p.sa, p.a_stage_bytes, p.sb) > IG_SMEM_LIMIT)
+      return fail("pipeline does not fit in shared memory");
+  }
+  p.ws = ws ? 1 : 0;
+  L->smem = igemm_smem_bytes(n_tile, p.sa, p.a_stage_bytes, p.sb);
+
+  // tensor maps
+  {
+    const uint64_t dims[3] = {(uint64_t)s.cin, (uint64_t)s.in.ws, (uint64_t)p.rows_total};
+    const uint64_t strides[2] = {(uint64_t)s.in.c * 2, (uint64_t)s.in.ws * s.in.c * 2};
+    if (!encode_tmap_bf16(&L->tmA, s.in.ptr + s.in_coff, 3, dims, strides, boxA, why)) return false;
+    const uint64_t dimsB[2] = {(uint64_t)s.cin, (uint64_t)s.taps * s.n_total};
+    const uint64_t stridesB[1] = {(uint64_t)s.cin * 2};
+    const uint32_t boxB[2] = {64, (uint32_t)n_tile};
+    if (!encode_tmap_bf16(&L->tmB, s.w, 2, dimsB, stridesB, boxB, why)) return false;
+  }
+
+  // epilogue
+  p.n_total = s.n_total;
+  p.epi_mode = s.epi_mode;
+  p.act = s.act;
+  p.slope = s.slope;
+  p.bias = s.bias;
+  if (s.epi_mode == EPI_HEAD) {
+    p.head_w = s.head_w; p.head_b = s.head_b; p.head_out = s.head_out;
+    p.h_unpad = s.head_unpad; p.h_size_y = s.head_hy; p.h_size_x = s.head_hx;
+    p.h_row = s.head_hx; p.h_plane = (long long)s.head_hy * s.head_hx; p.h_img = 3 * p.h_plane;
+    p.head_sigmoid = s.head_sigmoid;
+  } else {
+    const int up = s.epi_mode == EPI_D2S ? 2 : 1;
+    if (s.out.hs < up * p.h_valid + 2 * s.out_halo || s.out.ws < up * p.w_valid + 2 * s.out_halo)
+      return fail("destination buffer too small");
+    const int cols = s.epi_mode == EPI_D2S ? s.d2s_cout : s.n_total;
+    if (s.out_coff + cols > s.out.c) return fail("destination channel range out of bounds");
+    if (s.out.b != s.in.b) return fail("batch mismatch");
+    p.o_pix = s.out.c;
+    p.o_row = (long long)s.out.ws * s.out.c;
+    p.o_img = (long long)s.out.hs * p.o_row;
+    p.out = s.out.ptr + (long long)s.out_halo * p.o_row + (long long)s.out_halo * p.o_pix + s.out_coff;
+    p.d2s_cout = s.d2s_cout;
+  }
+  L->grid = p.total_tiles < (s.max_ctas > 0 ? s.max_ctas : device_sm_count())
+                ? p.total_tiles
+                : (s.max_ctas > 0 ? s.max_ctas : device_sm_count());
+  L->flops = 2.0 * s.in.b * (double)p.h_valid * p.w_valid * s.n_total * s.cin * s.taps;
+  return true;
+}
+
+inline cudaError_t igemm_set_attrs() {
+  static bool done = false;
+  if (done) return cudaSuccess;
+  cudaError_t e;
+  e = cudaFuncSetAttribute(igemm_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)IG_SMEM_LIMIT);
+  if (e != cudaSuccess) return e;
+  e = cudaFuncSetAttribute(igemm_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)IG_SMEM_LIMIT);
+  if (e != cudaSuccess) return e;
+  e = cudaFuncSetAttribute(igemm_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)IG_SMEM_LIMIT);
+  if (e != cudaSuccess) return e;
+  done = true;
+  return cudaSuccess;
+}
+
+inline cudaError_t launch_igemm(const IgemmLaunch& L, int* err_flag, cudaStream_t st) {
+  cudaError_t e = igemm_set_attrs();
+  if (e != cudaSuccess) return e;
+  IgemmParams p = L.p;
+  p.err = err_flag;
+  switch (L.n_tile) {
+    case 64: igemm_kernel<64><<<L.grid, IG_THREADS, L.smem, st>>>(L.tmA, L.tmB, p); break;
+    case 128: igemm_kernel<128><<<L.grid, IG_THREADS, L.smem, st>>>(L.tmA, L.tmB, p); break;
+    default: igemm_kernel<256><<<L.grid, IG_THREADS, L.smem, st>>>(L.tmA, L.tmB, p); break;
+  }
+  return cudaGetLastError();
+}
+
+}  // namespace nind

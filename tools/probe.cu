@@ -1,0 +1,356 @@
+// Stand-alone GPU probe (no torch): checks the UMMA shared-memory descriptor semantics the
+// implicit-GEMM kernel relies on, then checks the kernel itself against a naive CUDA-core
+// convolution.  Each invocation runs ONE test so that a trap in one cannot mask the others.
+//
+//   probe desc <r0> <sbo_bytes> <bo_mode>
+//   probe conv <taps> <cin> <n_total> <B> <Hs> <Ws> <a_mode> <bo_mode> <epi> [n_tile] [ws] [ctas]
+//
+// Build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -o tools/probe tools/probe.cu
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <vector>
+#include "../nind_denoise_b200/csrc/igemm_host.cuh"
+
+using namespace nind;
+
+#define CK(x)                                                                      \
+  do {                                                                             \
+    cudaError_t e_ = (x);                                                          \
+    if (e_ != cudaSuccess) {                                                       \
+      printf("CUDA error %s at %s:%d\n", cudaGetErrorString(e_), __FILE__, __LINE__); \
+      exit(2);                                                                     \
+    }                                                                              \
+  } while (0)
+
+static uint32_t rng_state = 12345u;
+static float frand() {
+  rng_state = rng_state * 1664525u + 1013904223u;
+  return ((rng_state >> 8) & 0xFFFF) / 32768.0f - 1.0f;
+}
+
+// ------------------------------------------------------------------ descriptor probe
+__global__ void __launch_bounds__(128, 1)
+desc_probe_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                  float* out, int r0, uint32_t sbo, int bo_mode, int* err) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t a_s = sbase;               // 256 rows x 128 B
+  const uint32_t b_s = sbase + 256 * 128;   // 64 rows x 128 B
+  const uint32_t bar_ld = b_s + 64 * 128;
+  const uint32_t bar_mma = bar_ld + 8;
+  const uint32_t slot = bar_ld + 16;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    mbar_init(bar_ld, 1);
+    mbar_init(bar_mma, 1);
+    mbar_fence_init();
+  }
+  if (warp == 0) {
+    tmem_alloc(slot, 64);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(slot));
+  if (threadIdx.x == 0) {
+    mbar_arrive_expect_tx(bar_ld, 256 * 128 + 64 * 128);
+    tma_load_2d(a_s, &tmA, bar_ld, 0, 0);
+    tma_load_2d(b_s, &tmB, bar_ld, 0, 0);
+    mbar_wait(bar_ld, 0, err, 1);
+    tc_fence_after();
+    const uint32_t a_addr = a_s + r0 * 128;
+    const uint32_t bo = bo_mode ? ((a_addr >> 7) & 7) : 0;
+    for (int k = 0; k < 4; ++k)
+      umma_bf16(tmem_base, umma_desc_sw128(a_addr + 32 * k, sbo, bo), umma_desc_sw128(b_s + 32 * k, 1024),
+                umma_idesc_bf16(128, 64), k > 0);
+    umma_commit(bar_mma);
+  }
+  __syncwarp();
+  mbar_wait(bar_mma, 0, err, 2);
+  tc_fence_after();
+  for (int c = 0; c < 2; ++c) {
+    uint32_t v[32];
+    tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(warp * 32) << 16) + c * 32, v);
+    tmem_wait_ld();
+    for (int j = 0; j < 32; ++j) out[(warp * 32 + lane) * 64 + c * 32 + j] = __uint_as_float(v[j]);
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem_base, 64);
+}
+
+static int run_desc(int r0, int sbo, int bo_mode) {
+  const int R = 256;
+  std::vector<__nv_bfloat16> hA(R * 64), hB(64 * 64);
+  std::vector<float> fA(R * 64), fB(64 * 64);
+  for (int i = 0; i < R * 64; ++i) { hA[i] = __float2bfloat16(frand()); fA[i] = __bfloat162float(hA[i]); }
+  for (int i = 0; i < 64 * 64; ++i) { hB[i] = __float2bfloat16(frand()); fB[i] = __bfloat162float(hB[i]); }
+  __nv_bfloat16 *dA, *dB;
+  float* dO;
+  int* dErr;
+  CK(cudaMalloc(&dA, hA.size() * 2));
+  CK(cudaMalloc(&dB, hB.size() * 2));
+  CK(cudaMalloc(&dO, 128 * 64 * 4));
+  CK(cudaMalloc(&dErr, 4));
+  CK(cudaMemset(dErr, 0, 4));
+  CK(cudaMemset(dO, 0, 128 * 64 * 4));
+  CK(cudaMemcpy(dA, hA.data(), hA.size() * 2, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(dB, hB.data(), hB.size() * 2, cudaMemcpyHostToDevice));
+  CUtensorMap tA, tB;
+  std::string why;
+  {
+    uint64_t d[2] = {64, (uint64_t)R}, s[1] = {128};
+    uint32_t bx[2] = {64, 256};
+    if (!encode_tmap_bf16(&tA, dA, 2, d, s, bx, &why)) { printf("%s\n", why.c_str()); return 2; }
+    uint64_t d2[2] = {64, 64};
+    uint32_t bx2[2] = {64, 64};
+    if (!encode_tmap_bf16(&tB, dB, 2, d2, s, bx2, &why)) { printf("%s\n", why.c_str()); return 2; }
+  }
+  const size_t smem = 1024 + 256 * 128 + 64 * 128 + 64;
+  CK(cudaFuncSetAttribute(desc_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  desc_probe_kernel<<<1, 128, smem>>>(tA, tB, dO, r0, (uint32_t)sbo, bo_mode, dErr);
+  CK(cudaGetLastError());
+  cudaError_t e = cudaDeviceSynchronize();
+  if (e != cudaSuccess) { printf("DESC r0=%d sbo=%d bo=%d : kernel failed: %s\n", r0, sbo, bo_mode, cudaGetErrorString(e)); return 1; }
+  std::vector<float> hO(128 * 64);
+  CK(cudaMemcpy(hO.data(), dO, hO.size() * 4, cudaMemcpyDeviceToHost));
+  // expected under "absolute address" semantics
+  double maxerr = 0;
+  int bad = 0;
+  for (int i = 0; i < 128; ++i) {
+    const int arow = r0 + (i / 8) * (sbo / 128) + (i % 8);
+    for (int n = 0; n < 64; ++n) {
+      float acc = 0;
+      for (int k = 0; k < 64; ++k) acc += fA[arow * 64 + k] * fB[n * 64 + k];
+      const double d = fabs(acc - hO[i * 64 + n]);
+      if (d > maxerr) maxerr = d;
+      if (d > 1e-2) ++bad;
+    }
+  }
+  printf("DESC r0=%d sbo=%d bo=%d : maxerr=%.5f bad=%d/8192 -> %s\n", r0, sbo, bo_mode, maxerr, bad,
+         bad == 0 ? "PASS" : "FAIL");
+  if (bad) {
+    // Which A row does each output row actually correspond to?  (diagnostic)
+    for (int i = 0; i < 24; ++i) {
+      int best = -1;
+      for (int r = 0; r < 256 && best < 0; ++r) {
+        bool ok = true;
+        for (int n = 0; n < 8 && ok; ++n) {
+          float acc = 0;
+          for (int k = 0; k < 64; ++k) acc += fA[r * 64 + k] * fB[n * 64 + k];
+          if (fabs(acc - hO[i * 64 + n]) > 1e-2) ok = false;
+        }
+        if (ok) best = r;
+      }
+      printf("  out row %d matches A row %d (expected %d)\n", i, best, r0 + (i / 8) * (sbo / 128) + (i % 8));
+    }
+  }
+  return bad ? 1 : 0;
+}
+
+// ------------------------------------------------------------------ naive reference conv
+// in: NHWC bf16 [B][Hs][Ws][C] (channels coff..coff+cin used); w: [taps][n_total][cin] bf16;
+// out: fp32 [B][Hv][Wv][n_total] after bias + activation.
+__global__ void naive_conv_kernel(const __nv_bfloat16* in, int B, int Hs, int Ws, int C, int coff, int cin,
+                                  const __nv_bfloat16* w, int taps, int n_total, const float* bias, int act,
+                                  float slope, float* out) {
+  const int tw = taps == 9 ? 3 : 1;
+  const int Hv = Hs - (tw - 1), Wv = Ws - (tw - 1);
+  const long long total = (long long)B * Hv * Wv * n_total;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int n = i % n_total;
+    long long r = i / n_total;
+    const int x = r % Wv; r /= Wv;
+    const int y = r % Hv;
+    const int b = r / Hv;
+    float acc = 0.f;
+    for (int t = 0; t < taps; ++t) {
+      const int ky = t / tw, kx = t % tw;
+      const __nv_bfloat16* ip = in + (((long long)b * Hs + y + ky) * Ws + x + kx) * C + coff;
+      const __nv_bfloat16* wp = w + ((long long)t * n_total + n) * cin;
+      for (int c = 0; c < cin; ++c) acc += __bfloat162float(ip[c]) * __bfloat162float(wp[c]);
+    }
+    acc += bias[n];
+    if (act == ACT_PRELU) acc = acc > 0.f ? acc : acc * slope;
+    out[i] = acc;
+  }
+}
+
+static int run_conv(int argc, char** argv) {
+  if (argc < 11) { printf("conv: not enough args\n"); return 2; }
+  const int taps = atoi(argv[2]), cin = atoi(argv[3]), n_total = atoi(argv[4]), B = atoi(argv[5]),
+            Hs = atoi(argv[6]), Ws = atoi(argv[7]), a_mode = atoi(argv[8]), bo_mode = atoi(argv[9]),
+            epi = atoi(argv[10]);
+  const int n_tile = argc > 11 ? atoi(argv[11]) : 0;
+  const int ws = argc > 12 ? atoi(argv[12]) : -1;
+  const int ctas = argc > 13 ? atoi(argv[13]) : 0;
+  const int tw = taps == 9 ? 3 : 1;
+  const int Hv = Hs - (tw - 1), Wv = Ws - (tw - 1);
+  const int Cbuf = cin + 64, coff = 64;  // read a channel sub-range to exercise offsets
+  const int act = ACT_PRELU;
+  const float slope = 0.25f;
+
+  std::vector<__nv_bfloat16> hin((size_t)B * Hs * Ws * Cbuf), hw((size_t)taps * n_total * cin);
+  for (auto& v : hin) v = __float2bfloat16(frand());
+  const float wscale = 1.0f / sqrtf((float)(taps * cin));
+  for (auto& v : hw) v = __float2bfloat16(frand() * wscale * 2.f);
+  const int nbias = n_total;
+  std::vector<float> hbias(nbias);
+  for (auto& v : hbias) v = frand() * 0.5f;
+  std::vector<float> hhw(3 * 64), hhb(3);
+  for (auto& v : hhw) v = frand() * 0.2f;
+  for (auto& v : hhb) v = frand() * 0.1f;
+
+  __nv_bfloat16 *din, *dw, *dout = nullptr;
+  float *dbias, *dref, *dhw, *dhb, *dhead = nullptr;
+  int* derr;
+  CK(cudaMalloc(&din, hin.size() * 2));
+  CK(cudaMalloc(&dw, hw.size() * 2));
+  CK(cudaMalloc(&dbias, hbias.size() * 4));
+  CK(cudaMalloc(&dref, (size_t)B * Hv * Wv * n_total * 4));
+  CK(cudaMalloc(&dhw, hhw.size() * 4));
+  CK(cudaMalloc(&dhb, hhb.size() * 4));
+  CK(cudaMalloc(&derr, 4));
+  CK(cudaMemset(derr, 0, 4));
+  CK(cudaMemcpy(din, hin.data(), hin.size() * 2, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(dw, hw.data(), hw.size() * 2, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(dbias, hbias.data(), hbias.size() * 4, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(dhw, hhw.data(), hhw.size() * 4, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(dhb, hhb.data(), hhb.size() * 4, cudaMemcpyHostToDevice));
+
+  ConvSpec s;
+  s.in = ActBuf{din, B, Hs, Ws, Cbuf};
+  s.in_coff = coff; s.cin = cin; s.taps = taps; s.w = dw; s.n_total = n_total; s.bias = dbias;
+  s.act = act; s.slope = slope; s.epi_mode = epi; s.a_mode = a_mode; s.a_bo_mode = bo_mode;
+  s.n_tile = n_tile; s.force_ws = ws; s.max_ctas = ctas;
+  const int halo = 2, ocoff = 32;
+  int Ho = 0, Wo = 0, Co = 0;
+  const int unpad = 1;
+  int d2s_cout = n_total / 4;
+  if (epi == EPI_STORE) {
+    Ho = Hv + 2 * halo; Wo = Wv + 2 * halo; Co = n_total + 64;
+  } else if (epi == EPI_D2S) {
+    Ho = 2 * Hv + 2 * halo; Wo = 2 * Wv + 2 * halo; Co = d2s_cout + 64;
+    std::vector<float> b2(d2s_cout);
+    for (auto& v : b2) v = frand() * 0.5f;
+    // bias per co (repeat for the 4 sub-pixels in the reference)
+    for (int n = 0; n < n_total; ++n) hbias[n] = b2[n % d2s_cout];
+    CK(cudaMemcpy(dbias, hbias.data(), hbias.size() * 4, cudaMemcpyHostToDevice));
+  }
+  std::vector<__nv_bfloat16> hout;
+  if (epi != EPI_HEAD) {
+    hout.assign((size_t)B * Ho * Wo * Co, __float2bfloat16(-77.f));
+    CK(cudaMalloc(&dout, hout.size() * 2));
+    CK(cudaMemcpy(dout, hout.data(), hout.size() * 2, cudaMemcpyHostToDevice));
+    s.out = ActBuf{dout, B, Ho, Wo, Co};
+    s.out_coff = ocoff; s.out_halo = halo; s.d2s_cout = d2s_cout;
+  } else {
+    s.head_w = dhw; s.head_b = dhb; s.head_unpad = unpad; s.head_hy = Hv - 2 * unpad; s.head_hx = Wv - 2 * unpad;
+    CK(cudaMalloc(&dhead, (size_t)B * 3 * s.head_hy * s.head_hx * 4));
+    CK(cudaMemset(dhead, 0xFF, (size_t)B * 3 * s.head_hy * s.head_hx * 4));
+    s.head_out = dhead;
+  }
+
+  IgemmLaunch L;
+  std::string why;
+  if (!build_igemm(s, &L, &why)) { printf("build_igemm failed: %s\n", why.c_str()); return 2; }
+  printf("CONV taps=%d cin=%d N=%d B=%d %dx%d a_mode=%d bo=%d epi=%d | n_tile=%d tiles=%d (x%d y%d n%d) grid=%d sa=%d sb=%d ws=%d smem=%zu\n",
+         taps, cin, n_total, B, Hs, Ws, a_mode, bo_mode, epi, L.n_tile, L.p.total_tiles, L.p.tiles_x,
+         L.p.tiles_y, L.p.tiles_n, L.grid, L.p.sa, L.p.sb, L.p.ws, L.smem);
+
+  naive_conv_kernel<<<1024, 256>>>(din, B, Hs, Ws, Cbuf, coff, cin, dw, taps, n_total, dbias, act, slope, dref);
+  CK(cudaGetLastError());
+  CK(cudaDeviceSynchronize());
+
+  cudaEvent_t e0, e1;
+  CK(cudaEventCreate(&e0));
+  CK(cudaEventCreate(&e1));
+  CK(launch_igemm(L, derr, 0));
+  cudaError_t e = cudaDeviceSynchronize();
+  if (e != cudaSuccess) {
+    int herr = -1;
+    printf("  igemm kernel failed: %s\n", cudaGetErrorString(e));
+    (void)herr;
+    return 1;
+  }
+  const int reps = 5;
+  CK(cudaEventRecord(e0));
+  for (int i = 0; i < reps; ++i) CK(launch_igemm(L, derr, 0));
+  CK(cudaEventRecord(e1));
+  CK(cudaDeviceSynchronize());
+  float ms = 0;
+  CK(cudaEventElapsedTime(&ms, e0, e1));
+  ms /= reps;
+  printf("  time %.3f ms  -> %.1f TFLOP/s (useful)\n", ms, L.flops / ms * 1e-9);
+
+  std::vector<float> href((size_t)B * Hv * Wv * n_total);
+  CK(cudaMemcpy(href.data(), dref, href.size() * 4, cudaMemcpyDeviceToHost));
+  double maxerr = 0;
+  long long bad = 0, checked = 0;
+  auto report = [&](const char* what, int b, int y, int x, int n, float got, float exp) {
+    if (bad < 12) printf("  mismatch %s b=%d y=%d x=%d n=%d got=%f exp=%f\n", what, b, y, x, n, got, exp);
+  };
+  if (epi == EPI_HEAD) {
+    std::vector<float> hh((size_t)B * 3 * s.head_hy * s.head_hx);
+    CK(cudaMemcpy(hh.data(), dhead, hh.size() * 4, cudaMemcpyDeviceToHost));
+    for (int b = 0; b < B; ++b)
+      for (int c = 0; c < 3; ++c)
+        for (int oy = 0; oy < s.head_hy; ++oy)
+          for (int ox = 0; ox < s.head_hx; ++ox) {
+            const float* rp = &href[(((size_t)b * Hv + oy + unpad) * Wv + ox + unpad) * n_total];
+            float acc = hhb[c];
+            for (int n = 0; n < 64; ++n) acc += rp[n] * hhw[c * 64 + n];
+            const float got = hh[(((size_t)b * 3 + c) * s.head_hy + oy) * s.head_hx + ox];
+            const double d = fabs(got - acc);
+            ++checked;
+            if (d > maxerr) maxerr = d;
+            if (!(d <= 2e-3 + 2e-3 * fabs(acc))) { report("head", b, oy, ox, c, got, acc); ++bad; }
+          }
+  } else {
+    CK(cudaMemcpy(hout.data(), dout, hout.size() * 2, cudaMemcpyDeviceToHost));
+    std::vector<uint8_t> touched((size_t)B * Ho * Wo * Co, 0);
+    for (int b = 0; b < B; ++b)
+      for (int y = 0; y < Hv; ++y)
+        for (int x = 0; x < Wv; ++x)
+          for (int n = 0; n < n_total; ++n) {
+            const float exp = href[(((size_t)b * Hv + y) * Wv + x) * n_total + n];
+            size_t di;
+            if (epi == EPI_STORE) {
+              di = (((size_t)b * Ho + y + halo) * Wo + x + halo) * Co + ocoff + n;
+            } else {
+              const int q = n / d2s_cout, co = n % d2s_cout;
+              di = (((size_t)b * Ho + 2 * y + (q >> 1) + halo) * Wo + 2 * x + (q & 1) + halo) * Co + ocoff + co;
+            }
+            touched[di] = 1;
+            const float got = __bfloat162float(hout[di]);
+            const double d = fabs(got - exp);
+            ++checked;
+            if (d > maxerr) maxerr = d;
+            if (!(d <= 0.02 + 0.01 * fabs(exp))) { report("out", b, y, x, n, got, exp); ++bad; }
+          }
+    // everything else must be untouched (sentinel)
+    long long stray = 0;
+    for (size_t i = 0; i < hout.size(); ++i)
+      if (!touched[i] && __bfloat162float(hout[i]) != -77.f) ++stray;
+    if (stray) { printf("  %lld stray writes outside the valid region\n", stray); bad += stray; }
+  }
+  int herr = 0;
+  CK(cudaMemcpy(&herr, derr, 4, cudaMemcpyDeviceToHost));
+  printf("  checked=%lld maxerr=%.5f bad=%lld err_flag=%d -> %s\n", checked, maxerr, bad, herr,
+         bad == 0 ? "PASS" : "FAIL");
+  return bad ? 1 : 0;
+}
+
+int main(int argc, char** argv) {
+  if (argc < 2) { printf("usage: probe desc|conv ...\n"); return 2; }
+  if (!strcmp(argv[1], "desc")) {
+    if (argc < 5) return 2;
+    return run_desc(atoi(argv[2]), atoi(argv[3]), atoi(argv[4]));
+  }
+  if (!strcmp(argv[1], "conv")) return run_conv(argc, argv);
+  return 2;
+}
