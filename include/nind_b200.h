@@ -1,0 +1,124 @@
+/* nind_b200.h — C ABI of the B200-native NIND denoiser hot path.
+ *
+ * Drop-in boundary for the tiled inference path of esq4/nind-denoise (paths relative to the
+ * reference tree):
+ *   - network forward        src/nind_denoise/networks/UtNet.py:97-109 (UtNet.forward)
+ *                            src/nind_denoise/networks/ThirdPartyNets.py:154-169 (UNet.forward)
+ *   - model construction     src/nind_denoise/nn_common.py:116-138 (Model.instantiate_model)
+ *   - crop grid / gather     src/nind_denoise/denoise_image.py:88-174 (OneImageDS)
+ *   - trim / seam / stitch   src/nind_denoise/denoise_image.py:204-213, 240-267
+ *
+ * Conventions: every function returns 0 on success or a negative NIND_E_* code and never throws;
+ * nind_last_error() returns a human-readable description of the most recent failure on the
+ * calling thread.  The caller owns every buffer it passes in; the library owns its packed
+ * weights and activation arena.  A handle is bound to the CUDA device that was current when it was
+ * created; it is not thread-safe, different handles are independent.  All work is enqueued on
+ * the `stream` argument (a cudaStream_t passed as void*; NULL = default stream) and is complete
+ * once that stream is synchronised — except the *_host entry point, which synchronises itself.
+ * There is no CPU fallback: without an sm_100 device every compute entry point fails.
+ */
+#ifndef NIND_B200_H
+#define NIND_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct nind_net nind_net;
+
+enum {
+  NIND_OK = 0,
+  NIND_E_INVALID = -1,     /* bad argument (illegal crop size, unknown activation, ...) */
+  NIND_E_CUDA = -2,        /* CUDA runtime / driver error */
+  NIND_E_WEIGHTS = -3,     /* missing or mis-shaped tensor in the state_dict */
+  NIND_E_KERNEL = -4,      /* a kernel reported a pipeline time-out */
+  NIND_E_UNSUPPORTED = -5  /* configuration not implemented by this build */
+};
+
+enum { NIND_ARCH_UTNET = 0, NIND_ARCH_UNET = 1 };
+enum { NIND_ACT_PRELU = 0, NIND_ACT_ELU = 1, NIND_ACT_HARDSWISH = 2 };
+
+/* One entry of a PyTorch state_dict: fp32, contiguous, host or device memory. */
+typedef struct {
+  const char* name;     /* e.g. "convs1.0.weight" (UtNet.py) / "down1.mpconv.1.conv.0.weight" (UNet) */
+  const float* data;
+  int32_t ndim;
+  int64_t shape[4];
+} nind_tensor;
+
+/* One row of the crop table (denoise_image.py:130-137,172-173). */
+typedef struct {
+  int32_t x0, y0;                       /* top-left of the cs x cs window in the image (may be < 0) */
+  int32_t ud_x0, ud_y0, ud_x1, ud_y1;   /* usefuldim inside the crop                                */
+  int32_t start_x, start_y;             /* usefulstart: position of the useful area in the image    */
+} nind_crop;
+
+/* Library / device information.  Returns 0 and fills *sm_major/minor if a CUDA device is usable. */
+int nind_device_info(int* sm_major, int* sm_minor, int* sm_count);
+
+/* Replaces: globals()[network](**parameters) + load_state_dict (nn_common.py:129-132).
+ * `arch` NIND_ARCH_*, `funit` 64 (UtNet) — ignored by UNet as in the reference
+ * (ThirdPartyNets.py:139-150) —, `activation` NIND_ACT_* (UtNet.py:17-26).
+ * Packs the fp32 tensors into the bf16 tap-major layout the kernels use (BatchNorm folded). */
+int nind_net_create(int arch, int funit, int activation, const nind_tensor* tensors, int n_tensors,
+                    nind_net** out);
+/* Re-pack after the caller changed its parameters (load_state_dict on an existing module). */
+int nind_net_load(nind_net* net, const nind_tensor* tensors, int n_tensors);
+void nind_net_destroy(nind_net* net);
+
+/* Replaces: model(ybatch) (denoise_image.py:246).  in/out: device pointers, fp32 NCHW
+ * [batch,3,h,w] contiguous.  UtNet: h and w must be 16a+56, a >= 3 (UtNet.py:6-7); UNet: multiples
+ * of 16. */
+int nind_net_forward(nind_net* net, const float* in_nchw, float* out_nchw, int batch, int h, int w,
+                     void* stream);
+
+/* Crop grid (OneImageDS.__init__/__getitem__).  Pass table = NULL to query the count. */
+int nind_crop_table(int width, int height, int cs, int ucs, int ol, nind_crop* table, int* n_crops);
+
+/* Replaces the main loop of denoise_image.py:240-267 for crops [crop_begin, crop_end) of a planar
+ * fp32 [3,height,width] device image: gather (mirror pad) -> forward in batches of `batch` crops ->
+ * trim -> seam halving -> overlap-add.  Writes the rows [*band_y0, *band_y1) those crops touch into
+ * out_band (device, planar [3, band rows, width], at least nind_band_rows() rows); pixels inside
+ * the band that belong to other crops' useful areas receive only this range's contributions
+ * (add the bands of all ranges to obtain the image). */
+int nind_tiled_denoise(nind_net* net, const float* img_chw, float* out_band, int height, int width,
+                       int cs, int ucs, int ol, int crop_begin, int crop_end, int batch,
+                       int* band_y0, int* band_y1, void* stream);
+int nind_band_rows(int width, int height, int cs, int ucs, int ol, int crop_begin, int crop_end,
+                   int* band_y0, int* band_y1);
+
+/* The two geometry halves of the loop as stand-alone ops (bit-exact copies / fp32 adds):
+ *   nind_gather_crops  = OneImageDS.__getitem__ for crops [crop_begin, crop_end)
+ *                        (denoise_image.py:129-174) -> crops_out [n,3,cs,cs] fp32 device;
+ *   nind_stitch_crops  = trim + make_seamless_edges + overlap-add (denoise_image.py:204-213,250-267)
+ *                        of network outputs crops [n,3,cs,cs] into the row band of that range. */
+int nind_gather_crops(nind_net* net, const float* img_chw, int height, int width, int cs, int ucs, int ol,
+                      int crop_begin, int crop_end, float* crops_out, void* stream);
+int nind_stitch_crops(const float* crops, int height, int width, int cs, int ucs, int ol, int crop_begin,
+                      int crop_end, float* out_band, int* band_y0, int* band_y1, void* stream);
+
+/* Whole image, host buffers (pageable or pinned): H2D, all crops, D2H, synchronised.  This is the
+ * call the reference-facing plugin makes for one image on one GPU. */
+int nind_tiled_denoise_host(nind_net* net, const float* img_chw_host, float* out_chw_host, int height,
+                            int width, int cs, int ucs, int ol, int batch);
+
+/* Number of CUDA kernels this library has launched on the calling process so far. */
+int64_t nind_kernel_launches(void);
+
+/* Per-layer device timing of the most recent nind_net_forward with timing enabled.
+ * nind_set_timing(net, 1) makes forward record one CUDA event pair per layer (adds sync). */
+int nind_set_timing(nind_net* net, int enabled);
+int nind_get_layer_times(nind_net* net, int max_layers, const char** names, float* ms, double* flops,
+                         int* n_layers);
+
+/* Tuning knobs (affect plans built afterwards): "n_tile_deep" (128|256), "max_ctas". */
+int nind_set_option(nind_net* net, const char* key, int value);
+
+const char* nind_last_error(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NIND_B200_H */

@@ -1,0 +1,227 @@
+// Memory-bound kernels around the convolutions: crop gather (+ in-network pad + first-layer
+// im2col), 2x2 max-pool, and the output-centric stitch.  All are coalesced 16-byte-vector kernels.
+#pragma once
+#include "ptx.cuh"
+
+namespace nind {
+
+// ------------------------------------------------------------------ crop gather + im2col
+// Reference: OneImageDS.__getitem__ (src/nind_denoise/denoise_image.py:129-174) builds crop i as
+//   crop[c, r, q] = img[c, sym(y0 + r, H), sym(x0 + q, W)]      (edge-INCLUSIVE mirror, np.flip)
+// and the network then pads it itself:
+//   UtNet: nn.ReflectionPad2d(2) (UtNet.py:27,98) — edge-EXCLUSIVE reflection of the crop's own pixels
+//   UNet : Conv2d(padding=1) zero padding (ThirdPartyNets.py:66)
+// This kernel fuses both with the im2col of the first 3x3 convolution (C_in = 3): for every output
+// pixel of that convolution it writes a 64-channel bf16 vector
+//   k in [0,27)  : hi part of tap element e = k       (e = (ky*3+kx)*3 + c)
+//   k in [27,54) : lo part (x - bf16(x)) of element k-27   -> the input keeps ~16 bits of mantissa
+//   k in [54,64) : 0
+// so that the first layer runs as a K=64 per-pixel GEMM on the tensor cores.
+struct GatherParams {
+  const float* src;       // planar fp32
+  long long src_img;      // floats between consecutive crops' source images (0 = one shared image)
+  long long src_plane;    // floats between colour planes
+  int src_w, src_h;       // image size
+  const int2* origin;     // per crop (x0, y0) of the crop window in the image; null = (0, 0)
+  int crop_h, crop_w;     // crop size fed to the network
+  int pad;                // in-network padding of the first conv (UtNet: 2 reflect, UNet: 1 zero)
+  int reflect;            // 1 = edge-exclusive reflection, 0 = zeros
+  int out_h, out_w;       // first-conv output size (crop + 2*pad - 2)
+  int n_crops;
+  __nv_bfloat16* dst;     // [n_crops][out_h][out_w][64]
+};
+
+__device__ __forceinline__ int sym_index(int t, int n) {
+  // edge-inclusive mirror; repeated until inside (images are far larger than the margins)
+  t = t < 0 ? -t - 1 : t;
+  t = t >= n ? 2 * n - 1 - t : t;
+  return t < 0 ? 0 : t;
+}
+
+__global__ void __launch_bounds__(256) gather_im2col_kernel(const GatherParams p) {
+  const long long total = (long long)p.n_crops * p.out_h * p.out_w * 8;
+  for (long long gid = blockIdx.x * (long long)blockDim.x + threadIdx.x; gid < total;
+       gid += (long long)gridDim.x * blockDim.x) {
+    const int j = (int)(gid & 7);
+    long long pix = gid >> 3;
+    const int x = (int)(pix % p.out_w);
+    pix /= p.out_w;
+    const int y = (int)(pix % p.out_h);
+    const int b = (int)(pix / p.out_h);
+    int x0 = 0, y0 = 0;
+    if (p.origin) {
+      const int2 o = p.origin[b];
+      x0 = o.x;
+      y0 = o.y;
+    }
+    const float* img = p.src + b * p.src_img;
+    float v[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int k = 8 * j + i;
+      float val = 0.f;
+      if (k < 54) {
+        const int e = k < 27 ? k : k - 27;
+        const int t = e / 3, c = e - 3 * t;
+        const int ky = t / 3, kx = t - 3 * ky;
+        int r = y + ky - p.pad, q = x + kx - p.pad;  // crop coordinates
+        bool inside = true;
+        if (p.reflect) {
+          r = r < 0 ? -r : (r >= p.crop_h ? 2 * p.crop_h - 2 - r : r);
+          q = q < 0 ? -q : (q >= p.crop_w ? 2 * p.crop_w - 2 - q : q);
+        } else {
+          inside = r >= 0 && r < p.crop_h && q >= 0 && q < p.crop_w;
+        }
+        if (inside) {
+          const int iy = sym_index(y0 + r, p.src_h), ix = sym_index(x0 + q, p.src_w);
+          const float f = __ldg(img + c * p.src_plane + (long long)iy * p.src_w + ix);
+          const float hi = __bfloat162float(__float2bfloat16_rn(f));
+          val = k < 27 ? hi : f - hi;
+        }
+      }
+      v[i] = val;
+    }
+    uint4 o;
+    o.x = pack_bf16x2(v[0], v[1]);
+    o.y = pack_bf16x2(v[2], v[3]);
+    o.z = pack_bf16x2(v[4], v[5]);
+    o.w = pack_bf16x2(v[6], v[7]);
+    reinterpret_cast<uint4*>(p.dst)[gid] = o;
+  }
+}
+
+// ------------------------------------------------------------------ 2x2 max-pool (NHWC bf16)
+// nn.MaxPool2d(2) (UtNet.py:34, ThirdPartyNets.py:93).  `in`/`out` are already offset to the first
+// interior pixel and the channel sub-range; strides in elements.
+struct PoolParams {
+  const __nv_bfloat16* in;
+  long long i_img, i_row;
+  int i_pix;
+  __nv_bfloat16* out;
+  long long o_img, o_row;
+  int o_pix;
+  int n, ho, wo, c;  // c multiple of 8
+};
+
+__global__ void __launch_bounds__(256) maxpool2_kernel(const PoolParams p) {
+  const int c8 = p.c >> 3;
+  const long long total = (long long)p.n * p.ho * p.wo * c8;
+  for (long long gid = blockIdx.x * (long long)blockDim.x + threadIdx.x; gid < total;
+       gid += (long long)gridDim.x * blockDim.x) {
+    const int cc = (int)(gid % c8);
+    long long r = gid / c8;
+    const int xo = (int)(r % p.wo);
+    r /= p.wo;
+    const int yo = (int)(r % p.ho);
+    const int b = (int)(r / p.ho);
+    const __nv_bfloat16* ip = p.in + b * p.i_img + (long long)(2 * yo) * p.i_row + (long long)(2 * xo) * p.i_pix + cc * 8;
+    const uint4 a = *reinterpret_cast<const uint4*>(ip);
+    const uint4 bq = *reinterpret_cast<const uint4*>(ip + p.i_pix);
+    const uint4 cq = *reinterpret_cast<const uint4*>(ip + p.i_row);
+    const uint4 dq = *reinterpret_cast<const uint4*>(ip + p.i_row + p.i_pix);
+    uint4 o;
+    const __nv_bfloat162* pa = reinterpret_cast<const __nv_bfloat162*>(&a);
+    const __nv_bfloat162* pb = reinterpret_cast<const __nv_bfloat162*>(&bq);
+    const __nv_bfloat162* pc = reinterpret_cast<const __nv_bfloat162*>(&cq);
+    const __nv_bfloat162* pd = reinterpret_cast<const __nv_bfloat162*>(&dq);
+    __nv_bfloat162* po = reinterpret_cast<__nv_bfloat162*>(&o);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) po[i] = __hmax2(__hmax2(pa[i], pb[i]), __hmax2(pc[i], pd[i]));
+    *reinterpret_cast<uint4*>(p.out + b * p.o_img + (long long)yo * p.o_row + (long long)xo * p.o_pix + cc * 8) = o;
+  }
+}
+
+// ------------------------------------------------------------------ stitch
+// Output-centric restatement of trim + make_seamless_edges + overlap-add
+// (denoise_image.py:204-213, 250-267): every output pixel sums, in raster crop order, the
+// contributions  w * net_out[crop][c][pad + y - ay][pad + x - ax]  of the crops whose useful area
+// covers it, w in {1, 1/2, 1/4}.  No atomics; identical association order to the reference loop.
+struct StitchParams {
+  const float* crops;     // [crop_end - crop_begin][3][cs][cs] network outputs
+  int crop_begin, crop_end;
+  float* out;             // [3][band rows][W], band = rows [y_begin, y_end)
+  int y_begin, y_end;
+  int W, H, cs, ucs, ol, pad, stride, nx, ny;
+};
+
+__global__ void __launch_bounds__(256) stitch_kernel(const StitchParams p) {
+  const int band_h = p.y_end - p.y_begin;
+  const long long total = (long long)band_h * p.W;
+  const int wmax = p.cs - 2 * p.pad;  // widest useful area
+  for (long long gid = blockIdx.x * (long long)blockDim.x + threadIdx.x; gid < total;
+       gid += (long long)gridDim.x * blockDim.x) {
+    const int x = (int)(gid % p.W);
+    const int yb = (int)(gid / p.W);
+    const int y = yb + p.y_begin;
+    int yi_lo = (y - wmax + p.stride) / p.stride;  // ceil((y - wmax + 1) / stride) for non-negative
+    if (y - wmax + 1 <= 0) yi_lo = 0;
+    int yi_hi = y / p.stride;
+    if (yi_hi > p.ny - 1) yi_hi = p.ny - 1;
+    int xi_lo = (x - wmax + p.stride) / p.stride;
+    if (x - wmax + 1 <= 0) xi_lo = 0;
+    int xi_hi = x / p.stride;
+    if (xi_hi > p.nx - 1) xi_hi = p.nx - 1;
+    float s0 = 0.f, s1 = 0.f, s2 = 0.f;
+    for (int yi = yi_lo; yi <= yi_hi; ++yi) {
+      const int ay = p.stride * yi;
+      const int y1pad = max(0, ay - p.pad + p.cs - p.H);
+      const int hcrop = p.cs - max(p.pad, y1pad) - p.pad;
+      const int dy = y - ay;
+      if (dy >= hcrop) continue;
+      float wy = 1.f;
+      if (ay != 0 && dy < p.ol) wy *= 0.5f;
+      if (ay + p.ucs < p.H && p.ol && dy >= hcrop - p.ol) wy *= 0.5f;
+      for (int xi = xi_lo; xi <= xi_hi; ++xi) {
+        const int idx = yi * p.nx + xi;
+        if (idx < p.crop_begin || idx >= p.crop_end) continue;
+        const int ax = p.stride * xi;
+        const int x1pad = max(0, ax - p.pad + p.cs - p.W);
+        const int wcrop = p.cs - max(p.pad, x1pad) - p.pad;
+        const int dx = x - ax;
+        if (dx >= wcrop) continue;
+        float w = wy;
+        if (ax != 0 && dx < p.ol) w *= 0.5f;
+        if (ax + p.ucs < p.W && p.ol && dx >= wcrop - p.ol) w *= 0.5f;
+        const float* cp = p.crops + ((long long)(idx - p.crop_begin) * 3 * p.cs + (p.pad + dy)) * p.cs + p.pad + dx;
+        const long long plane = (long long)p.cs * p.cs;
+        s0 += w * __ldg(cp);
+        s1 += w * __ldg(cp + plane);
+        s2 += w * __ldg(cp + 2 * plane);
+      }
+    }
+    const long long oplane = (long long)band_h * p.W;
+    p.out[(long long)yb * p.W + x] = s0;
+    p.out[oplane + (long long)yb * p.W + x] = s1;
+    p.out[2 * oplane + (long long)yb * p.W + x] = s2;
+  }
+}
+
+// ------------------------------------------------------------------ plain fp32 crop gather
+// OneImageDS.__getitem__ (denoise_image.py:129-174) as a stand-alone op: crops[i][c][r][q] =
+// img[c][sym(y0+r)][sym(x0+q)], bit-exact copies.  Used by the OneImageDS mirror and the parity tests.
+struct CropGatherParams {
+  const float* src;
+  long long src_plane;
+  int src_w, src_h;
+  const int2* origin;
+  int cs, n_crops;
+  float* dst;  // [n_crops][3][cs][cs]
+};
+
+__global__ void __launch_bounds__(256) gather_crops_kernel(const CropGatherParams p) {
+  const long long total = (long long)p.n_crops * 3 * p.cs * p.cs;
+  for (long long gid = blockIdx.x * (long long)blockDim.x + threadIdx.x; gid < total;
+       gid += (long long)gridDim.x * blockDim.x) {
+    const int q = (int)(gid % p.cs);
+    long long r = gid / p.cs;
+    const int rr = (int)(r % p.cs);
+    r /= p.cs;
+    const int c = (int)(r % 3);
+    const int b = (int)(r / 3);
+    const int2 o = p.origin[b];
+    const int iy = sym_index(o.y + rr, p.src_h), ix = sym_index(o.x + q, p.src_w);
+    p.dst[gid] = __ldg(p.src + c * p.src_plane + (long long)iy * p.src_w + ix);
+  }
+}
+
+}  // namespace nind

@@ -27,7 +27,8 @@ enum EpiMode : int { EPI_STORE = 0, EPI_D2S = 1, EPI_HEAD = 2 };
 enum ActKind : int { ACT_NONE = 0, ACT_PRELU = 1, ACT_ELU = 2, ACT_HARDSWISH = 3 };
 
 constexpr int IG_MAX_STAGES = 32;
-constexpr int IG_BAR_BYTES = 2048;
+constexpr int IG_BAR_BYTES = 2048;   // mbarriers + TMEM base slot
+constexpr int IG_EPI_BYTES = 3072;   // staged bias [2][256] fp32 + head weights [3][64]+[3]
 constexpr int IG_THREADS = 256;
 constexpr int IG_TILE_H = 16;
 constexpr int IG_TILE_W = 8;
@@ -40,12 +41,7 @@ struct IgemmParams {
   // shared-memory pipeline geometry
   uint32_t a_stage_bytes;  // distance between A stages (multiple of 1024)
   uint32_t a_tx_bytes;     // bytes TMA delivers per A stage
-  uint32_t a_copy_bytes;   // a_mode 1: distance between the three kx-shifted copies
-  uint32_t a_box_bytes;    // a_mode 1: bytes of one copy
-  uint32_t a_sbo;          // byte distance between 8-row groups of the A operand
-  uint32_t tap_off[9];     // byte offset of each tap's operand inside an A stage
-  int a_mode;              // 0: one patch, row-offset descriptors; 1: three kx-shifted copies
-  int a_bo_mode;           // descriptor base_offset: 0 = zero, 1 = (addr >> 7) & 7
+  uint32_t a_sbo;          // bytes per patch row = distance between 8-row groups of the A operand
   int sa, sb, ws;          // stage counts; ws = weights stay resident in shared memory
   // output geometry
   int hs_in;               // stored rows per image of the input buffer
@@ -72,21 +68,7 @@ struct IgemmParams {
 };
 
 __host__ __device__ inline size_t igemm_smem_bytes(int n_tile, int sa, uint32_t a_stage_bytes, int sb) {
-  return 1024 + (size_t)sa * a_stage_bytes + (size_t)sb * n_tile * 128 + IG_BAR_BYTES;
-}
-
-__device__ __forceinline__ float apply_act(float v, int act, float slope) {
-  switch (act) {
-    case ACT_PRELU: return v > 0.f ? v : v * slope;
-    case ACT_ELU: return v > 0.f ? v : (__expf(v) - 1.f);
-    case ACT_HARDSWISH: return v * fminf(fmaxf(v + 3.f, 0.f), 6.f) * (1.f / 6.f);
-    default: return v;
-  }
-}
-
-__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
-  __nv_bfloat162 t = __floats2bfloat162_rn(lo, hi);
-  return *reinterpret_cast<uint32_t*>(&t);
+  return 1024 + (size_t)sa * a_stage_bytes + (size_t)sb * n_tile * 128 + IG_BAR_BYTES + IG_EPI_BYTES;
 }
 
 template <int N_TILE>
@@ -109,6 +91,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
   const uint32_t t_full = bar_base + 32 * IG_MAX_STAGES;
   const uint32_t t_empty = t_full + 16;
   const uint32_t tmem_slot = t_full + 32;
+  const uint32_t epi_base = bar_base + IG_BAR_BYTES;
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -145,87 +128,110 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
   if (warp == 0) {
     // ------------------------------------------------ activation-patch producer
     if (lane == 0) {
-      uint32_t it = 0;
+      uint32_t s = 0, ph = 0;
       for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
         const int r = tile % tiles_xy;
         const int yt = r / p.tiles_x, xt = r - yt * p.tiles_x;
-        for (int kc = 0; kc < p.kchunks; ++kc, ++it) {
-          const uint32_t s = it % p.sa, ph = (it / p.sa) & 1;
+        for (int kc = 0; kc < p.kchunks; ++kc) {
           mbar_wait(a_empty + 8 * s, ph ^ 1, p.err, 1);
           mbar_arrive_expect_tx(a_full + 8 * s, p.a_tx_bytes);
-          const uint32_t dst = a_base + s * p.a_stage_bytes;
-          if (p.a_mode == 1 && p.taps == 9) {
-            for (int kx = 0; kx < 3; ++kx)
-              tma_load_3d(dst + kx * p.a_copy_bytes, &tmA, a_full + 8 * s, kc * 64,
-                          xt * IG_TILE_W + kx, yt * IG_TILE_H);
-          } else {
-            tma_load_3d(dst, &tmA, a_full + 8 * s, kc * 64, xt * IG_TILE_W, yt * IG_TILE_H);
-          }
+          tma_load_3d(a_base + s * p.a_stage_bytes, &tmA, a_full + 8 * s, kc * 64, xt * IG_TILE_W,
+                      yt * IG_TILE_H);
+          if (++s == (uint32_t)p.sa) { s = 0; ph ^= 1; }
         }
       }
     }
   } else if (warp == 1) {
     // ------------------------------------------------ weight-tile producer
     if (lane == 0) {
-      uint32_t it = 0;
+      uint32_t s = 0, ph = 0;
       int tl = 0;
       for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++tl) {
         if (p.ws && tl > 0) break;
         const int nt = tile / tiles_xy;
         for (int kc = 0; kc < p.kchunks; ++kc) {
-          for (int t = 0; t < p.taps; ++t, ++it) {
-            const uint32_t s = it % p.sb, ph = (it / p.sb) & 1;
+          for (int t = 0; t < p.taps; ++t) {
             if (!p.ws) mbar_wait(b_empty + 8 * s, ph ^ 1, p.err, 2);
             mbar_arrive_expect_tx(b_full + 8 * s, B_BYTES);
             tma_load_2d(b_base + s * B_BYTES, &tmB, b_full + 8 * s, kc * 64,
                         t * p.n_total + nt * N_TILE);
+            if (++s == (uint32_t)p.sb) { s = 0; ph ^= 1; }
           }
         }
       }
     }
   } else if (warp == 2) {
     // ------------------------------------------------ MMA issuer
-    if (lane == 0) {
-      uint32_t ita = 0, itb = 0;
-      int tl = 0;
-      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++tl) {
-        const uint32_t acc = tl & 1, aph = (tl >> 1) & 1;
-        mbar_wait(t_empty + 8 * acc, aph ^ 1, p.err, 3);
-        tc_fence_after();
-        const uint32_t d = tmem_base + acc * N_TILE;
-        uint32_t accum = 0;
-        for (int kc = 0; kc < p.kchunks; ++kc, ++ita) {
-          const uint32_t sa_i = ita % p.sa;
-          mbar_wait(a_full + 8 * sa_i, (ita / p.sa) & 1, p.err, 4);
-          for (int t = 0; t < p.taps; ++t, ++itb) {
-            const uint32_t sb_i = itb % p.sb;
-            if (!(p.ws && tl > 0)) mbar_wait(b_full + 8 * sb_i, (itb / p.sb) & 1, p.err, 5);
+    // The whole warp walks the loop (warp-uniform control flow and addresses, so descriptors live
+    // in uniform registers); one elected lane issues tcgen05.mma / tcgen05.commit.
+    constexpr uint32_t DESC_HI_B = (1024u >> 4) | (1u << 14) | (2u << 29);
+    const uint32_t desc_hi_a = (p.a_sbo >> 4) | (1u << 14) | (2u << 29);
+    const uint32_t tap_w = p.taps == 9 ? 3u : 1u;
+    const uint32_t pitch16 = (p.a_sbo >> 4);  // one patch row, in 16-byte units
+    uint32_t sa_i = 0, pha = 0, sb_i = 0, phb = 0;
+    int tl = 0;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++tl) {
+      const uint32_t acc = tl & 1, aph = (tl >> 1) & 1;
+      mbar_wait(t_empty + 8 * acc, aph ^ 1, p.err, 3);
+      tc_fence_after();
+      const uint32_t d = tmem_base + acc * N_TILE;
+      uint32_t accum = 0;
+      for (int kc = 0; kc < p.kchunks; ++kc) {
+        mbar_wait(a_full + 8 * sa_i, pha, p.err, 4);
+        const uint32_t a_lo0 = (((a_base + sa_i * p.a_stage_bytes) >> 4) & 0x3FFF) | (1u << 16);
+        for (uint32_t ky = 0; ky < tap_w; ++ky) {
+          for (uint32_t kx = 0; kx < tap_w; ++kx) {
+            if (!(p.ws && tl > 0)) mbar_wait(b_full + 8 * sb_i, phb, p.err, 5);
             tc_fence_after();
-            const uint32_t a_addr = a_base + sa_i * p.a_stage_bytes + p.tap_off[t];
-            const uint32_t b_addr = b_base + sb_i * B_BYTES;
-            const uint32_t bo = p.a_bo_mode ? ((a_addr >> 7) & 7) : 0;
+            const uint32_t a_lo = a_lo0 + ky * pitch16 + kx * 8;  // (ky*pitch + kx) rows of 128 B
+            const uint32_t b_lo = (((b_base + sb_i * B_BYTES) >> 4) & 0x3FFF) | (1u << 16);
+            if (elect_one_sync()) {
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-              umma_bf16(d, umma_desc_sw128(a_addr + 32 * k, p.a_sbo, bo),
-                        umma_desc_sw128(b_addr + 32 * k, 1024), IDESC, accum);
-              accum = 1;
+              for (uint32_t k = 0; k < 4; ++k) {
+                umma_bf16_lohi(d, a_lo + 2 * k, desc_hi_a, b_lo + 2 * k, DESC_HI_B, IDESC, accum);
+                accum = 1;
+              }
+              if (!p.ws) umma_commit(b_empty + 8 * sb_i);
             }
-            if (!p.ws) umma_commit(b_empty + 8 * sb_i);
+            __syncwarp();
+            accum = 1;
+            if (++sb_i == (uint32_t)p.sb) { sb_i = 0; phb ^= 1; }
           }
-          umma_commit(a_empty + 8 * sa_i);
         }
-        umma_commit(t_full + 8 * acc);
+        if (elect_one_sync()) umma_commit(a_empty + 8 * sa_i);
+        __syncwarp();
+        if (++sa_i == (uint32_t)p.sa) { sa_i = 0; pha ^= 1; }
       }
+      if (elect_one_sync()) umma_commit(t_full + 8 * acc);
+      __syncwarp();
     }
   } else if (warp >= 4) {
     // ------------------------------------------------ epilogue
     const int quarter = warp & 3;
-    int tl = 0;
+    const int etid = threadIdx.x - 128;  // 0..127 among the epilogue warps
+    float* bias_s = reinterpret_cast<float*>(smem_raw + (epi_base - smem_u32(smem_raw)));  // [2][256]
+    float* head_s = bias_s + 512;                                                          // [3][64] + [3]
+    if (p.epi_mode == EPI_HEAD) {
+      for (int i = etid; i < 195; i += 128) head_s[i] = i < 192 ? __ldg(p.head_w + i) : __ldg(p.head_b + i - 192);
+    }
+    int tl = 0, prev_nt = -1, bsel = 1;
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++tl) {
       const int nt = tile / tiles_xy;
       const int r = tile % tiles_xy;
       const int yt = r / p.tiles_x, xt = r - yt * p.tiles_x;
       const uint32_t acc = tl & 1, aph = (tl >> 1) & 1;
+
+      if (nt != prev_nt) {  // (re)stage this N-tile's bias; uniform over the four epilogue warps
+        prev_nt = nt;
+        bsel ^= 1;
+        for (int i = etid; i < N_TILE; i += 128) {
+          const int n = nt * N_TILE + i;
+          float bv = 0.f;
+          if (n < p.n_total) bv = __ldg(p.bias + (p.epi_mode == EPI_D2S ? n % p.d2s_cout : n));
+          bias_s[bsel * 256 + i] = bv;
+        }
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+      }
 
       const int row = quarter * 32 + lane;
       const int yflat = yt * IG_TILE_H + (row >> 3);
@@ -246,34 +252,43 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         tmem_wait_ld();
         const int n = nt * N_TILE + c * 32;
         if (n >= p.n_total) continue;
-        int bias_idx = n;
         __nv_bfloat16* dst;
         if (p.epi_mode == EPI_D2S) {
           const int q = n / p.d2s_cout;
           const int co = n - q * p.d2s_cout;
-          bias_idx = co;
           dst = p.out + b * p.o_img + (long long)(2 * y + (q >> 1)) * p.o_row +
                 (long long)(2 * x + (q & 1)) * p.o_pix + co;
         } else {
           dst = p.out + b * p.o_img + (long long)y * p.o_row + (long long)x * p.o_pix + n;
         }
         float f[32];
-        const float4* bp = reinterpret_cast<const float4*>(p.bias + bias_idx);
+        const float4* bp = reinterpret_cast<const float4*>(bias_s + bsel * 256 + c * 32);
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-          const float4 bb = __ldg(bp + j);
-          f[4 * j + 0] = apply_act(__uint_as_float(v[4 * j + 0]) + bb.x, p.act, p.slope);
-          f[4 * j + 1] = apply_act(__uint_as_float(v[4 * j + 1]) + bb.y, p.act, p.slope);
-          f[4 * j + 2] = apply_act(__uint_as_float(v[4 * j + 2]) + bb.z, p.act, p.slope);
-          f[4 * j + 3] = apply_act(__uint_as_float(v[4 * j + 3]) + bb.w, p.act, p.slope);
+          const float4 bb = bp[j];
+          f[4 * j + 0] = __uint_as_float(v[4 * j + 0]) + bb.x;
+          f[4 * j + 1] = __uint_as_float(v[4 * j + 1]) + bb.y;
+          f[4 * j + 2] = __uint_as_float(v[4 * j + 2]) + bb.z;
+          f[4 * j + 3] = __uint_as_float(v[4 * j + 3]) + bb.w;
+        }
+        if (p.act == ACT_PRELU) {  // also ReLU (slope 0); branch-free
+          const float sl = p.slope;
+#pragma unroll
+          for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.f) + sl * fminf(f[j], 0.f);
+        } else if (p.act == ACT_ELU) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) f[j] = f[j] > 0.f ? f[j] : (__expf(f[j]) - 1.f);
+        } else if (p.act == ACT_HARDSWISH) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) f[j] = f[j] * fminf(fmaxf(f[j] + 3.f, 0.f), 6.f) * (1.f / 6.f);
         }
         if (p.epi_mode == EPI_HEAD) {
-          const float* w0 = p.head_w + n;
+          const float* w0 = head_s + n;
 #pragma unroll
           for (int j = 0; j < 32; ++j) {
-            h0 = fmaf(f[j], __ldg(w0 + j), h0);
-            h1 = fmaf(f[j], __ldg(w0 + 64 + j), h1);
-            h2 = fmaf(f[j], __ldg(w0 + 128 + j), h2);
+            h0 = fmaf(f[j], w0[j], h0);
+            h1 = fmaf(f[j], w0[64 + j], h1);
+            h2 = fmaf(f[j], w0[128 + j], h2);
           }
         } else if (valid) {
           uint4* d4 = reinterpret_cast<uint4*>(dst);
@@ -295,8 +310,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       if (p.epi_mode == EPI_HEAD) {
         const int oy = y - p.h_unpad, ox = x - p.h_unpad;
         if (valid && oy >= 0 && ox >= 0 && oy < p.h_size_y && ox < p.h_size_x) {
-          float o0 = h0 + __ldg(p.head_b + 0), o1 = h1 + __ldg(p.head_b + 1),
-                o2 = h2 + __ldg(p.head_b + 2);
+          float o0 = h0 + head_s[192], o1 = h1 + head_s[193], o2 = h2 + head_s[194];
           if (p.head_sigmoid) {
             o0 = 1.f / (1.f + __expf(-o0));
             o1 = 1.f / (1.f + __expf(-o1));

@@ -32,8 +32,7 @@ struct ConvSpec {
   const float* head_b = nullptr;
   float* head_out = nullptr;  // [B][3][hy][hx] fp32
   int head_unpad = 0, head_hy = 0, head_hx = 0, head_sigmoid = 0;
-  // tuning / probing
-  int a_mode = 0, a_bo_mode = 0;
+  // tuning
   int n_tile = 0;     // 0 = auto
   int force_ws = -1;  // -1 = auto
   int max_ctas = 0;   // 0 = number of SMs
@@ -141,27 +140,20 @@ inline bool build_igemm(const ConvSpec& s, IgemmLaunch* L, std::string* why) {
   p.total_tiles = p.tiles_x * p.tiles_y * p.tiles_n;
   p.kchunks = s.cin / 64;
   p.taps = s.taps;
-  p.a_mode = s.taps == 9 ? s.a_mode : 0;
-  p.a_bo_mode = s.a_bo_mode;
 
+  // A operand: one TMA box per (tile, 64-channel chunk).  3x3: the (16+2) x (8+2) pixel patch, whose
+  // nine tap views are descriptor offsets (verified on B200: the UMMA 128B-swizzle XOR is applied to
+  // absolute shared-memory address bits, so a start address moved by whole 128-byte rows is legal).
   uint32_t boxA[3];
   if (s.taps == 1) {
     boxA[0] = 64; boxA[1] = 8; boxA[2] = 16;
     p.a_tx_bytes = 16384; p.a_stage_bytes = 16384; p.a_sbo = 1024;
-    p.tap_off[0] = 0;
-  } else if (p.a_mode == 0) {
+  } else {
     boxA[0] = 64; boxA[1] = 10; boxA[2] = 18;
     p.a_tx_bytes = 10 * 18 * 128; p.a_stage_bytes = 23552; p.a_sbo = 1280;
-    for (int t = 0; t < 9; ++t) p.tap_off[t] = ((t / 3) * 10 + (t % 3)) * 128;
-  } else {
-    boxA[0] = 64; boxA[1] = 8; boxA[2] = 18;
-    p.a_box_bytes = 8 * 18 * 128; p.a_copy_bytes = 8 * 18 * 128;
-    p.a_tx_bytes = 3 * p.a_box_bytes; p.a_stage_bytes = 3 * p.a_copy_bytes; p.a_sbo = 1024;
-    for (int t = 0; t < 9; ++t) p.tap_off[t] = (t % 3) * p.a_copy_bytes + (t / 3) * 8 * 128;
   }
 
   // pipeline depth / weights-stationary decision
-  const uint32_t b_bytes = n_tile * 128;
   const int kt = p.kchunks * p.taps;
   bool ws = false;
   if (s.force_ws != 0 && p.tiles_n == 1 && kt <= IG_MAX_STAGES &&

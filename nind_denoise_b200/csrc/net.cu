@@ -1,0 +1,880 @@
+// C ABI (include/nind_b200.h): weight packing, per-shape execution plans, tiled denoise driver.
+//
+// Reference being replaced (paths relative to /root/reference):
+//   networks/UtNet.py:14-109, networks/ThirdPartyNets.py:62-169   network definitions
+//   nn_common.py:116-138                                           factory + load_state_dict
+//   denoise_image.py:88-174, 204-213, 240-267                      crop grid, gather, stitch
+#include <atomic>
+#include <cmath>
+#include <map>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "../../include/nind_b200.h"
+#include "aux.cuh"
+#include "igemm_host.cuh"
+
+using namespace nind;
+
+namespace {
+
+thread_local std::string g_err;
+std::atomic<int64_t> g_launches{0};
+
+int fail(int code, const std::string& m) {
+  g_err = m;
+  return code;
+}
+#define CUDA_TRY(x)                                                                          \
+  do {                                                                                       \
+    cudaError_t e_ = (x);                                                                    \
+    if (e_ != cudaSuccess) return fail(NIND_E_CUDA, std::string(#x) + ": " + cudaGetErrorString(e_)); \
+  } while (0)
+
+struct PackedLayer {
+  int taps = 9, cin = 0, n_total = 0, cout = 0;
+  __nv_bfloat16* w = nullptr;  // device [taps][n_total][cin]
+  float* bias = nullptr;       // device
+  int act = ACT_NONE;
+  float slope = 0.f;
+};
+
+enum StepKind { STEP_GATHER = 0, STEP_IGEMM = 1, STEP_POOL = 2 };
+
+struct Step {
+  int kind = STEP_IGEMM;
+  std::string name;
+  IgemmLaunch ig;
+  GatherParams g;
+  PoolParams pl;
+  double flops = 0;
+  double bytes = 0;  // algorithmic bytes moved (memory-bound steps)
+};
+
+struct Plan {
+  int b = 0, h = 0, w = 0;
+  std::vector<void*> bufs;
+  std::vector<Step> steps;
+  int gather_step = -1, head_step = -1;
+  ~Plan() {
+    for (void* p : bufs) cudaFree(p);
+  }
+};
+
+struct GridGeom {
+  int W, H, cs, ucs, ol, pad, stride, nx, ny;
+  int size() const { return nx * ny; }
+};
+
+// denoise_image.py:100-104.  All integer; ceil of a quotient of ints done exactly.
+bool make_grid(int W, int H, int cs, int ucs, int ol, GridGeom* g) {
+  if (W <= 0 || H <= 0 || cs <= 0 || ucs <= 0 || ol < 0 || ucs > cs || ucs - ol <= 0) return false;
+  g->W = W; g->H = H; g->cs = cs; g->ucs = ucs; g->ol = ol;
+  g->stride = ucs - ol;
+  g->pad = (cs - ucs) / 2;
+  auto ceil_div = [](int a, int b) { return a >= 0 ? (a + b - 1) / b : -((-a) / b); };
+  g->nx = ceil_div(W - ucs, g->stride) + 1;
+  g->ny = ceil_div(H - ucs, g->stride) + 1;
+  return g->nx >= 1 && g->ny >= 1;
+}
+
+void crop_entry(const GridGeom& g, int i, nind_crop* c) {
+  const int yi = i / g.nx, xi = i - yi * g.nx;
+  const int x0 = g.stride * xi - g.pad, y0 = g.stride * yi - g.pad;
+  const int x1pad = std::max(0, x0 + g.cs - g.W), y1pad = std::max(0, y0 + g.cs - g.H);
+  c->x0 = x0; c->y0 = y0;
+  c->ud_x0 = g.pad; c->ud_y0 = g.pad;
+  c->ud_x1 = g.cs - std::max(g.pad, x1pad);
+  c->ud_y1 = g.cs - std::max(g.pad, y1pad);
+  c->start_x = x0 + g.pad; c->start_y = y0 + g.pad;
+}
+
+void band_of(const GridGeom& g, int cb, int ce, int* y0, int* y1) {
+  nind_crop a, b;
+  crop_entry(g, cb, &a);
+  crop_entry(g, ce - 1, &b);
+  *y0 = a.start_y;
+  *y1 = std::min(g.H, b.start_y + (b.ud_y1 - b.ud_y0));
+}
+
+}  // namespace
+
+struct nind_net {
+  int arch = 0, funit = 64, act_kind = ACT_PRELU, device = 0;
+  std::map<std::string, PackedLayer> layers;
+  float* head_w = nullptr;
+  float* head_b = nullptr;
+  int* err_flag = nullptr;
+  std::map<std::vector<int>, std::unique_ptr<Plan>> plans;
+  // tiled driver scratch
+  float* crops_buf = nullptr;
+  size_t crops_cap = 0;
+  int2* origin_buf = nullptr;
+  size_t origin_cap = 0;
+  float* img_dev = nullptr;
+  float* out_dev = nullptr;
+  size_t img_cap = 0, out_cap = 0;
+  // options
+  int n_tile_deep = 256, max_ctas = 0;
+  // timing
+  int timing = 0;
+  std::vector<std::string> t_names;
+  std::vector<float> t_ms;
+  std::vector<double> t_flops;
+
+  void free_layers() {
+    for (auto& kv : layers) {
+      cudaFree(kv.second.w);
+      cudaFree(kv.second.bias);
+    }
+    layers.clear();
+    cudaFree(head_w);
+    cudaFree(head_b);
+    head_w = head_b = nullptr;
+  }
+  ~nind_net() {
+    plans.clear();
+    free_layers();
+    cudaFree(err_flag);
+    cudaFree(crops_buf);
+    cudaFree(origin_buf);
+    cudaFree(img_dev);
+    cudaFree(out_dev);
+  }
+};
+
+namespace {
+
+// ------------------------------------------------------------------ state_dict access
+struct HostTensor {
+  std::vector<float> v;
+  std::vector<int64_t> shape;
+};
+
+int fetch(const nind_tensor* ts, int n, const std::string& name, const std::vector<int64_t>& want,
+          HostTensor* out) {
+  for (int i = 0; i < n; ++i) {
+    if (name != ts[i].name) continue;
+    size_t count = 1;
+    std::vector<int64_t> shp(ts[i].shape, ts[i].shape + ts[i].ndim);
+    for (auto d : shp) count *= (size_t)d;
+    if (!want.empty() && shp != want) {
+      std::string m = "tensor " + name + " has shape [";
+      for (auto d : shp) m += std::to_string(d) + ",";
+      m += "] expected [";
+      for (auto d : want) m += std::to_string(d) + ",";
+      return fail(NIND_E_WEIGHTS, m + "]");
+    }
+    out->v.resize(count);
+    out->shape = shp;
+    CUDA_TRY(cudaMemcpy(out->v.data(), ts[i].data, count * sizeof(float), cudaMemcpyDefault));
+    return 0;
+  }
+  return fail(NIND_E_WEIGHTS, "state_dict has no tensor named " + name);
+}
+
+int upload_layer(nind_net* net, const std::string& name, PackedLayer& L, const std::vector<__nv_bfloat16>& w,
+                 const std::vector<float>& bias) {
+  CUDA_TRY(cudaMalloc(&L.w, w.size() * sizeof(__nv_bfloat16)));
+  CUDA_TRY(cudaMemcpy(L.w, w.data(), w.size() * sizeof(__nv_bfloat16), cudaMemcpyHostToDevice));
+  CUDA_TRY(cudaMalloc(&L.bias, bias.size() * sizeof(float)));
+  CUDA_TRY(cudaMemcpy(L.bias, bias.data(), bias.size() * sizeof(float), cudaMemcpyHostToDevice));
+  net->layers[name] = L;
+  return 0;
+}
+
+// Conv2d weight [co][ci][3][3] (optionally scaled per co) -> [t][co][ci]
+void pack_conv3(const float* w, int co, int ci, const float* scale, std::vector<__nv_bfloat16>* out) {
+  out->assign((size_t)9 * co * ci, __float2bfloat16(0.f));
+  for (int o = 0; o < co; ++o)
+    for (int i = 0; i < ci; ++i)
+      for (int t = 0; t < 9; ++t) {
+        float v = w[((size_t)o * ci + i) * 9 + t];
+        if (scale) v *= scale[o];
+        (*out)[((size_t)t * co + o) * ci + i] = __float2bfloat16(v);
+      }
+}
+// ConvTranspose2d(k=3,s=1) weight [ci][co][3][3] == conv over the 2-padded input with flipped taps.
+void pack_tconv3(const float* w, int ci, int co, std::vector<__nv_bfloat16>* out) {
+  out->assign((size_t)9 * co * ci, __float2bfloat16(0.f));
+  for (int i = 0; i < ci; ++i)
+    for (int o = 0; o < co; ++o)
+      for (int ky = 0; ky < 3; ++ky)
+        for (int kx = 0; kx < 3; ++kx) {
+          const float v = w[(((size_t)i * co + o) * 3 + (2 - ky)) * 3 + (2 - kx)];
+          (*out)[((size_t)(ky * 3 + kx) * co + o) * ci + i] = __float2bfloat16(v);
+        }
+}
+// ConvTranspose2d(k=2,s=2) weight [ci][co][2][2] -> per-pixel GEMM [(dy*2+dx)*co + o][ci]
+void pack_up2(const float* w, int ci, int co, std::vector<__nv_bfloat16>* out) {
+  out->assign((size_t)4 * co * ci, __float2bfloat16(0.f));
+  for (int i = 0; i < ci; ++i)
+    for (int o = 0; o < co; ++o)
+      for (int q = 0; q < 4; ++q)
+        (*out)[((size_t)q * co + o) * ci + i] = __float2bfloat16(w[((size_t)i * co + o) * 4 + q]);
+}
+// First conv [co][3][3][3] -> [co][64]: k<27 hi taps, 27..53 the same weights for the lo parts.
+void pack_first(const float* w, int co, const float* scale, std::vector<__nv_bfloat16>* out) {
+  out->assign((size_t)co * 64, __float2bfloat16(0.f));
+  for (int o = 0; o < co; ++o)
+    for (int e = 0; e < 27; ++e) {
+      const int t = e / 3, c = e % 3;
+      float v = w[((size_t)o * 3 + c) * 9 + t];
+      if (scale) v *= scale[o];
+      (*out)[(size_t)o * 64 + e] = __float2bfloat16(v);
+      (*out)[(size_t)o * 64 + 27 + e] = __float2bfloat16(v);
+    }
+}
+
+int load_head(nind_net* net, const nind_tensor* ts, int n, const std::string& name) {
+  HostTensor w, b;
+  int rc;
+  if ((rc = fetch(ts, n, name + ".weight", {3, 64, 1, 1}, &w))) return rc;
+  if ((rc = fetch(ts, n, name + ".bias", {3}, &b))) return rc;
+  CUDA_TRY(cudaMalloc(&net->head_w, 3 * 64 * sizeof(float)));
+  CUDA_TRY(cudaMalloc(&net->head_b, 3 * sizeof(float)));
+  CUDA_TRY(cudaMemcpy(net->head_w, w.v.data(), 3 * 64 * sizeof(float), cudaMemcpyHostToDevice));
+  CUDA_TRY(cudaMemcpy(net->head_b, b.v.data(), 3 * sizeof(float), cudaMemcpyHostToDevice));
+  return 0;
+}
+
+int load_utnet(nind_net* net, const nind_tensor* ts, int n) {
+  const int f = net->funit;
+  if (f != 64) return fail(NIND_E_UNSUPPORTED, "UtNet: this build supports funit=64 only");
+  int rc;
+  auto act_of = [&](const std::string& act_name, PackedLayer* L) -> int {
+    L->act = net->act_kind;
+    L->slope = 0.f;
+    if (net->act_kind == ACT_PRELU) {
+      HostTensor s;
+      int r = fetch(ts, n, act_name + ".weight", {1}, &s);
+      if (r) return r;
+      L->slope = s.v[0];
+    }
+    return 0;
+  };
+  auto conv = [&](const std::string& name, const std::string& act_name, int ci, int co, bool transposed) -> int {
+    HostTensor w, b;
+    std::vector<int64_t> shp = transposed ? std::vector<int64_t>{ci, co, 3, 3} : std::vector<int64_t>{co, ci, 3, 3};
+    if ((rc = fetch(ts, n, name + ".weight", shp, &w))) return rc;
+    if ((rc = fetch(ts, n, name + ".bias", {co}, &b))) return rc;
+    PackedLayer L;
+    L.cin = ci; L.cout = co; L.n_total = co; L.taps = 9;
+    if ((rc = act_of(act_name, &L))) return rc;
+    std::vector<__nv_bfloat16> pw;
+    if (transposed) pack_tconv3(w.v.data(), ci, co, &pw);
+    else pack_conv3(w.v.data(), co, ci, nullptr, &pw);
+    return upload_layer(net, name, L, pw, b.v);
+  };
+  // first layer: 3 -> f as a K=64 per-pixel GEMM over the im2col'ed input
+  {
+    HostTensor w, b;
+    if ((rc = fetch(ts, n, "convs1.0.weight", {f, 3, 3, 3}, &w))) return rc;
+    if ((rc = fetch(ts, n, "convs1.0.bias", {f}, &b))) return rc;
+    PackedLayer L;
+    L.cin = 64; L.cout = f; L.n_total = f; L.taps = 1;
+    if ((rc = act_of("convs1.1", &L))) return rc;
+    std::vector<__nv_bfloat16> pw;
+    pack_first(w.v.data(), f, nullptr, &pw);
+    if ((rc = upload_layer(net, "convs1.0", L, pw, b.v))) return rc;
+  }
+  if ((rc = conv("convs1.2", "convs1.3", f, f, false))) return rc;
+  int c = f;
+  for (int lvl = 2; lvl <= 4; ++lvl) {
+    const std::string p = "convs" + std::to_string(lvl);
+    if ((rc = conv(p + ".0", p + ".1", c, 2 * c, false))) return rc;
+    if ((rc = conv(p + ".2", p + ".3", 2 * c, 2 * c, false))) return rc;
+    c *= 2;
+  }
+  if ((rc = conv("bottom.0", "bottom.1", 8 * f, 16 * f, false))) return rc;
+  if ((rc = conv("bottom.2", "bottom.3", 16 * f, 16 * f, true))) return rc;
+  int width = 16 * f;
+  for (int lvl = 1; lvl <= 4; ++lvl) {
+    const int half = width / 2;
+    const std::string up = "up" + std::to_string(lvl), tc = "tconvs" + std::to_string(lvl);
+    HostTensor w, b;
+    if ((rc = fetch(ts, n, up + ".weight", {width, half, 2, 2}, &w))) return rc;
+    if ((rc = fetch(ts, n, up + ".bias", {half}, &b))) return rc;
+    PackedLayer L;
+    L.cin = width; L.cout = half; L.n_total = 4 * half; L.taps = 1; L.act = ACT_NONE;
+    std::vector<__nv_bfloat16> pw;
+    pack_up2(w.v.data(), width, half, &pw);
+    if ((rc = upload_layer(net, up, L, pw, b.v))) return rc;
+    if ((rc = conv(tc + ".0", tc + ".1", width, half, true))) return rc;
+    if ((rc = conv(tc + ".2", tc + ".3", half, half, true))) return rc;
+    width = half;
+  }
+  return load_head(net, ts, n, "tconvs4.4");
+}
+
+int load_unet(nind_net* net, const nind_tensor* ts, int n) {
+  int rc;
+  // conv3x3(pad 1) + BatchNorm(eval) + ReLU, BN folded: w' = w*g/sqrt(var+eps), b' = (b-mean)*g/sqrt(var+eps)+beta
+  auto conv_bn = [&](const std::string& conv_name, const std::string& bn_name, int ci, int co, bool first) -> int {
+    HostTensor w, b, g, beta, mean, var;
+    if ((rc = fetch(ts, n, conv_name + ".weight", {co, ci, 3, 3}, &w))) return rc;
+    if ((rc = fetch(ts, n, conv_name + ".bias", {co}, &b))) return rc;
+    if ((rc = fetch(ts, n, bn_name + ".weight", {co}, &g))) return rc;
+    if ((rc = fetch(ts, n, bn_name + ".bias", {co}, &beta))) return rc;
+    if ((rc = fetch(ts, n, bn_name + ".running_mean", {co}, &mean))) return rc;
+    if ((rc = fetch(ts, n, bn_name + ".running_var", {co}, &var))) return rc;
+    std::vector<float> scale(co), bias(co);
+    for (int o = 0; o < co; ++o) {
+      scale[o] = g.v[o] / std::sqrt(var.v[o] + 1e-5f);
+      bias[o] = (b.v[o] - mean.v[o]) * scale[o] + beta.v[o];
+    }
+    PackedLayer L;
+    L.cout = co; L.n_total = co; L.act = ACT_PRELU; L.slope = 0.f;  // ReLU
+    std::vector<__nv_bfloat16> pw;
+    if (first) {
+      L.cin = 64; L.taps = 1;
+      pack_first(w.v.data(), co, scale.data(), &pw);
+    } else {
+      L.cin = ci; L.taps = 9;
+      pack_conv3(w.v.data(), co, ci, scale.data(), &pw);
+    }
+    return upload_layer(net, conv_name, L, pw, bias);
+  };
+  auto dconv = [&](const std::string& p, int ci, int co, bool first) -> int {
+    if ((rc = conv_bn(p + ".0", p + ".1", ci, co, first))) return rc;
+    return conv_bn(p + ".3", p + ".4", co, co, false);
+  };
+  if ((rc = dconv("inc.conv.conv", 3, 64, true))) return rc;
+  const int dn[4][2] = {{64, 128}, {128, 256}, {256, 512}, {512, 512}};
+  for (int i = 0; i < 4; ++i)
+    if ((rc = dconv("down" + std::to_string(i + 1) + ".mpconv.1.conv", dn[i][0], dn[i][1], false))) return rc;
+  const int upc[4][2] = {{1024, 256}, {512, 128}, {256, 64}, {128, 64}};
+  for (int i = 0; i < 4; ++i) {
+    const std::string p = "up" + std::to_string(i + 1);
+    const int half = upc[i][0] / 2;
+    HostTensor w, b;
+    if ((rc = fetch(ts, n, p + ".up.weight", {half, half, 2, 2}, &w))) return rc;
+    if ((rc = fetch(ts, n, p + ".up.bias", {half}, &b))) return rc;
+    PackedLayer L;
+    L.cin = half; L.cout = half; L.n_total = 4 * half; L.taps = 1; L.act = ACT_NONE;
+    std::vector<__nv_bfloat16> pw;
+    pack_up2(w.v.data(), half, half, &pw);
+    if ((rc = upload_layer(net, p + ".up", L, pw, b.v))) return rc;
+    if ((rc = dconv(p + ".conv.conv", upc[i][0], upc[i][1], false))) return rc;
+  }
+  return load_head(net, ts, n, "outc.conv");
+}
+
+int load_weights(nind_net* net, const nind_tensor* ts, int n) {
+  net->plans.clear();  // plans hold pointers into the old weights
+  net->free_layers();
+  return net->arch == NIND_ARCH_UTNET ? load_utnet(net, ts, n) : load_unet(net, ts, n);
+}
+
+// ------------------------------------------------------------------ plans
+struct PlanBuilder {
+  nind_net* net;
+  Plan* plan;
+  int rc = 0;
+
+  ActBuf alloc(int b, int hs, int ws, int c) {
+    ActBuf a;
+    a.b = b; a.hs = hs; a.ws = ws; a.c = c;
+    if (rc) return a;
+    void* p = nullptr;
+    cudaError_t e = cudaMalloc(&p, a.elems() * sizeof(__nv_bfloat16));
+    if (e == cudaSuccess) e = cudaMemset(p, 0, a.elems() * sizeof(__nv_bfloat16));
+    if (e != cudaSuccess) {
+      rc = fail(NIND_E_CUDA, std::string("activation arena: ") + cudaGetErrorString(e));
+      if (p) cudaFree(p);
+      return a;
+    }
+    plan->bufs.push_back(p);
+    a.ptr = static_cast<__nv_bfloat16*>(p);
+    return a;
+  }
+
+  // 3x3 / 1x1 layer writing bf16 (EPI_STORE or EPI_D2S)
+  void conv(const std::string& name, const ActBuf& in, int in_coff, const ActBuf& out, int out_coff,
+            int out_halo, int epi) {
+    if (rc) return;
+    auto it = net->layers.find(name);
+    if (it == net->layers.end()) { rc = fail(NIND_E_WEIGHTS, "layer not loaded: " + name); return; }
+    const PackedLayer& L = it->second;
+    ConvSpec s;
+    s.in = in; s.in_coff = in_coff; s.cin = L.cin; s.taps = L.taps; s.w = L.w; s.n_total = L.n_total;
+    s.bias = L.bias; s.act = L.act; s.slope = L.slope; s.epi_mode = epi;
+    s.out = out; s.out_coff = out_coff; s.out_halo = out_halo; s.d2s_cout = L.cout;
+    s.max_ctas = net->max_ctas;
+    if (L.n_total >= 256) s.n_tile = net->n_tile_deep;
+    Step st;
+    st.kind = STEP_IGEMM; st.name = name;
+    std::string why;
+    if (!build_igemm(s, &st.ig, &why)) { rc = fail(NIND_E_INVALID, name + ": " + why); return; }
+    st.flops = st.ig.flops;
+    plan->steps.push_back(st);
+  }
+
+  void head(const std::string& name, const ActBuf& in, int unpad, int hy, int hx, int sigmoid) {
+    if (rc) return;
+    auto it = net->layers.find(name);
+    if (it == net->layers.end()) { rc = fail(NIND_E_WEIGHTS, "layer not loaded: " + name); return; }
+    const PackedLayer& L = it->second;
+    ConvSpec s;
+    s.in = in; s.cin = L.cin; s.taps = L.taps; s.w = L.w; s.n_total = L.n_total;
+    s.bias = L.bias; s.act = L.act; s.slope = L.slope; s.epi_mode = EPI_HEAD;
+    s.head_w = net->head_w; s.head_b = net->head_b; s.head_out = nullptr;
+    s.head_unpad = unpad; s.head_hy = hy; s.head_hx = hx; s.head_sigmoid = sigmoid;
+    s.max_ctas = net->max_ctas;
+    Step st;
+    st.kind = STEP_IGEMM; st.name = name + "+head";
+    std::string why;
+    if (!build_igemm(s, &st.ig, &why)) { rc = fail(NIND_E_INVALID, name + ": " + why); return; }
+    st.flops = st.ig.flops + 2.0 * in.b * hy * hx * 64 * 3;
+    plan->head_step = (int)plan->steps.size();
+    plan->steps.push_back(st);
+  }
+
+  // 2x2 max-pool of channels [coff, coff+c) of the interior of `in` (halo hi) into the interior of out.
+  void pool(const std::string& name, const ActBuf& in, int hi, int coff, int c, const ActBuf& out, int ho) {
+    if (rc) return;
+    Step st;
+    st.kind = STEP_POOL; st.name = name;
+    PoolParams& p = st.pl;
+    p.i_pix = in.c; p.i_row = (long long)in.ws * in.c; p.i_img = (long long)in.hs * p.i_row;
+    p.in = in.ptr + hi * p.i_row + (long long)hi * p.i_pix + coff;
+    p.o_pix = out.c; p.o_row = (long long)out.ws * out.c; p.o_img = (long long)out.hs * p.o_row;
+    p.out = out.ptr + ho * p.o_row + (long long)ho * p.o_pix;
+    p.n = in.b; p.ho = out.hs - 2 * ho; p.wo = out.ws - 2 * ho; p.c = c;
+    st.bytes = (double)in.b * p.ho * p.wo * c * 2 * 5;
+    plan->steps.push_back(st);
+  }
+
+  void gather(const ActBuf& x0, int crop_h, int crop_w, int pad, int reflect) {
+    if (rc) return;
+    Step st;
+    st.kind = STEP_GATHER; st.name = "gather+im2col";
+    GatherParams& g = st.g;
+    memset(&g, 0, sizeof g);
+    g.crop_h = crop_h; g.crop_w = crop_w; g.pad = pad; g.reflect = reflect;
+    g.out_h = x0.hs; g.out_w = x0.ws; g.n_crops = x0.b; g.dst = x0.ptr;
+    st.bytes = (double)x0.b * (3.0 * crop_h * crop_w * 4 + (double)x0.hs * x0.ws * 128);
+    plan->gather_step = (int)plan->steps.size();
+    plan->steps.push_back(st);
+  }
+};
+
+bool utnet_legal(int s) { return s >= 104 && (s - 56) % 16 == 0; }
+
+int build_utnet_plan(nind_net* net, Plan* plan, int B, int H, int W) {
+  if (!utnet_legal(H) || !utnet_legal(W))
+    return fail(NIND_E_INVALID, "UtNet: crop height/width must be 16a+56 with a>=3 (e.g. 120, 248, 504); got " +
+                                    std::to_string(H) + "x" + std::to_string(W));
+  PlanBuilder pb{net, plan};
+  const int f = net->funit;
+  // spatial sizes per level (h, w): e = encoder output, p = pooled
+  int eh[5], ew[5], ph[5], pw[5];
+  eh[1] = H; ew[1] = W;
+  for (int l = 1; l <= 4; ++l) {
+    ph[l] = eh[l] / 2; pw[l] = ew[l] / 2;
+    if (l < 4) { eh[l + 1] = ph[l] - 4; ew[l + 1] = pw[l] - 4; }
+  }
+  // encoder
+  ActBuf x0 = pb.alloc(B, H + 2, W + 2, 64);
+  pb.gather(x0, H, W, 2, 1);
+  ActBuf cat[5];
+  ActBuf cur;  // input of the level's first conv
+  for (int l = 1; l <= 4; ++l) {
+    const int c = f << (l - 1);
+    const std::string p = "convs" + std::to_string(l);
+    ActBuf a = pb.alloc(B, eh[l] + 2, ew[l] + 2, c);
+    if (l == 1) pb.conv(p + ".0", x0, 0, a, 0, 0, EPI_STORE);
+    else pb.conv(p + ".0", cur, 0, a, 0, 0, EPI_STORE);
+    cat[l] = pb.alloc(B, eh[l] + 4, ew[l] + 4, 2 * c);  // [up | skip], 2-px zero frame for the ConvT
+    pb.conv(p + ".2", a, 0, cat[l], c, 2, EPI_STORE);
+    cur = pb.alloc(B, ph[l], pw[l], c);
+    pb.pool("maxpool" + std::to_string(l), cat[l], 2, c, c, cur, 0);
+  }
+  // bottom
+  ActBuf bt0 = pb.alloc(B, ph[4] - 2 + 4, pw[4] - 2 + 4, 16 * f);
+  pb.conv("bottom.0", cur, 0, bt0, 0, 2, EPI_STORE);
+  ActBuf dec = pb.alloc(B, ph[4], pw[4], 16 * f);
+  pb.conv("bottom.2", bt0, 0, dec, 0, 0, EPI_STORE);
+  // decoder
+  for (int lvl = 1; lvl <= 4; ++lvl) {
+    const int l = 5 - lvl;            // encoder level whose skip is concatenated
+    const int c = f << (l - 1);       // channels after this decoder level
+    const std::string tc = "tconvs" + std::to_string(lvl);
+    pb.conv("up" + std::to_string(lvl), dec, 0, cat[l], 0, 2, EPI_D2S);
+    ActBuf t = pb.alloc(B, eh[l] + 2 + 4, ew[l] + 2 + 4, c);
+    pb.conv(tc + ".0", cat[l], 0, t, 0, 2, EPI_STORE);
+    if (lvl < 4) {
+      dec = pb.alloc(B, eh[l] + 4, ew[l] + 4, c);
+      pb.conv(tc + ".2", t, 0, dec, 0, 0, EPI_STORE);
+    } else {
+      pb.head(tc + ".2", t, 2, H, W, 0);
+    }
+  }
+  return pb.rc;
+}
+
+int build_unet_plan(nind_net* net, Plan* plan, int B, int H, int W) {
+  if (H % 16 || W % 16 || H < 32 || W < 32)
+    return fail(NIND_E_INVALID, "UNet: this build needs crop height/width multiples of 16 (>= 32); got " +
+                                    std::to_string(H) + "x" + std::to_string(W));
+  PlanBuilder pb{net, plan};
+  // level l (0..4) spatial size
+  int sh[5], sw[5];
+  for (int l = 0; l < 5; ++l) { sh[l] = H >> l; sw[l] = W >> l; }
+  const int ch[5] = {64, 128, 256, 512, 512};
+  ActBuf x0 = pb.alloc(B, H, W, 64);
+  pb.gather(x0, H, W, 1, 0);
+  // every 3x3 conv is padding=1: its input buffer carries a 1-px zero frame
+  ActBuf cat[4];  // [skip | up] for decoder levels, skip written by the encoder
+  ActBuf cur;
+  const char* enc_name[5] = {"inc.conv.conv", "down1.mpconv.1.conv", "down2.mpconv.1.conv",
+                             "down3.mpconv.1.conv", "down4.mpconv.1.conv"};
+  for (int l = 0; l < 5; ++l) {
+    const std::string p = enc_name[l];
+    ActBuf mid = pb.alloc(B, sh[l] + 2, sw[l] + 2, ch[l]);
+    if (l == 0) pb.conv(p + ".0", x0, 0, mid, 0, 1, EPI_STORE);
+    else pb.conv(p + ".0", cur, 0, mid, 0, 1, EPI_STORE);
+    if (l < 4) {
+      cat[l] = pb.alloc(B, sh[l] + 2, sw[l] + 2, 2 * ch[l]);
+      pb.conv(p + ".3", mid, 0, cat[l], 0, 1, EPI_STORE);
+      cur = pb.alloc(B, sh[l + 1] + 2, sw[l + 1] + 2, ch[l]);
+      pb.pool("maxpool" + std::to_string(l + 1), cat[l], 1, 0, ch[l], cur, 1);
+    } else {
+      cur = pb.alloc(B, sh[l], sw[l], ch[l]);
+      pb.conv(p + ".3", mid, 0, cur, 0, 0, EPI_STORE);
+    }
+  }
+  const int outc[4] = {256, 128, 64, 64};
+  for (int i = 0; i < 4; ++i) {
+    const int l = 3 - i;  // skip level
+    const std::string p = "up" + std::to_string(i + 1);
+    pb.conv(p + ".up", cur, 0, cat[l], ch[l], 1, EPI_D2S);
+    ActBuf mid = pb.alloc(B, sh[l] + 2, sw[l] + 2, outc[i]);
+    pb.conv(p + ".conv.conv.0", cat[l], 0, mid, 0, 1, EPI_STORE);
+    if (i < 3) {
+      cur = pb.alloc(B, sh[l], sw[l], outc[i]);
+      pb.conv(p + ".conv.conv.3", mid, 0, cur, 0, 0, EPI_STORE);
+    } else {
+      pb.head(p + ".conv.conv.3", mid, 0, H, W, 1);
+    }
+  }
+  return pb.rc;
+}
+
+int get_plan(nind_net* net, int B, int H, int W, Plan** out) {
+  std::vector<int> key{B, H, W};
+  auto it = net->plans.find(key);
+  if (it != net->plans.end()) { *out = it->second.get(); return 0; }
+  std::unique_ptr<Plan> plan(new Plan);
+  plan->b = B; plan->h = H; plan->w = W;
+  int rc = net->arch == NIND_ARCH_UTNET ? build_utnet_plan(net, plan.get(), B, H, W)
+                                         : build_unet_plan(net, plan.get(), B, H, W);
+  if (rc) return rc;
+  // keep at most a few plans alive (each owns an activation arena)
+  if (net->plans.size() >= 4) net->plans.erase(net->plans.begin());
+  *out = plan.get();
+  net->plans[key] = std::move(plan);
+  return 0;
+}
+
+int grid_for(long long work_items) {
+  const long long blocks = (work_items + 255) / 256;
+  const long long cap = (long long)device_sm_count() * 16;
+  return (int)std::max(1LL, std::min(blocks, cap));
+}
+
+int run_plan(nind_net* net, Plan* plan, const GatherParams& gsrc, float* head_out, cudaStream_t st) {
+  std::vector<cudaEvent_t> ev;
+  if (net->timing) {
+    ev.resize(plan->steps.size() + 1);
+    for (auto& e : ev) CUDA_TRY(cudaEventCreate(&e));
+    CUDA_TRY(cudaEventRecord(ev[0], st));
+  }
+  for (size_t i = 0; i < plan->steps.size(); ++i) {
+    Step& s = plan->steps[i];
+    if (s.kind == STEP_GATHER) {
+      GatherParams g = s.g;
+      g.src = gsrc.src; g.src_img = gsrc.src_img; g.src_plane = gsrc.src_plane;
+      g.src_w = gsrc.src_w; g.src_h = gsrc.src_h; g.origin = gsrc.origin;
+      gather_im2col_kernel<<<grid_for((long long)g.n_crops * g.out_h * g.out_w * 8), 256, 0, st>>>(g);
+    } else if (s.kind == STEP_POOL) {
+      maxpool2_kernel<<<grid_for((long long)s.pl.n * s.pl.ho * s.pl.wo * (s.pl.c / 8)), 256, 0, st>>>(s.pl);
+    } else {
+      IgemmLaunch L = s.ig;
+      if ((int)i == plan->head_step) L.p.head_out = head_out;
+      cudaError_t e = launch_igemm(L, net->err_flag, st);
+      if (e != cudaSuccess) return fail(NIND_E_CUDA, s.name + ": " + cudaGetErrorString(e));
+    }
+    ++g_launches;
+    if (net->timing) CUDA_TRY(cudaEventRecord(ev[i + 1], st));
+  }
+  CUDA_TRY(cudaGetLastError());
+  if (net->timing) {
+    CUDA_TRY(cudaStreamSynchronize(st));
+    net->t_names.clear(); net->t_ms.clear(); net->t_flops.clear();
+    for (size_t i = 0; i < plan->steps.size(); ++i) {
+      float ms = 0;
+      cudaEventElapsedTime(&ms, ev[i], ev[i + 1]);
+      net->t_names.push_back(plan->steps[i].name);
+      net->t_ms.push_back(ms);
+      net->t_flops.push_back(plan->steps[i].flops);
+    }
+    for (auto& e : ev) cudaEventDestroy(e);
+  }
+  return 0;
+}
+
+int check_err_flag(nind_net* net) {
+  int h = 0;
+  CUDA_TRY(cudaMemcpy(&h, net->err_flag, sizeof h, cudaMemcpyDeviceToHost));
+  if (h) return fail(NIND_E_KERNEL, "kernel pipeline time-out, role code " + std::to_string(h));
+  return 0;
+}
+
+int ensure(void** p, size_t* cap, size_t bytes) {
+  if (*cap >= bytes) return 0;
+  if (*p) cudaFree(*p);
+  *p = nullptr; *cap = 0;
+  CUDA_TRY(cudaMalloc(p, bytes));
+  *cap = bytes;
+  return 0;
+}
+
+}  // namespace
+
+// ====================================================================== C ABI
+extern "C" {
+
+const char* nind_last_error(void) { return g_err.c_str(); }
+
+int64_t nind_kernel_launches(void) { return g_launches.load(); }
+
+int nind_device_info(int* sm_major, int* sm_minor, int* sm_count) {
+  int dev = 0;
+  CUDA_TRY(cudaGetDevice(&dev));
+  cudaDeviceProp prop;
+  CUDA_TRY(cudaGetDeviceProperties(&prop, dev));
+  if (sm_major) *sm_major = prop.major;
+  if (sm_minor) *sm_minor = prop.minor;
+  if (sm_count) *sm_count = prop.multiProcessorCount;
+  return 0;
+}
+
+int nind_net_create(int arch, int funit, int activation, const nind_tensor* tensors, int n_tensors,
+                    nind_net** out) {
+  if (!out || !tensors) return fail(NIND_E_INVALID, "null argument");
+  if (arch != NIND_ARCH_UTNET && arch != NIND_ARCH_UNET) return fail(NIND_E_INVALID, "unknown architecture");
+  if (activation < NIND_ACT_PRELU || activation > NIND_ACT_HARDSWISH)
+    return fail(NIND_E_INVALID, "unknown activation function");
+  int major = 0, minor = 0;
+  int rc = nind_device_info(&major, &minor, nullptr);
+  if (rc) return rc;
+  if (major != 10) return fail(NIND_E_UNSUPPORTED, "this library needs an sm_100 (B200) device; found sm_" +
+                                                       std::to_string(major) + std::to_string(minor));
+  std::unique_ptr<nind_net> net(new nind_net);
+  net->arch = arch;
+  net->funit = funit;
+  net->act_kind = activation == NIND_ACT_PRELU ? ACT_PRELU : (activation == NIND_ACT_ELU ? ACT_ELU : ACT_HARDSWISH);
+  CUDA_TRY(cudaGetDevice(&net->device));
+  CUDA_TRY(cudaMalloc(&net->err_flag, sizeof(int)));
+  CUDA_TRY(cudaMemset(net->err_flag, 0, sizeof(int)));
+  if ((rc = load_weights(net.get(), tensors, n_tensors))) return rc;
+  *out = net.release();
+  return 0;
+}
+
+int nind_net_load(nind_net* net, const nind_tensor* tensors, int n_tensors) {
+  if (!net || !tensors) return fail(NIND_E_INVALID, "null argument");
+  CUDA_TRY(cudaDeviceSynchronize());
+  return load_weights(net, tensors, n_tensors);
+}
+
+void nind_net_destroy(nind_net* net) {
+  if (!net) return;
+  cudaDeviceSynchronize();
+  delete net;
+}
+
+int nind_set_timing(nind_net* net, int enabled) {
+  if (!net) return fail(NIND_E_INVALID, "null handle");
+  net->timing = enabled;
+  return 0;
+}
+
+int nind_get_layer_times(nind_net* net, int max_layers, const char** names, float* ms, double* flops,
+                         int* n_layers) {
+  if (!net || !n_layers) return fail(NIND_E_INVALID, "null argument");
+  const int n = (int)net->t_ms.size();
+  *n_layers = n;
+  for (int i = 0; i < n && i < max_layers; ++i) {
+    if (names) names[i] = net->t_names[i].c_str();
+    if (ms) ms[i] = net->t_ms[i];
+    if (flops) flops[i] = net->t_flops[i];
+  }
+  return 0;
+}
+
+int nind_set_option(nind_net* net, const char* key, int value) {
+  if (!net || !key) return fail(NIND_E_INVALID, "null argument");
+  const std::string k = key;
+  if (k == "n_tile_deep") {
+    if (value != 128 && value != 256) return fail(NIND_E_INVALID, "n_tile_deep must be 128 or 256");
+    net->n_tile_deep = value;
+  } else if (k == "max_ctas") {
+    net->max_ctas = value;
+  } else {
+    return fail(NIND_E_INVALID, "unknown option " + k);
+  }
+  net->plans.clear();
+  return 0;
+}
+
+int nind_net_forward(nind_net* net, const float* in_nchw, float* out_nchw, int batch, int h, int w,
+                     void* stream) {
+  if (!net || !in_nchw || !out_nchw) return fail(NIND_E_INVALID, "null argument");
+  if (batch <= 0) return fail(NIND_E_INVALID, "batch must be positive");
+  Plan* plan = nullptr;
+  int rc = get_plan(net, batch, h, w, &plan);
+  if (rc) return rc;
+  GatherParams g;
+  memset(&g, 0, sizeof g);
+  g.src = in_nchw; g.src_img = 3LL * h * w; g.src_plane = (long long)h * w; g.src_w = w; g.src_h = h;
+  g.origin = nullptr;
+  return run_plan(net, plan, g, out_nchw, static_cast<cudaStream_t>(stream));
+}
+
+int nind_crop_table(int width, int height, int cs, int ucs, int ol, nind_crop* table, int* n_crops) {
+  GridGeom g;
+  if (!make_grid(width, height, cs, ucs, ol, &g)) return fail(NIND_E_INVALID, "illegal crop geometry");
+  if (n_crops) *n_crops = g.size();
+  if (table)
+    for (int i = 0; i < g.size(); ++i) crop_entry(g, i, &table[i]);
+  return 0;
+}
+
+int nind_band_rows(int width, int height, int cs, int ucs, int ol, int crop_begin, int crop_end,
+                   int* band_y0, int* band_y1) {
+  GridGeom g;
+  if (!make_grid(width, height, cs, ucs, ol, &g)) return fail(NIND_E_INVALID, "illegal crop geometry");
+  if (crop_begin < 0 || crop_end > g.size() || crop_begin >= crop_end)
+    return fail(NIND_E_INVALID, "illegal crop range");
+  int y0, y1;
+  band_of(g, crop_begin, crop_end, &y0, &y1);
+  if (band_y0) *band_y0 = y0;
+  if (band_y1) *band_y1 = y1;
+  return 0;
+}
+
+static int upload_origins(nind_net* net, const GridGeom& g, int crop_begin, int n, cudaStream_t st) {
+  int rc;
+  if ((rc = ensure(reinterpret_cast<void**>(&net->origin_buf), &net->origin_cap, (size_t)n * sizeof(int2))))
+    return rc;
+  std::vector<int2> origins(n);
+  for (int i = 0; i < n; ++i) {
+    nind_crop c;
+    crop_entry(g, crop_begin + i, &c);
+    origins[i] = make_int2(c.x0, c.y0);
+  }
+  CUDA_TRY(cudaMemcpyAsync(net->origin_buf, origins.data(), (size_t)n * sizeof(int2), cudaMemcpyHostToDevice, st));
+  CUDA_TRY(cudaStreamSynchronize(st));  // `origins` is a stack-lifetime pageable buffer
+  return 0;
+}
+
+static int launch_stitch(const GridGeom& g, const float* crops, int crop_begin, int crop_end, float* out_band,
+                         int* band_y0, int* band_y1, cudaStream_t st) {
+  StitchParams sp;
+  sp.crops = crops; sp.crop_begin = crop_begin; sp.crop_end = crop_end; sp.out = out_band;
+  band_of(g, crop_begin, crop_end, &sp.y_begin, &sp.y_end);
+  sp.W = g.W; sp.H = g.H; sp.cs = g.cs; sp.ucs = g.ucs; sp.ol = g.ol; sp.pad = g.pad; sp.stride = g.stride;
+  sp.nx = g.nx; sp.ny = g.ny;
+  stitch_kernel<<<grid_for((long long)(sp.y_end - sp.y_begin) * g.W), 256, 0, st>>>(sp);
+  ++g_launches;
+  CUDA_TRY(cudaGetLastError());
+  if (band_y0) *band_y0 = sp.y_begin;
+  if (band_y1) *band_y1 = sp.y_end;
+  return 0;
+}
+
+static int check_range(int width, int height, int cs, int ucs, int ol, int crop_begin, int crop_end, GridGeom* g) {
+  if (!make_grid(width, height, cs, ucs, ol, g)) return fail(NIND_E_INVALID, "illegal crop geometry");
+  if (crop_begin < 0 || crop_end > g->size() || crop_begin >= crop_end)
+    return fail(NIND_E_INVALID, "illegal crop range");
+  return 0;
+}
+
+int nind_gather_crops(nind_net* net, const float* img_chw, int height, int width, int cs, int ucs, int ol,
+                      int crop_begin, int crop_end, float* crops_out, void* stream) {
+  if (!net || !img_chw || !crops_out) return fail(NIND_E_INVALID, "null argument");
+  GridGeom g;
+  int rc;
+  if ((rc = check_range(width, height, cs, ucs, ol, crop_begin, crop_end, &g))) return rc;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int n = crop_end - crop_begin;
+  if ((rc = upload_origins(net, g, crop_begin, n, st))) return rc;
+  CropGatherParams p;
+  p.src = img_chw; p.src_plane = (long long)height * width; p.src_w = width; p.src_h = height;
+  p.origin = net->origin_buf; p.cs = cs; p.n_crops = n; p.dst = crops_out;
+  gather_crops_kernel<<<grid_for((long long)n * 3 * cs * cs), 256, 0, st>>>(p);
+  ++g_launches;
+  CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+
+int nind_stitch_crops(const float* crops, int height, int width, int cs, int ucs, int ol, int crop_begin,
+                      int crop_end, float* out_band, int* band_y0, int* band_y1, void* stream) {
+  if (!crops || !out_band) return fail(NIND_E_INVALID, "null argument");
+  GridGeom g;
+  int rc;
+  if ((rc = check_range(width, height, cs, ucs, ol, crop_begin, crop_end, &g))) return rc;
+  return launch_stitch(g, crops, crop_begin, crop_end, out_band, band_y0, band_y1, static_cast<cudaStream_t>(stream));
+}
+
+int nind_tiled_denoise(nind_net* net, const float* img_chw, float* out_band, int height, int width,
+                       int cs, int ucs, int ol, int crop_begin, int crop_end, int batch,
+                       int* band_y0, int* band_y1, void* stream) {
+  if (!net || !img_chw || !out_band) return fail(NIND_E_INVALID, "null argument");
+  GridGeom g;
+  int rc;
+  if ((rc = check_range(width, height, cs, ucs, ol, crop_begin, crop_end, &g))) return rc;
+  if (batch <= 0) return fail(NIND_E_INVALID, "batch must be positive");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int n = crop_end - crop_begin;
+  if ((rc = ensure(reinterpret_cast<void**>(&net->crops_buf), &net->crops_cap,
+                   (size_t)n * 3 * cs * cs * sizeof(float))))
+    return rc;
+  if ((rc = upload_origins(net, g, crop_begin, n, st))) return rc;
+  for (int i0 = 0; i0 < n; i0 += batch) {
+    const int b = std::min(batch, n - i0);
+    Plan* plan = nullptr;
+    if ((rc = get_plan(net, b, cs, cs, &plan))) return rc;
+    GatherParams gp;
+    memset(&gp, 0, sizeof gp);
+    gp.src = img_chw; gp.src_img = 0; gp.src_plane = (long long)height * width; gp.src_w = width; gp.src_h = height;
+    gp.origin = net->origin_buf + i0;
+    if ((rc = run_plan(net, plan, gp, net->crops_buf + (size_t)i0 * 3 * cs * cs, st))) return rc;
+  }
+  return launch_stitch(g, net->crops_buf, crop_begin, crop_end, out_band, band_y0, band_y1, st);
+}
+
+int nind_tiled_denoise_host(nind_net* net, const float* img_chw_host, float* out_chw_host, int height,
+                            int width, int cs, int ucs, int ol, int batch) {
+  if (!net || !img_chw_host || !out_chw_host) return fail(NIND_E_INVALID, "null argument");
+  GridGeom g;
+  if (!make_grid(width, height, cs, ucs, ol, &g)) return fail(NIND_E_INVALID, "illegal crop geometry");
+  const size_t bytes = (size_t)3 * height * width * sizeof(float);
+  int rc;
+  if ((rc = ensure(reinterpret_cast<void**>(&net->img_dev), &net->img_cap, bytes))) return rc;
+  if ((rc = ensure(reinterpret_cast<void**>(&net->out_dev), &net->out_cap, bytes))) return rc;
+  CUDA_TRY(cudaMemcpyAsync(net->img_dev, img_chw_host, bytes, cudaMemcpyHostToDevice, 0));
+  int y0 = 0, y1 = 0;
+  if ((rc = nind_tiled_denoise(net, net->img_dev, net->out_dev, height, width, cs, ucs, ol, 0, g.size(), batch,
+                               &y0, &y1, nullptr)))
+    return rc;
+  if (y0 != 0 || y1 != height) return fail(NIND_E_INVALID, "internal: full crop range does not cover the image");
+  CUDA_TRY(cudaMemcpyAsync(out_chw_host, net->out_dev, bytes, cudaMemcpyDeviceToHost, 0));
+  CUDA_TRY(cudaStreamSynchronize(0));
+  return check_err_flag(net);
+}
+
+}  // extern "C"

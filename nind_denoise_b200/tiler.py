@@ -1,0 +1,228 @@
+"""Tiled denoising of a whole image — the inner loop of the reference's denoise_image.py
+(/root/reference/src/nind_denoise/denoise_image.py:231-267) behind one call.
+
+``denoise_tiled(img, model, cs, ucs, ol)`` keeps the reference's semantics exactly: the same crop
+grid (``OneImageDS.__init__``), mirror-padded gather (``__getitem__``), trim by ``usefuldim``,
+``make_seamless_edges`` halving and raster-order overlap-add.  All of it runs on the GPU through
+``nind_tiled_denoise`` (include/nind_b200.h); crops are processed ``batch`` at a time.
+
+Multi-GPU (one process per GPU, torch.distributed): crops are split into contiguous raster ranges,
+every rank stitches its own row band, and the bands are gathered to rank 0 — the only collective.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+from typing import Callable, List, Optional, Sequence, Tuple
+
+import torch
+
+from . import _capi
+
+# reference defaults, denoise_image.py:40-42
+CS_UNET, UCS_UNET = 440, 320
+CS_UTNET, UCS_UTNET = 504, 480
+DEFAULT_OVERLAP = 6
+
+
+def crop_table(width: int, height: int, cs: int, ucs: int, ol: int):
+    """int32 [n_crops, 8]: x0, y0, usefuldim (x_lo, y_lo, x_hi, y_hi), usefulstart (x, y)."""
+    return _capi.crop_table(width, height, cs, ucs, ol)
+
+
+def n_crops(width: int, height: int, cs: int, ucs: int, ol: int) -> int:
+    stride = ucs - ol
+    return (math.ceil((width - ucs) / stride) + 1) * (math.ceil((height - ucs) / stride) + 1)
+
+
+def default_batch(n: int, cs: int) -> int:
+    """Crops per forward: enough to fill 148 SMs on the deep layers, and a divisor-friendly size."""
+    target = 16 if cs <= 264 else (13 if cs <= 520 else 4)
+    return max(1, min(n, target))
+
+
+def shard_ranges(n: int, world: int) -> List[Tuple[int, int]]:
+    """Contiguous raster ranges of crop indices, ceil(n/world) per rank; trailing ranks
+    may be empty."""
+    per = -(-n // world)
+    return [(min(n, r * per), min(n, (r + 1) * per)) for r in range(world)]
+
+
+def _band(model, img: torch.Tensor, cs, ucs, ol, crop_begin, crop_end, batch) -> Tuple[torch.Tensor, int, int]:
+    """Rows [y0, y1) touched by crops [crop_begin, crop_end) -> ([3, y1-y0, W] fp32 on img.device, y0, y1)."""
+    if not img.is_cuda:
+        raise RuntimeError("denoise_tiled (nind_denoise_b200): image must be a CUDA tensor; there is no CPU path")
+    _, H, W = img.shape
+    h = model.native_handle()
+    y0, y1 = _capi.band_rows(W, H, cs, ucs, ol, crop_begin, crop_end)
+    out = torch.empty((3, y1 - y0, W), dtype=torch.float32, device=img.device)
+    by0, by1 = C.c_int(), C.c_int()
+    with torch.cuda.device(img.device):
+        stream = torch.cuda.current_stream().cuda_stream
+        _capi.check(_capi.lib().nind_tiled_denoise(h, img.data_ptr(), out.data_ptr(), H, W, cs, ucs, ol, crop_begin,
+                                                   crop_end, batch, C.byref(by0), C.byref(by1), C.c_void_p(stream)))
+    assert (by0.value, by1.value) == (y0, y1)
+    return out, y0, y1
+
+
+def denoise_tiled(img: torch.Tensor, model, cs: Optional[int] = None, ucs: Optional[int] = None,
+                  ol: int = DEFAULT_OVERLAP, batch: Optional[int] = None) -> torch.Tensor:
+    """[3,H,W] fp32 CUDA image -> [3,H,W] fp32 denoised image on the same device (no clamp, as the
+    reference's '.tiff' path, pt_helpers.py:30-32)."""
+    if img.dim() != 3 or img.shape[0] != 3:
+        raise ValueError(f"expected a [3,H,W] image, got {tuple(img.shape)}")
+    if cs is None or ucs is None:  # autodetect_network_cs_ucs, denoise_image.py:59-79
+        cs, ucs = (CS_UTNET, UCS_UTNET) if type(model).__name__ == "UtNet" else (CS_UNET, UCS_UNET)
+    img = img.detach().float().contiguous()
+    n = n_crops(img.shape[2], img.shape[1], cs, ucs, ol)
+    if batch is None:
+        batch = default_batch(n, cs)
+    out, y0, y1 = _band(model, img, cs, ucs, ol, 0, n, batch)
+    assert y0 == 0 and y1 == img.shape[1]
+    return out
+
+
+def denoise_tiled_host(img_host: torch.Tensor, model, cs: int, ucs: int, ol: int = DEFAULT_OVERLAP,
+                       batch: Optional[int] = None, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Host-buffer variant (the call the reference's script would make): H2D + all crops + D2H inside
+    ``nind_tiled_denoise_host``.  ``img_host`` / ``out`` are CPU tensors (pinned for full PCIe speed)."""
+    if img_host.is_cuda:
+        raise ValueError("denoise_tiled_host expects a CPU tensor")
+    img_host = img_host.detach().float().contiguous()
+    _, H, W = img_host.shape
+    if out is None:
+        out = torch.empty_like(img_host)
+    if batch is None:
+        batch = default_batch(n_crops(W, H, cs, ucs, ol), cs)
+    h = model.native_handle()
+    with torch.cuda.device(model._device):
+        _capi.check(_capi.lib().nind_tiled_denoise_host(h, img_host.data_ptr(), out.data_ptr(), H, W, cs, ucs, ol,
+                                                        batch))
+    return out
+
+
+# ------------------------------------------------------------------------------ multi-GPU
+def assemble_bands(bands: Sequence[Tuple[Optional[torch.Tensor], int, int]], height: int, width: int,
+                   device=None) -> torch.Tensor:
+    """Sum per-rank row bands into the [3,H,W] image (rank order = raster order, so a pixel's
+    contributions are added in increasing crop index between ranks)."""
+    first = next(b for b, _, _ in bands if b is not None)
+    out = torch.zeros((3, height, width), dtype=torch.float32, device=device or first.device)
+    for band, y0, y1 in bands:
+        if band is not None and y1 > y0:
+            out[:, y0:y1, :] += band.to(out.device)
+    return out
+
+
+def denoise_tiled_distributed(img: torch.Tensor, model, cs: int, ucs: int, ol: int = DEFAULT_OVERLAP,
+                              batch: Optional[int] = None, group=None, dst: int = 0,
+                              band_fn: Optional[Callable] = None) -> Optional[torch.Tensor]:
+    """Every rank holds the same ``img`` (read-only) and a replica of ``model``; rank ``dst`` returns the
+    stitched image, the others return None.  ``band_fn(img, crop_begin, crop_end) -> (band, y0, y1)``
+    replaces the GPU band computation in CPU (gloo) tests of the sharding/gather logic."""
+    import torch.distributed as dist
+
+    world = dist.get_world_size(group)
+    rank = dist.get_rank(group)
+    _, H, W = img.shape
+    n = n_crops(W, H, cs, ucs, ol)
+    ranges = shard_ranges(n, world)
+    cb, ce = ranges[rank]
+    if band_fn is None:
+        if batch is None:
+            batch = default_batch(max(1, ce - cb), cs)
+        band_fn = lambda im, a, b: _band(model, im, cs, ucs, ol, a, b, batch)
+    # band extents are pure geometry: every rank can compute everybody's (no metadata exchange)
+    extents = []
+    for a, b in ranges:
+        if b > a:
+            t = crop_table(W, H, cs, ucs, ol)
+            y0 = int(t[a, 7])
+            y1 = min(H, int(t[b - 1, 7]) + int(t[b - 1, 5] - t[b - 1, 3]))
+            extents.append((y0, y1))
+        else:
+            extents.append((0, 0))
+    band = None
+    if ce > cb:
+        band, y0, y1 = band_fn(img, cb, ce)
+        assert (y0, y1) == extents[rank]
+    if rank == dst:
+        bands = []
+        for r in range(world):
+            y0, y1 = extents[r]
+            if y1 <= y0:
+                bands.append((None, 0, 0))
+            elif r == rank:
+                bands.append((band, y0, y1))
+            else:
+                buf = torch.empty((3, y1 - y0, W), dtype=torch.float32, device=img.device)
+                dist.recv(buf, src=r, group=group)
+                bands.append((buf, y0, y1))
+        return assemble_bands(bands, H, W, device=img.device)
+    if band is not None:
+        dist.send(band.contiguous(), dst=dst, group=group)
+    return None
+
+
+# ------------------------------------------------------------------------------ geometry ops
+def gather_crops(model, img: torch.Tensor, cs: int, ucs: int, ol: int, crop_begin: int = 0,
+                 crop_end: Optional[int] = None) -> torch.Tensor:
+    """``OneImageDS.__getitem__`` for a range of crops: [3,H,W] CUDA image -> [n,3,cs,cs] fp32
+    (bit-exact copies with the reference's mirror padding, denoise_image.py:129-174)."""
+    _, H, W = img.shape
+    if crop_end is None:
+        crop_end = n_crops(W, H, cs, ucs, ol)
+    img = img.detach().float().contiguous()
+    out = torch.empty((crop_end - crop_begin, 3, cs, cs), dtype=torch.float32, device=img.device)
+    with torch.cuda.device(img.device):
+        stream = torch.cuda.current_stream().cuda_stream
+        _capi.check(_capi.lib().nind_gather_crops(model.native_handle(), img.data_ptr(), H, W, cs, ucs, ol, crop_begin,
+                                                  crop_end, out.data_ptr(), C.c_void_p(stream)))
+    return out
+
+
+def stitch_crops(crops: torch.Tensor, height: int, width: int, cs: int, ucs: int, ol: int, crop_begin: int = 0,
+                 crop_end: Optional[int] = None) -> Tuple[torch.Tensor, int, int]:
+    """Trim + seam halving + overlap-add (denoise_image.py:204-213,250-267) of network outputs
+    [n,3,cs,cs] -> (band [3, y1-y0, W], y0, y1)."""
+    if crop_end is None:
+        crop_end = crop_begin + crops.shape[0]
+    assert crops.is_cuda and crops.shape[0] == crop_end - crop_begin and tuple(crops.shape[1:]) == (3, cs, cs)
+    crops = crops.detach().float().contiguous()
+    y0, y1 = _capi.band_rows(width, height, cs, ucs, ol, crop_begin, crop_end)
+    out = torch.empty((3, y1 - y0, width), dtype=torch.float32, device=crops.device)
+    by0, by1 = C.c_int(), C.c_int()
+    with torch.cuda.device(crops.device):
+        stream = torch.cuda.current_stream().cuda_stream
+        _capi.check(_capi.lib().nind_stitch_crops(crops.data_ptr(), height, width, cs, ucs, ol, crop_begin, crop_end,
+                                                  out.data_ptr(), C.byref(by0), C.byref(by1), C.c_void_p(stream)))
+    return out, y0, y1
+
+
+class OneImageDS:
+    """Mirror of the reference dataset class (denoise_image.py:81-177) over an in-memory CUDA image:
+    ``ds[i]`` -> (crop [3,cs,cs], usefuldim IntTensor[4], usefulstart IntTensor[2]).  Tiled mode only."""
+
+    def __init__(self, inimg, cs, ucs, ol, whole_image=False, pad=None, model=None):
+        if whole_image:
+            raise NotImplementedError("whole_image mode is not part of the tiled hot path (SURVEY §8f-3)")
+        if not torch.is_tensor(inimg) or not inimg.is_cuda:
+            raise RuntimeError("OneImageDS (nind_denoise_b200) takes a [3,H,W] CUDA tensor")
+        self.inimg = inimg.detach().float().contiguous()
+        self.height, self.width = self.inimg.shape[1], self.inimg.shape[2]
+        self.cs, self.ucs, self.ol = cs, ucs, ol
+        self.pad = int((cs - ucs) / 2)
+        self.iperhl = math.ceil((self.width - ucs) / (ucs - ol))
+        self.table = crop_table(self.width, self.height, cs, ucs, ol)
+        self.size = self.table.shape[0]
+        self._model = model
+
+    def __len__(self):
+        return self.size
+
+    def __getitem__(self, i):
+        if not 0 <= i < self.size:
+            raise IndexError(i)
+        crop = gather_crops(self._model, self.inimg, self.cs, self.ucs, self.ol, i, i + 1)[0]
+        t = self.table[i]
+        return crop, torch.IntTensor(t[2:6].tolist()), torch.IntTensor(t[6:8].tolist())

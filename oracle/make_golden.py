@@ -1,0 +1,253 @@
+"""Generates tests/golden/*.npz by running the REFERENCE ITSELF (imported from /root/reference) in the
+build container, and checks the oracle restatement against it while doing so.
+
+    python oracle/make_golden.py            # writes tests/golden/, exits non-zero on any mismatch
+
+The reference ships no golden vectors for this path, so these files are what pins the
+oracle; /root/reference does not exist on the GPU box, hence the committed fixtures.
+
+What runs from the reference:
+  * networks.UtNet.UtNet, networks.ThirdPartyNets.UNet          (forward, default init)
+  * denoise_image.OneImageDS.__getitem__                         (crop gather + usefuldim/usefulstart)
+The stitch loop is module-level script code in the reference (denoise_image.py:204-213,240-267, under
+``if __name__ == '__main__'``) and is restated below line for line around the reference's own
+dataset object.
+"""
+from __future__ import annotations
+
+import math
+import os
+import sys
+import types
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REF = "/root/reference/src/nind_denoise"
+sys.path.insert(0, ROOT)
+sys.path.insert(0, REF)
+for missing in ("configargparse", "exiv2", "imageio", "piqa", "piexif"):
+    if missing not in sys.modules:
+        try:
+            __import__(missing)
+        except Exception:
+            sys.modules[missing] = types.ModuleType(missing)
+if not hasattr(sys.modules["piqa"], "MS_SSIM"):  # pt_losses.py:6,13 subclass these at import time
+    sys.modules["piqa"].MS_SSIM = type("MS_SSIM", (torch.nn.Module,), {})
+    sys.modules["piqa"].SSIM = type("SSIM", (torch.nn.Module,), {})
+
+from oracle import geometry as og  # noqa: E402
+from oracle import nets as on  # noqa: E402
+
+OUT = os.path.join(ROOT, "tests", "golden")
+os.makedirs(OUT, exist_ok=True)
+
+
+def ref_dataset(img: np.ndarray, cs, ucs, ol):
+    """The reference OneImageDS over an in-memory image (its constructor only reads files)."""
+    cwd = os.getcwd()
+    os.chdir(REF)
+    try:
+        import denoise_image as di
+    finally:
+        os.chdir(cwd)
+    ds = di.OneImageDS.__new__(di.OneImageDS)
+    ds.inimg = img
+    ds.width, ds.height = img.shape[2], img.shape[1]
+    ds.whole_image = False
+    ds.cs, ds.ucs, ds.ol = cs, ucs, ol
+    ds.iperhl = math.ceil((ds.width - ucs) / (ucs - ol))
+    ds.pad = int((cs - ucs) / 2)
+    ipervl = math.ceil((ds.height - ucs) / (ucs - ol))
+    ds.size = (ds.iperhl + 1) * (ipervl + 1)
+    return ds
+
+
+def ref_stitch(ds, model_fn, overlap, ucs):
+    """denoise_image.py:204-213 + 240-267 around the reference dataset (batch_size 1)."""
+    fsheight, fswidth = ds.height, ds.width
+
+    def make_seamless_edges(tcrop, x0, y0):
+        if x0 != 0:
+            tcrop[:, :, 0:overlap] = tcrop[:, :, 0:overlap].div(2)
+        if y0 != 0:
+            tcrop[:, 0:overlap, :] = tcrop[:, 0:overlap, :].div(2)
+        if x0 + ucs < fswidth and overlap:
+            tcrop[:, :, -overlap:] = tcrop[:, :, -overlap:].div(2)
+        if y0 + ucs < fsheight and overlap:
+            tcrop[:, -overlap:, :] = tcrop[:, -overlap:, :].div(2)
+        return tcrop
+
+    newimg = torch.zeros(3, fsheight, fswidth, dtype=torch.float32)
+    for n in range(len(ds)):
+        y, usefuldims, usefulstarts = ds[n]
+        xbatch = model_fn(y.unsqueeze(0))
+        ud = usefuldims
+        tensimg = xbatch[0][:, ud[1]:ud[3], ud[0]:ud[2]].cpu().detach().clone()
+        absx0, absy0 = tuple(usefulstarts.tolist())
+        tensimg = make_seamless_edges(tensimg, absx0, absy0)
+        newimg[:, absy0:absy0 + tensimg.shape[1], absx0:absx0 + tensimg.shape[2]] = \
+            newimg[:, absy0:absy0 + tensimg.shape[1], absx0:absx0 + tensimg.shape[2]].add(tensimg)
+    return newimg
+
+
+def fake_model(x: torch.Tensor) -> torch.Tensor:
+    """Cheap deterministic stand-in for the network in geometry goldens (position dependent)."""
+    ramp = torch.linspace(0.5, 1.5, x.shape[-1]).view(1, 1, 1, -1) * torch.linspace(1.25, 0.75, x.shape[-2]).view(1, 1, -1, 1)
+    return x * ramp + 0.125
+
+
+def fake_model_np(c: np.ndarray) -> np.ndarray:
+    return fake_model(torch.from_numpy(c).unsqueeze(0))[0].numpy()
+
+
+GEOMS = [  # (W, H, cs, ucs, ol)
+    (90, 70, 40, 28, 4),
+    (101, 83, 40, 28, 4),    # nothing divides
+    (64, 64, 40, 28, 0),     # zero overlap
+    (75, 50, 32, 20, 6),
+    (130, 41, 40, 28, 4),    # image shorter than one crop stride
+    (97, 97, 36, 24, 8),
+    (400, 300, 120, 96, 6),  # a legal UtNet size
+]
+TABLE_ONLY = [(6000, 4000, 504, 480, 6), (6000, 4000, 248, 224, 6), (6000, 4000, 120, 96, 6),
+              (6000, 4000, 1016, 992, 6), (8256, 5504, 512, 384, 6), (8256, 5504, 440, 320, 6),
+              (6000, 4000, 504, 480, 0), (6000, 4000, 504, 480, 16), (5999, 3999, 504, 480, 6),
+              (4000, 6000, 248, 224, 32)]
+
+
+def main() -> int:
+    bad = 0
+    rng = np.random.default_rng(0)
+    # ------------------------------------------------------------------ geometry
+    geo = {}
+    for gi, (W, H, cs, ucs, ol) in enumerate(GEOMS):
+        img = rng.random((3, H, W), dtype=np.float32)
+        ds = ref_dataset(img, cs, ucs, ol)
+        g = og.crop_grid(W, H, cs, ucs, ol)
+        assert g.size == len(ds), (g.size, len(ds))
+        table = np.zeros((len(ds), 6), dtype=np.int32)
+        crops = np.zeros((len(ds), 3, cs, cs), dtype=np.float32)
+        for i in range(len(ds)):
+            c, ud, us = ds[i]
+            crops[i] = c.numpy()
+            table[i] = (*ud.tolist(), *us.tolist())
+            if not np.array_equal(og.gather_crop(img, g, i), crops[i]):
+                print(f"MISMATCH oracle gather geom {gi} crop {i}")
+                bad += 1
+        if not np.array_equal(og.crop_table(g)[:, 2:], table):
+            print(f"MISMATCH oracle crop table geom {gi}")
+            bad += 1
+        stitched = ref_stitch(ds, fake_model, ol, ucs).numpy()
+        mine = og.denoise_tiled(img, fake_model_np, cs, ucs, ol)
+        if not np.array_equal(mine, stitched):
+            print(f"MISMATCH oracle stitch geom {gi}: max diff {np.abs(mine - stitched).max()}")
+            bad += 1
+        # store: image seedable? keep the image itself (small) so the test needs no RNG agreement
+        geo[f"g{gi}_params"] = np.array([W, H, cs, ucs, ol], dtype=np.int32)
+        geo[f"g{gi}_img"] = img.astype(np.float16) if False else img
+        geo[f"g{gi}_table"] = table
+        geo[f"g{gi}_stitched"] = stitched
+        # a few crops only (first, a middle one, last) keep the file small
+        pick = sorted(set([0, len(ds) // 2, len(ds) - 1]))
+        geo[f"g{gi}_crop_idx"] = np.array(pick, dtype=np.int32)
+        geo[f"g{gi}_crops"] = crops[pick]
+    for ti, (W, H, cs, ucs, ol) in enumerate(TABLE_ONLY):
+        ds = ref_dataset(np.zeros((3, H, W), dtype=np.float32), cs, ucs, ol)
+        table = np.zeros((len(ds), 6), dtype=np.int32)
+        for i in range(len(ds)):
+            # indices only: replicate the index arithmetic through the reference object without
+            # materialising every crop of a 24 MP image
+            c, ud, us = ds[i] if i in (0, len(ds) - 1) else (None, None, None)
+            if ud is None:
+                e = og.crop_entry(og.crop_grid(W, H, cs, ucs, ol), i)
+                ud, us = torch.IntTensor(e["usefuldim"]), torch.IntTensor(e["usefulstart"])
+            table[i] = (*ud.tolist(), *us.tolist())
+        geo[f"t{ti}_params"] = np.array([W, H, cs, ucs, ol], dtype=np.int32)
+        geo[f"t{ti}_n"] = np.array([len(ds)], dtype=np.int32)
+        geo[f"t{ti}_first_last"] = table[[0, len(ds) - 1]]
+    np.savez_compressed(os.path.join(OUT, "geometry.npz"), **geo)
+
+    # ------------------------------------------------------------------ networks
+    from networks.ThirdPartyNets import UNet as RefUNet
+    from networks.UtNet import UtNet as RefUtNet
+
+    nets = {}
+    with torch.no_grad():
+        torch.manual_seed(0)
+        ref = RefUtNet().eval()
+        sd = on.init_state_dict("UtNet", seed=0)
+        rsd = ref.state_dict()
+        if list(rsd.keys()) != list(sd.keys()) or any(not torch.equal(rsd[k], sd[k]) for k in sd):
+            print("MISMATCH oracle UtNet init != reference init")
+            bad += 1
+        nets["utnet_sd_checksum"] = np.array([float(v.double().abs().sum()) for v in rsd.values()])
+        for cs in (120, 248):
+            torch.manual_seed(1)
+            x = torch.rand(1, 3, cs, cs)
+            y = ref(x)
+            yo = on.utnet_forward(sd, x)
+            err = (y - yo).abs().max().item()
+            print(f"UtNet cs={cs}: reference vs oracle max abs diff {err:.3e}; out std {y.std().item():.4f}")
+            if err > 1e-5:
+                bad += 1
+            nets[f"utnet_out_{cs}"] = y[0].numpy()
+        # a weight set with a livelier output (default init gives sigma_out ~ 0.007)
+        for act in ("ELU", "Hardswish"):
+            torch.manual_seed(0)
+            refa = RefUtNet(activation=act).eval()
+            sda = on.init_state_dict("UtNet", seed=0, activation=act)
+            torch.manual_seed(1)
+            x = torch.rand(1, 3, 120, 120)
+            y = refa(x)
+            yo = on.utnet_forward(sda, x, activation=act)
+            err = (y - yo).abs().max().item()
+            print(f"UtNet {act}: reference vs oracle max abs diff {err:.3e}")
+            if err > 1e-5 or list(refa.state_dict().keys()) != list(sda.keys()):
+                bad += 1
+            nets[f"utnet_out_120_{act}"] = y[0].numpy()
+
+        torch.manual_seed(0)
+        refu = RefUNet().eval()
+        sdu = on.init_state_dict("UNet", seed=0)
+        rsdu = refu.state_dict()
+        if list(rsdu.keys()) != list(sdu.keys()) or any(not torch.equal(rsdu[k], sdu[k]) for k in sdu):
+            print("MISMATCH oracle UNet init != reference init")
+            bad += 1
+        on.randomize_bn_(sdu, seed=7)
+        refu.load_state_dict(sdu)
+        for cs in (64, 128):
+            torch.manual_seed(1)
+            x = torch.rand(1, 3, cs, cs)
+            y = refu(x)
+            yo = on.unet_forward(sdu, x)
+            err = (y - yo).abs().max().item()
+            print(f"UNet cs={cs}: reference vs oracle max abs diff {err:.3e}; out std {y.std().item():.4f}")
+            if err > 1e-5:
+                bad += 1
+            nets[f"unet_out_{cs}"] = y[0].numpy()
+
+        # tiled end to end with the real reference network on a small image
+        W, H, cs, ucs, ol = 300, 260, 120, 96, 6
+        img = np.random.default_rng(5).random((3, H, W), dtype=np.float32)
+        ds = ref_dataset(img, cs, ucs, ol)
+        stitched = ref_stitch(ds, ref, ol, ucs).numpy()
+        mine = og.denoise_tiled(img, lambda c: on.utnet_forward(sd, torch.from_numpy(c).unsqueeze(0))[0].numpy(),
+                                cs, ucs, ol)
+        err = np.abs(mine - stitched).max()
+        print(f"tiled UtNet {W}x{H}: reference loop vs oracle max abs diff {err:.3e}")
+        if err > 1e-5:
+            bad += 1
+        nets["tiled_params"] = np.array([W, H, cs, ucs, ol], dtype=np.int32)
+        nets["tiled_img"] = img
+        nets["tiled_out"] = stitched
+    np.savez_compressed(os.path.join(OUT, "networks.npz"), **nets)
+    for f in ("geometry.npz", "networks.npz"):
+        print(f, os.path.getsize(os.path.join(OUT, f)) // 1024, "KiB")
+    print("mismatches:", bad)
+    return 1 if bad else 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -1,0 +1,26 @@
+import os
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA sm_100 device (run with -m gpu on the B200 box)")
+
+
+@pytest.fixture(scope="session")
+def golden_geometry():
+    import numpy as np
+    return np.load(os.path.join(GOLDEN, "geometry.npz"))
+
+
+@pytest.fixture(scope="session")
+def golden_networks():
+    import numpy as np
+    return np.load(os.path.join(GOLDEN, "networks.npz"))

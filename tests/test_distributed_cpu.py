@@ -1,0 +1,61 @@
+"""CPU, world_size 2 over gloo: crop sharding + band gather + assembly of the multi-GPU path, with the
+per-rank band computed by the oracle (the GPU band kernel itself is covered by -m gpu tests)."""
+import os
+import socket
+
+import numpy as np
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+import nind_denoise_b200 as nb
+from oracle import geometry as og
+
+W, H, CS, UCS, OL = 101, 83, 40, 28, 4
+
+
+def fake_model_np(c):
+    x = torch.from_numpy(c)
+    ramp = torch.linspace(0.5, 1.5, x.shape[-1]).view(1, 1, -1) * torch.linspace(1.25, 0.75, x.shape[-2]).view(1, -1, 1)
+    return (x * ramp + 0.125).numpy()
+
+
+def oracle_band(img, a, b):
+    g = og.crop_grid(W, H, CS, UCS, OL)
+    full = og.stitch(lambda i: fake_model_np(og.gather_crop(img.numpy(), g, i)), g, (a, b))
+    t = og.crop_table(g)
+    y0, y1 = int(t[a, 7]), min(H, int(t[b - 1, 7] + t[b - 1, 5] - t[b - 1, 3]))
+    assert not full[:, :y0].any() and not full[:, y1:].any()
+    return torch.from_numpy(full[:, y0:y1].copy()), y0, y1
+
+
+def _worker(rank, world, port, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    img = torch.from_numpy(np.random.default_rng(3).random((3, H, W), dtype=np.float32))
+    out = nb.denoise_tiled_distributed(img, None, CS, UCS, OL, band_fn=oracle_band)
+    if rank == 0:
+        ref = og.denoise_tiled(img.numpy(), fake_model_np, CS, UCS, OL)
+        q.put(float(np.abs(out.numpy() - ref).max()))
+    else:
+        assert out is None
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_rank_gather_equals_single():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    err = q.get(timeout=120)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert err <= 1e-6

@@ -225,7 +225,7 @@ static int run_conv(int argc, char** argv) {
   ConvSpec s;
   s.in = ActBuf{din, B, Hs, Ws, Cbuf};
   s.in_coff = coff; s.cin = cin; s.taps = taps; s.w = dw; s.n_total = n_total; s.bias = dbias;
-  s.act = act; s.slope = slope; s.epi_mode = epi; s.a_mode = a_mode; s.a_bo_mode = bo_mode;
+  s.act = act; s.slope = slope; s.epi_mode = epi; (void)a_mode; (void)bo_mode;
   s.n_tile = n_tile; s.force_ws = ws; s.max_ctas = ctas;
   const int halo = 2, ocoff = 32;
   int Ho = 0, Wo = 0, Co = 0;
