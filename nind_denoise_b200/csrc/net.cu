@@ -112,6 +112,7 @@ struct nind_net {
   size_t crops_cap = 0;
   int2* origin_buf = nullptr;
   size_t origin_cap = 0;
+  std::vector<int> origin_key;  // geometry + range the device table currently holds
   float* img_dev = nullptr;
   float* out_dev = nullptr;
   size_t img_cap = 0, out_cap = 0;
@@ -768,6 +769,9 @@ int nind_band_rows(int width, int height, int cs, int ucs, int ol, int crop_begi
 
 static int upload_origins(nind_net* net, const GridGeom& g, int crop_begin, int n, cudaStream_t st) {
   int rc;
+  const std::vector<int> key{g.W, g.H, g.cs, g.ucs, g.ol, crop_begin, n};
+  if (net->origin_buf && key == net->origin_key) return 0;  // same table as last call: no copy, no sync
+  net->origin_key.clear();
   if ((rc = ensure(reinterpret_cast<void**>(&net->origin_buf), &net->origin_cap, (size_t)n * sizeof(int2))))
     return rc;
   std::vector<int2> origins(n);
@@ -778,6 +782,7 @@ static int upload_origins(nind_net* net, const GridGeom& g, int crop_begin, int 
   }
   CUDA_TRY(cudaMemcpyAsync(net->origin_buf, origins.data(), (size_t)n * sizeof(int2), cudaMemcpyHostToDevice, st));
   CUDA_TRY(cudaStreamSynchronize(st));  // `origins` is a stack-lifetime pageable buffer
+  net->origin_key = key;
   return 0;
 }
 
