@@ -39,11 +39,12 @@ __device__ __forceinline__ int sym_index(int t, int n) {
 }
 
 __global__ void __launch_bounds__(256) gather_im2col_kernel(const GatherParams p) {
-  const long long total = (long long)p.n_crops * p.out_h * p.out_w * 8;
+  // One thread per output pixel of the first convolution: 6 index computations, 27 coalesced loads
+  // (neighbouring threads read neighbouring pixels), one 128-byte row of bf16 written.
+  const long long total = (long long)p.n_crops * p.out_h * p.out_w;
   for (long long gid = blockIdx.x * (long long)blockDim.x + threadIdx.x; gid < total;
        gid += (long long)gridDim.x * blockDim.x) {
-    const int j = (int)(gid & 7);
-    long long pix = gid >> 3;
+    long long pix = gid;
     const int x = (int)(pix % p.out_w);
     pix /= p.out_w;
     const int y = (int)(pix % p.out_h);
@@ -55,38 +56,49 @@ __global__ void __launch_bounds__(256) gather_im2col_kernel(const GatherParams p
       y0 = o.y;
     }
     const float* img = p.src + b * p.src_img;
-    float v[8];
+    long long rowoff[3];
+    int col[3];
+    bool vy[3], vx[3];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const int k = 8 * j + i;
-      float val = 0.f;
-      if (k < 54) {
-        const int e = k < 27 ? k : k - 27;
-        const int t = e / 3, c = e - 3 * t;
-        const int ky = t / 3, kx = t - 3 * ky;
-        int r = y + ky - p.pad, q = x + kx - p.pad;  // crop coordinates
-        bool inside = true;
-        if (p.reflect) {
-          r = r < 0 ? -r : (r >= p.crop_h ? 2 * p.crop_h - 2 - r : r);
-          q = q < 0 ? -q : (q >= p.crop_w ? 2 * p.crop_w - 2 - q : q);
-        } else {
-          inside = r >= 0 && r < p.crop_h && q >= 0 && q < p.crop_w;
-        }
-        if (inside) {
-          const int iy = sym_index(y0 + r, p.src_h), ix = sym_index(x0 + q, p.src_w);
-          const float f = __ldg(img + c * p.src_plane + (long long)iy * p.src_w + ix);
-          const float hi = __bfloat162float(__float2bfloat16_rn(f));
-          val = k < 27 ? hi : f - hi;
-        }
+    for (int k = 0; k < 3; ++k) {
+      int r = y + k - p.pad, q = x + k - p.pad;  // crop coordinates
+      if (p.reflect) {
+        r = r < 0 ? -r : (r >= p.crop_h ? 2 * p.crop_h - 2 - r : r);
+        q = q < 0 ? -q : (q >= p.crop_w ? 2 * p.crop_w - 2 - q : q);
+        vy[k] = vx[k] = true;
+      } else {
+        vy[k] = r >= 0 && r < p.crop_h;
+        vx[k] = q >= 0 && q < p.crop_w;
       }
-      v[i] = val;
+      rowoff[k] = (long long)sym_index(y0 + r, p.src_h) * p.src_w;
+      col[k] = sym_index(x0 + q, p.src_w);
     }
-    uint4 o;
-    o.x = pack_bf16x2(v[0], v[1]);
-    o.y = pack_bf16x2(v[2], v[3]);
-    o.z = pack_bf16x2(v[4], v[5]);
-    o.w = pack_bf16x2(v[6], v[7]);
-    reinterpret_cast<uint4*>(p.dst)[gid] = o;
+    float h[64];
+#pragma unroll
+    for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+      for (int kx = 0; kx < 3; ++kx)
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+          const int e = (ky * 3 + kx) * 3 + c;
+          float f = 0.f;
+          if (vy[ky] && vx[kx]) f = __ldg(img + c * p.src_plane + rowoff[ky] + col[kx]);
+          const float hi = __bfloat162float(__float2bfloat16_rn(f));
+          h[e] = hi;
+          h[27 + e] = f - hi;
+        }
+#pragma unroll
+    for (int k = 54; k < 64; ++k) h[k] = 0.f;
+    uint4* dst = reinterpret_cast<uint4*>(p.dst + gid * 64);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      uint4 o;
+      o.x = pack_bf16x2(h[8 * j + 0], h[8 * j + 1]);
+      o.y = pack_bf16x2(h[8 * j + 2], h[8 * j + 3]);
+      o.z = pack_bf16x2(h[8 * j + 4], h[8 * j + 5]);
+      o.w = pack_bf16x2(h[8 * j + 6], h[8 * j + 7]);
+      dst[j] = o;
+    }
   }
 }
 

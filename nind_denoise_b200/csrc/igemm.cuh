@@ -13,11 +13,16 @@
 // ((16+2) x (8+2) pixels x 64 channels) is loaded ONCE per chunk by a 3-D TMA box with 128-byte
 // swizzle; the nine taps are nine UMMA descriptors into the same patch (start address moved by
 // (ky*10+kx) rows, 8-row groups 10 rows apart), so shared memory — not L2 — serves the 9x reuse.
+// Weight tiles arrive TPS taps per pipeline stage (TPS = 3: one kernel row) so that the single
+// issuing thread pays one barrier round-trip per 12 MMAs; when the whole weight tensor of the layer
+// fits in shared memory it is loaded once per CTA and kept ("weights stationary").
 //
 // Warp roles (256 threads, 1 CTA/SM, persistent over tiles):
 //   warp 0: TMA producer for activation patches      warp 1: TMA producer for weight tiles
-//   warp 2: single-thread tcgen05.mma issuer         warp 3: TMEM allocator
-//   warps 4-7: epilogue (tcgen05.ld -> bias/activation -> bf16 -> global), double-buffered TMEM.
+//   warp 2: tcgen05.mma issuer (one elected lane)    warp 3: TMEM allocator
+//   warps 4-7: epilogue: tcgen05.ld -> bias/activation -> bf16 -> swizzled smem staging ->
+//              coalesced 16-byte global stores (4 pixels x 128 B per warp instruction);
+//              TMEM accumulators are double-buffered so the epilogue overlaps the next tile's MMAs.
 #pragma once
 #include "ptx.cuh"
 
@@ -27,8 +32,9 @@ enum EpiMode : int { EPI_STORE = 0, EPI_D2S = 1, EPI_HEAD = 2 };
 enum ActKind : int { ACT_NONE = 0, ACT_PRELU = 1, ACT_ELU = 2, ACT_HARDSWISH = 3 };
 
 constexpr int IG_MAX_STAGES = 32;
-constexpr int IG_BAR_BYTES = 2048;   // mbarriers + TMEM base slot
-constexpr int IG_EPI_BYTES = 3072;   // staged bias [2][256] fp32 + head weights [3][64]+[3]
+constexpr int IG_BAR_BYTES = 2048;     // mbarriers + TMEM base slot
+constexpr int IG_EPI_BYTES = 3072;     // staged bias [2][256] fp32 + head weights [3][64]+[3]
+constexpr int IG_STAGE_BYTES = 16384;  // epilogue staging: 4 warps x 32 rows x 128 B
 constexpr int IG_THREADS = 256;
 constexpr int IG_TILE_H = 16;
 constexpr int IG_TILE_W = 8;
@@ -65,25 +71,38 @@ struct IgemmParams {
   int h_size_y, h_size_x;  // output plane size
   int head_sigmoid;
   int* err;
+  long long* trace;        // optional [64 tiles][8 events] clock64 stamps written by CTA 0 (debug)
 };
 
-__host__ __device__ inline size_t igemm_smem_bytes(int n_tile, int sa, uint32_t a_stage_bytes, int sb) {
-  return 1024 + (size_t)sa * a_stage_bytes + (size_t)sb * n_tile * 128 + IG_BAR_BYTES + IG_EPI_BYTES;
+// pipeline trace events (CTA 0 only, first 64 tiles): see tools/probe.cu "trace"
+enum { TR_A_ISSUE = 0, TR_MMA_TEMPTY = 1, TR_MMA_AFULL = 2, TR_MMA_DONE = 3, TR_EPI_TFULL = 4, TR_EPI_TMEM = 5,
+       TR_EPI_DONE = 6 };
+#define NIND_TRACE(tl, ev)                                                                  \
+  do {                                                                                      \
+    if (p.trace && blockIdx.x == 0 && (tl) < 64 && lane == 0) p.trace[(tl) * 8 + (ev)] = clock64(); \
+  } while (0)
+
+__host__ __device__ inline size_t igemm_smem_bytes(int n_tile, int tps, int sa, uint32_t a_stage_bytes, int sb) {
+  return 1024 + (size_t)sa * a_stage_bytes + (size_t)sb * tps * n_tile * 128 + IG_BAR_BYTES + IG_EPI_BYTES +
+         IG_STAGE_BYTES;
 }
 
-template <int N_TILE>
+// N_TILE: GEMM N per CTA tile (64/128/256).  TPS: taps per weight pipeline stage (1 or 3).
+template <int N_TILE, int TPS>
 __global__ void __launch_bounds__(IG_THREADS, 1)
 igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
              const IgemmParams p) {
   extern __shared__ uint8_t smem_raw[];
-  constexpr uint32_t B_BYTES = N_TILE * 128;
+  constexpr uint32_t B_TAP_BYTES = N_TILE * 128;
+  constexpr uint32_t B_BYTES = TPS * B_TAP_BYTES;
   constexpr uint32_t TMEM_COLS = 2 * N_TILE;
   constexpr uint32_t IDESC = umma_idesc_bf16(128, N_TILE);
 
   const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t a_base = sbase;
   const uint32_t b_base = a_base + (uint32_t)p.sa * p.a_stage_bytes;
-  const uint32_t bar_base = b_base + (uint32_t)p.sb * B_BYTES;
+  const uint32_t stg_base = b_base + (uint32_t)p.sb * B_BYTES;  // 1024-aligned
+  const uint32_t bar_base = stg_base + IG_STAGE_BYTES;
   const uint32_t a_full = bar_base;
   const uint32_t a_empty = bar_base + 8 * IG_MAX_STAGES;
   const uint32_t b_full = bar_base + 16 * IG_MAX_STAGES;
@@ -124,16 +143,19 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
   asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
 
   const int tiles_xy = p.tiles_x * p.tiles_y;
+  const int groups = p.taps / TPS;  // weight stages per 64-channel chunk
 
   if (warp == 0) {
     // ------------------------------------------------ activation-patch producer
     if (lane == 0) {
       uint32_t s = 0, ph = 0;
-      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+      int tl = 0;
+      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++tl) {
         const int r = tile % tiles_xy;
         const int yt = r / p.tiles_x, xt = r - yt * p.tiles_x;
         for (int kc = 0; kc < p.kchunks; ++kc) {
           mbar_wait(a_empty + 8 * s, ph ^ 1, p.err, 1);
+          if (kc == 0) NIND_TRACE(tl, TR_A_ISSUE);
           mbar_arrive_expect_tx(a_full + 8 * s, p.a_tx_bytes);
           tma_load_3d(a_base + s * p.a_stage_bytes, &tmA, a_full + 8 * s, kc * 64, xt * IG_TILE_W,
                       yt * IG_TILE_H);
@@ -150,11 +172,13 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         if (p.ws && tl > 0) break;
         const int nt = tile / tiles_xy;
         for (int kc = 0; kc < p.kchunks; ++kc) {
-          for (int t = 0; t < p.taps; ++t) {
+          for (int g = 0; g < groups; ++g) {
             if (!p.ws) mbar_wait(b_empty + 8 * s, ph ^ 1, p.err, 2);
             mbar_arrive_expect_tx(b_full + 8 * s, B_BYTES);
-            tma_load_2d(b_base + s * B_BYTES, &tmB, b_full + 8 * s, kc * 64,
-                        t * p.n_total + nt * N_TILE);
+#pragma unroll
+            for (int j = 0; j < TPS; ++j)
+              tma_load_2d(b_base + s * B_BYTES + j * B_TAP_BYTES, &tmB, b_full + 8 * s, kc * 64,
+                          (g * TPS + j) * p.n_total + nt * N_TILE);
             if (++s == (uint32_t)p.sb) { s = 0; ph ^= 1; }
           }
         }
@@ -166,7 +190,6 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     // in uniform registers); one elected lane issues tcgen05.mma / tcgen05.commit.
     constexpr uint32_t DESC_HI_B = (1024u >> 4) | (1u << 14) | (2u << 29);
     const uint32_t desc_hi_a = (p.a_sbo >> 4) | (1u << 14) | (2u << 29);
-    const uint32_t tap_w = p.taps == 9 ? 3u : 1u;
     const uint32_t pitch16 = (p.a_sbo >> 4);  // one patch row, in 16-byte units
     uint32_t sa_i = 0, pha = 0, sb_i = 0, phb = 0;
     int tl = 0;
@@ -174,28 +197,39 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       const uint32_t acc = tl & 1, aph = (tl >> 1) & 1;
       mbar_wait(t_empty + 8 * acc, aph ^ 1, p.err, 3);
       tc_fence_after();
+      NIND_TRACE(tl, TR_MMA_TEMPTY);
       const uint32_t d = tmem_base + acc * N_TILE;
       uint32_t accum = 0;
       for (int kc = 0; kc < p.kchunks; ++kc) {
         mbar_wait(a_full + 8 * sa_i, pha, p.err, 4);
+        if (kc == 0) NIND_TRACE(tl, TR_MMA_AFULL);
         const uint32_t a_lo0 = (((a_base + sa_i * p.a_stage_bytes) >> 4) & 0x3FFF) | (1u << 16);
-        for (uint32_t ky = 0; ky < tap_w; ++ky) {
-          for (uint32_t kx = 0; kx < tap_w; ++kx) {
-            if (!(p.ws && tl > 0)) mbar_wait(b_full + 8 * sb_i, phb, p.err, 5);
-            tc_fence_after();
-            const uint32_t a_lo = a_lo0 + ky * pitch16 + kx * 8;  // (ky*pitch + kx) rows of 128 B
-            const uint32_t b_lo = (((b_base + sb_i * B_BYTES) >> 4) & 0x3FFF) | (1u << 16);
-            if (elect_one_sync()) {
+        uint32_t ky = 0, kx = 0;  // tap of the first MMA of the group
+        for (int g = 0; g < groups; ++g) {
+          if (!(p.ws && tl > 0)) mbar_wait(b_full + 8 * sb_i, phb, p.err, 5);
+          tc_fence_after();
+          const uint32_t a_lo = a_lo0 + ky * pitch16 + kx * 8;  // (ky*pitch + kx) rows of 128 B
+          const uint32_t b_lo = (((b_base + sb_i * B_BYTES) >> 4) & 0x3FFF) | (1u << 16);
+          if (elect_one_sync()) {
+#pragma unroll
+            for (uint32_t j = 0; j < (uint32_t)TPS; ++j) {
 #pragma unroll
               for (uint32_t k = 0; k < 4; ++k) {
-                umma_bf16_lohi(d, a_lo + 2 * k, desc_hi_a, b_lo + 2 * k, DESC_HI_B, IDESC, accum);
+                umma_bf16_lohi(d, a_lo + j * 8 + 2 * k, desc_hi_a, b_lo + j * (B_TAP_BYTES >> 4) + 2 * k,
+                               DESC_HI_B, IDESC, accum);
                 accum = 1;
               }
-              if (!p.ws) umma_commit(b_empty + 8 * sb_i);
             }
-            __syncwarp();
-            accum = 1;
-            if (++sb_i == (uint32_t)p.sb) { sb_i = 0; phb ^= 1; }
+            if (!p.ws) umma_commit(b_empty + 8 * sb_i);
+          }
+          __syncwarp();
+          accum = 1;
+          if (++sb_i == (uint32_t)p.sb) { sb_i = 0; phb ^= 1; }
+          if (TPS == 3) {
+            ++ky;
+          } else if (++kx == 3) {
+            kx = 0;
+            ++ky;
           }
         }
         if (elect_one_sync()) umma_commit(a_empty + 8 * sa_i);
@@ -204,16 +238,20 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       }
       if (elect_one_sync()) umma_commit(t_full + 8 * acc);
       __syncwarp();
+      NIND_TRACE(tl, TR_MMA_DONE);
     }
   } else if (warp >= 4) {
     // ------------------------------------------------ epilogue
     const int quarter = warp & 3;
     const int etid = threadIdx.x - 128;  // 0..127 among the epilogue warps
-    float* bias_s = reinterpret_cast<float*>(smem_raw + (epi_base - smem_u32(smem_raw)));  // [2][256]
-    float* head_s = bias_s + 512;                                                          // [3][64] + [3]
+    uint8_t* smem_gen = smem_raw + (sbase - smem_u32(smem_raw));
+    float* bias_s = reinterpret_cast<float*>(smem_gen + (epi_base - sbase));  // [2][256]
+    float* head_s = bias_s + 512;                                            // [3][64] + [3]
+    uint8_t* stg = smem_gen + (stg_base - sbase) + quarter * 4096;           // this warp's 32 rows x 128 B
     if (p.epi_mode == EPI_HEAD) {
       for (int i = etid; i < 195; i += 128) head_s[i] = i < 192 ? __ldg(p.head_w + i) : __ldg(p.head_b + i - 192);
     }
+    const int n_groups = N_TILE / 64;
     int tl = 0, prev_nt = -1, bsel = 1;
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++tl) {
       const int nt = tile / tiles_xy;
@@ -239,74 +277,101 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       const int b = yflat / p.hs_in;
       const int y = yflat - b * p.hs_in;
       const bool valid = (yflat < p.rows_total) && (y < p.h_valid) && (x < p.w_valid);
+      // element offset of this thread's pixel in the destination (channel 0 of the layer's range)
+      const long long pix_off = p.epi_mode == EPI_D2S
+                                    ? b * p.o_img + (long long)(2 * y) * p.o_row + (long long)(2 * x) * p.o_pix
+                                    : b * p.o_img + (long long)y * p.o_row + (long long)x * p.o_pix;
+      // number of 64-column groups of this tile that hold real output columns
+      int live = (p.n_total - nt * N_TILE + 63) / 64;
+      live = live > n_groups ? n_groups : live;
 
       mbar_wait(t_full + 8 * acc, aph, p.err, 6);
       tc_fence_after();
+      if (quarter == 0) NIND_TRACE(tl, TR_EPI_TFULL);
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * N_TILE;
 
       float h0 = 0.f, h1 = 0.f, h2 = 0.f;
 #pragma unroll 1
-      for (int c = 0; c < N_TILE / 32; ++c) {
-        uint32_t v[32];
-        tmem_ld_32x32(taddr + c * 32, v);
-        tmem_wait_ld();
-        const int n = nt * N_TILE + c * 32;
-        if (n >= p.n_total) continue;
-        __nv_bfloat16* dst;
-        if (p.epi_mode == EPI_D2S) {
-          const int q = n / p.d2s_cout;
-          const int co = n - q * p.d2s_cout;
-          dst = p.out + b * p.o_img + (long long)(2 * y + (q >> 1)) * p.o_row +
-                (long long)(2 * x + (q & 1)) * p.o_pix + co;
-        } else {
-          dst = p.out + b * p.o_img + (long long)y * p.o_row + (long long)x * p.o_pix + n;
-        }
-        float f[32];
-        const float4* bp = reinterpret_cast<const float4*>(bias_s + bsel * 256 + c * 32);
+      for (int c64 = 0; c64 < live; ++c64) {
+        const int n = nt * N_TILE + c64 * 64;
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const float4 bb = bp[j];
-          f[4 * j + 0] = __uint_as_float(v[4 * j + 0]) + bb.x;
-          f[4 * j + 1] = __uint_as_float(v[4 * j + 1]) + bb.y;
-          f[4 * j + 2] = __uint_as_float(v[4 * j + 2]) + bb.z;
-          f[4 * j + 3] = __uint_as_float(v[4 * j + 3]) + bb.w;
-        }
-        if (p.act == ACT_PRELU) {  // also ReLU (slope 0); branch-free
-          const float sl = p.slope;
-#pragma unroll
-          for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.f) + sl * fminf(f[j], 0.f);
-        } else if (p.act == ACT_ELU) {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) f[j] = f[j] > 0.f ? f[j] : (__expf(f[j]) - 1.f);
-        } else if (p.act == ACT_HARDSWISH) {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) f[j] = f[j] * fminf(fmaxf(f[j] + 3.f, 0.f), 6.f) * (1.f / 6.f);
-        }
-        if (p.epi_mode == EPI_HEAD) {
-          const float* w0 = head_s + n;
-#pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            h0 = fmaf(f[j], w0[j], h0);
-            h1 = fmaf(f[j], w0[64 + j], h1);
-            h2 = fmaf(f[j], w0[128 + j], h2);
+        for (int half = 0; half < 2; ++half) {
+          uint32_t v[32];
+          tmem_ld_32x32(taddr + c64 * 64 + half * 32, v);
+          tmem_wait_ld();
+          if (half == 1 && c64 == live - 1) {  // accumulator fully read: hand it back to the MMA warp
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(t_empty + 8 * acc);
+            if (quarter == 0) NIND_TRACE(tl, TR_EPI_TMEM);
           }
-        } else if (valid) {
-          uint4* d4 = reinterpret_cast<uint4*>(dst);
+          float f[32];
+          const float4* bp = reinterpret_cast<const float4*>(bias_s + bsel * 256 + c64 * 64 + half * 32);
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            uint4 o;
-            o.x = pack_bf16x2(f[8 * j + 0], f[8 * j + 1]);
-            o.y = pack_bf16x2(f[8 * j + 2], f[8 * j + 3]);
-            o.z = pack_bf16x2(f[8 * j + 4], f[8 * j + 5]);
-            o.w = pack_bf16x2(f[8 * j + 6], f[8 * j + 7]);
-            d4[j] = o;
+          for (int j = 0; j < 8; ++j) {
+            const float4 bb = bp[j];
+            f[4 * j + 0] = __uint_as_float(v[4 * j + 0]) + bb.x;
+            f[4 * j + 1] = __uint_as_float(v[4 * j + 1]) + bb.y;
+            f[4 * j + 2] = __uint_as_float(v[4 * j + 2]) + bb.z;
+            f[4 * j + 3] = __uint_as_float(v[4 * j + 3]) + bb.w;
           }
+          if (p.act == ACT_PRELU) {  // also ReLU (slope 0); branch-free
+            const float sl = p.slope;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.f) + sl * fminf(f[j], 0.f);
+          } else if (p.act == ACT_ELU) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) f[j] = f[j] > 0.f ? f[j] : (__expf(f[j]) - 1.f);
+          } else if (p.act == ACT_HARDSWISH) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) f[j] = f[j] * fminf(fmaxf(f[j] + 3.f, 0.f), 6.f) * (1.f / 6.f);
+          }
+          if (p.epi_mode == EPI_HEAD) {
+            const float* w0 = head_s + half * 32;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              h0 = fmaf(f[j], w0[j], h0);
+              h1 = fmaf(f[j], w0[64 + j], h1);
+              h2 = fmaf(f[j], w0[128 + j], h2);
+            }
+          } else {
+            // this thread's row -> staging, 16-byte chunks XOR-swizzled by (row & 7): conflict-free
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              uint4 o;
+              o.x = pack_bf16x2(f[8 * j + 0], f[8 * j + 1]);
+              o.y = pack_bf16x2(f[8 * j + 2], f[8 * j + 3]);
+              o.z = pack_bf16x2(f[8 * j + 4], f[8 * j + 5]);
+              o.w = pack_bf16x2(f[8 * j + 6], f[8 * j + 7]);
+              const int chunk = half * 4 + j;
+              *reinterpret_cast<uint4*>(stg + lane * 128 + ((chunk ^ (lane & 7)) << 4)) = o;
+            }
+          }
+        }
+        if (p.epi_mode != EPI_HEAD) {
+          // coalesced write-out: 8 lanes cover one pixel's 64 channels (128 B), 4 pixels per instruction
+          long long off = pix_off;
+          if (p.epi_mode == EPI_D2S) {
+            const int q = n / p.d2s_cout;
+            off += (long long)(q >> 1) * p.o_row + (long long)(q & 1) * p.o_pix + (n - q * p.d2s_cout);
+          } else {
+            off += n;
+          }
+          __syncwarp();
+          const int sub = lane >> 3, ch = lane & 7;
+#pragma unroll
+          for (int it = 0; it < 8; ++it) {
+            const int rr = it * 4 + sub;
+            const long long roff = __shfl_sync(0xffffffffu, off, rr);
+            const int rvalid = __shfl_sync(0xffffffffu, (int)valid, rr);
+            const uint4 o = *reinterpret_cast<const uint4*>(stg + rr * 128 + ((ch ^ (rr & 7)) << 4));
+            if (rvalid) *reinterpret_cast<uint4*>(p.out + roff + ch * 8) = o;
+          }
+          __syncwarp();
         }
       }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(t_empty + 8 * acc);
 
+      if (quarter == 0) NIND_TRACE(tl, TR_EPI_DONE);
       if (p.epi_mode == EPI_HEAD) {
         const int oy = y - p.h_unpad, ox = x - p.h_unpad;
         if (valid && oy >= 0 && ox >= 0 && oy < p.h_size_y && ox < p.h_size_x) {

@@ -41,7 +41,7 @@ struct ConvSpec {
 struct IgemmLaunch {
   CUtensorMap tmA, tmB;
   IgemmParams p;
-  int n_tile = 0;
+  int n_tile = 0, tps = 1;
   size_t smem = 0;
   int grid = 0;
   double flops = 0;  // algorithmic 2*MAC actually useful (valid outputs only)
@@ -118,7 +118,8 @@ inline bool build_igemm(const ConvSpec& s, IgemmLaunch* L, std::string* why) {
   };
   if (s.taps != 9 && s.taps != 1) return fail("taps must be 1 or 9");
   if (s.cin % 64 != 0 || s.cin <= 0) return fail("input channels must be a multiple of 64");
-  if (s.n_total % 32 != 0) return fail("output columns must be a multiple of 32");
+  if (s.n_total % 64 != 0) return fail("output columns must be a multiple of 64");
+  if (s.epi_mode == EPI_D2S && (s.d2s_cout % 64 != 0)) return fail("depth-to-space needs C_out multiple of 64");
   if (s.in.c % 8 != 0) return fail("buffer channel count must be a multiple of 8");
   const int shrink = s.taps == 9 ? 2 : 0;
   IgemmParams& p = L->p;
@@ -154,26 +155,31 @@ inline bool build_igemm(const ConvSpec& s, IgemmLaunch* L, std::string* why) {
   }
 
   // pipeline depth / weights-stationary decision
-  const int kt = p.kchunks * p.taps;
+  const int tps = (s.taps == 9 && n_tile <= 128) ? 3 : 1;  // taps per weight stage
+  L->tps = tps;
+  const int kt = p.kchunks * (p.taps / tps);
   bool ws = false;
   if (s.force_ws != 0 && p.tiles_n == 1 && kt <= IG_MAX_STAGES &&
-      igemm_smem_bytes(n_tile, 2, p.a_stage_bytes, kt) <= IG_SMEM_LIMIT)
+      igemm_smem_bytes(n_tile, tps, 2, p.a_stage_bytes, kt) <= IG_SMEM_LIMIT)
     ws = true;
   if (s.force_ws == 1 && !ws) return fail("weights do not fit in shared memory");
+  auto fits = [&](int sa, int sb) { return igemm_smem_bytes(n_tile, tps, sa, p.a_stage_bytes, sb) <= IG_SMEM_LIMIT; };
   if (ws) {
     p.sb = kt;
     p.sa = 2;
-    while (p.sa < 6 && igemm_smem_bytes(n_tile, p.sa + 1, p.a_stage_bytes, p.sb) <= IG_SMEM_LIMIT) ++p.sa;
+    while (p.sa < 6 && fits(p.sa + 1, p.sb)) ++p.sa;
   } else {
-    p.sb = 4;
+    p.sb = 2;
     p.sa = 2;
-    while (p.sa < 4 && igemm_smem_bytes(n_tile, p.sa + 1, p.a_stage_bytes, p.sb) <= IG_SMEM_LIMIT) ++p.sa;
-    while (p.sb < 8 && igemm_smem_bytes(n_tile, p.sa, p.a_stage_bytes, p.sb + 1) <= IG_SMEM_LIMIT) ++p.sb;
-    if (igemm_smem_bytes(n_tile, p.sa, p.a_stage_bytes, p.sb) > IG_SMEM_LIMIT)
-      return fail("pipeline does not fit in shared memory");
+    if (!fits(p.sa, p.sb)) return fail("pipeline does not fit in shared memory");
+    const int sb_max = tps == 3 ? 4 : 8;
+    while (p.sb < (tps == 3 ? 3 : 4) && fits(p.sa, p.sb + 1)) ++p.sb;
+    while (p.sa < 3 && fits(p.sa + 1, p.sb)) ++p.sa;
+    while (p.sb < sb_max && fits(p.sa, p.sb + 1)) ++p.sb;
+    while (p.sa < 4 && fits(p.sa + 1, p.sb)) ++p.sa;
   }
   p.ws = ws ? 1 : 0;
-  L->smem = igemm_smem_bytes(n_tile, p.sa, p.a_stage_bytes, p.sb);
+  L->smem = igemm_smem_bytes(n_tile, tps, p.sa, p.a_stage_bytes, p.sb);
 
   // tensor maps
   {
@@ -217,31 +223,33 @@ inline bool build_igemm(const ConvSpec& s, IgemmLaunch* L, std::string* why) {
   return true;
 }
 
-inline cudaError_t igemm_set_attrs() {
-  static bool done = false;
-  if (done) return cudaSuccess;
-  cudaError_t e;
-  e = cudaFuncSetAttribute(igemm_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)IG_SMEM_LIMIT);
-  if (e != cudaSuccess) return e;
-  e = cudaFuncSetAttribute(igemm_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)IG_SMEM_LIMIT);
-  if (e != cudaSuccess) return e;
-  e = cudaFuncSetAttribute(igemm_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)IG_SMEM_LIMIT);
-  if (e != cudaSuccess) return e;
-  done = true;
-  return cudaSuccess;
+template <int N, int T>
+inline cudaError_t igemm_launch_t(const IgemmLaunch& L, const IgemmParams& p, cudaStream_t st) {
+  static bool attr_done = false;
+  if (!attr_done) {
+    cudaError_t e = cudaFuncSetAttribute(igemm_kernel<N, T>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)IG_SMEM_LIMIT);
+    if (e != cudaSuccess) return e;
+    attr_done = true;
+  }
+  igemm_kernel<N, T><<<L.grid, IG_THREADS, L.smem, st>>>(L.tmA, L.tmB, p);
+  return cudaGetLastError();
 }
 
-inline cudaError_t launch_igemm(const IgemmLaunch& L, int* err_flag, cudaStream_t st) {
-  cudaError_t e = igemm_set_attrs();
-  if (e != cudaSuccess) return e;
+inline cudaError_t launch_igemm(const IgemmLaunch& L, int* err_flag, cudaStream_t st,
+                                long long* trace = nullptr) {
   IgemmParams p = L.p;
   p.err = err_flag;
-  switch (L.n_tile) {
-    case 64: igemm_kernel<64><<<L.grid, IG_THREADS, L.smem, st>>>(L.tmA, L.tmB, p); break;
-    case 128: igemm_kernel<128><<<L.grid, IG_THREADS, L.smem, st>>>(L.tmA, L.tmB, p); break;
-    default: igemm_kernel<256><<<L.grid, IG_THREADS, L.smem, st>>>(L.tmA, L.tmB, p); break;
+  p.trace = trace;
+  const int key = L.n_tile * 10 + L.tps;
+  switch (key) {
+    case 641: return igemm_launch_t<64, 1>(L, p, st);
+    case 643: return igemm_launch_t<64, 3>(L, p, st);
+    case 1281: return igemm_launch_t<128, 1>(L, p, st);
+    case 1283: return igemm_launch_t<128, 3>(L, p, st);
+    case 2561: return igemm_launch_t<256, 1>(L, p, st);
+    default: return cudaErrorInvalidValue;
   }
-  return cudaGetLastError();
 }
 
 }  // namespace nind

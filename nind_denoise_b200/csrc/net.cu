@@ -598,7 +598,7 @@ int run_plan(nind_net* net, Plan* plan, const GatherParams& gsrc, float* head_ou
       GatherParams g = s.g;
       g.src = gsrc.src; g.src_img = gsrc.src_img; g.src_plane = gsrc.src_plane;
       g.src_w = gsrc.src_w; g.src_h = gsrc.src_h; g.origin = gsrc.origin;
-      gather_im2col_kernel<<<grid_for((long long)g.n_crops * g.out_h * g.out_w * 8), 256, 0, st>>>(g);
+      gather_im2col_kernel<<<grid_for((long long)g.n_crops * g.out_h * g.out_w), 256, 0, st>>>(g);
     } else if (s.kind == STEP_POOL) {
       maxpool2_kernel<<<grid_for((long long)s.pl.n * s.pl.ho * s.pl.wo * (s.pl.c / 8)), 256, 0, st>>>(s.pl);
     } else {

@@ -260,7 +260,7 @@ static int run_conv(int argc, char** argv) {
   if (!build_igemm(s, &L, &why)) { printf("build_igemm failed: %s\n", why.c_str()); return 2; }
   printf("CONV taps=%d cin=%d N=%d B=%d %dx%d a_mode=%d bo=%d epi=%d | n_tile=%d tiles=%d (x%d y%d n%d) grid=%d sa=%d sb=%d ws=%d smem=%zu\n",
          taps, cin, n_total, B, Hs, Ws, a_mode, bo_mode, epi, L.n_tile, L.p.total_tiles, L.p.tiles_x,
-         L.p.tiles_y, L.p.tiles_n, L.grid, L.p.sa, L.p.sb, L.p.ws, L.smem);
+         L.p.tiles_y, L.p.tiles_n, L.grid, L.p.sa, L.p.sb, L.p.ws, L.smem); printf("  tps=%d\n", L.tps);
 
   naive_conv_kernel<<<1024, 256>>>(din, B, Hs, Ws, Cbuf, coff, cin, dw, taps, n_total, dbias, act, slope, dref);
   CK(cudaGetLastError());
@@ -286,6 +286,22 @@ static int run_conv(int argc, char** argv) {
   CK(cudaEventElapsedTime(&ms, e0, e1));
   ms /= reps;
   printf("  time %.3f ms  -> %.1f TFLOP/s (useful)\n", ms, L.flops / ms * 1e-9);
+  if (getenv("NIND_TRACE")) {
+    long long* dtr;
+    CK(cudaMalloc(&dtr, 64 * 8 * sizeof(long long)));
+    CK(cudaMemset(dtr, 0, 64 * 8 * sizeof(long long)));
+    CK(launch_igemm(L, derr, 0, dtr));
+    CK(cudaDeviceSynchronize());
+    std::vector<long long> tr(64 * 8);
+    CK(cudaMemcpy(tr.data(), dtr, tr.size() * 8, cudaMemcpyDeviceToHost));
+    const long long t0 = tr[0];
+    printf("  trace (CTA 0, clk rel. to first A issue): tile | A_issue MMA_tempty MMA_afull MMA_done EPI_tfull EPI_tmem EPI_done\n");
+    for (int t = 0; t < 16; ++t) {
+      printf("   %2d |", t);
+      for (int e = 0; e < 7; ++e) printf(" %8lld", tr[t * 8 + e] ? tr[t * 8 + e] - t0 : -1);
+      printf("\n");
+    }
+  }
 
   std::vector<float> href((size_t)B * Hv * Wv * n_total);
   CK(cudaMemcpy(href.data(), dref, href.size() * 4, cudaMemcpyDeviceToHost));

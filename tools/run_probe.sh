@@ -17,8 +17,10 @@ run conv 9 64 64 2 60 60 0 0 2
 run conv 1 128 256 2 40 40 0 0 1
 run conv 1 256 1024 2 28 28 0 0 1
 run conv 9 64 64 4 150 150 0 0 0 64 0
+run conv 9 256 64 2 100 100 0 0 0
 run conv 1 64 64 1 506 506 0 0 0
 run conv 9 64 64 1 510 510 0 0 0
+run conv 9 64 64 1 510 510 0 0 2
 run conv 9 128 64 1 508 508 0 0 0
 run conv 9 64 128 2 252 252 0 0 0
 run conv 9 128 128 2 252 252 0 0 0
