@@ -151,8 +151,10 @@ __global__ void __launch_bounds__(256) maxpool2_kernel(const PoolParams p) {
 struct StitchParams {
   const float* crops;     // [crop_end - crop_begin][3][cs][cs] network outputs
   int crop_begin, crop_end;
-  float* out;             // [3][band rows][W], band = rows [y_begin, y_end)
-  int y_begin, y_end;
+  float* out;             // planar; row y of plane c is at out[c*out_plane + (y - out_y0)*W]
+  long long out_plane;    // band output: (y_end-y_begin)*W with out_y0 = y_begin; whole image: H*W, 0
+  int out_y0;
+  int y_begin, y_end;     // rows written
   int W, H, cs, ucs, ol, pad, stride, nx, ny;
 };
 
@@ -201,10 +203,10 @@ __global__ void __launch_bounds__(256) stitch_kernel(const StitchParams p) {
         s2 += w * __ldg(cp + 2 * plane);
       }
     }
-    const long long oplane = (long long)band_h * p.W;
-    p.out[(long long)yb * p.W + x] = s0;
-    p.out[oplane + (long long)yb * p.W + x] = s1;
-    p.out[2 * oplane + (long long)yb * p.W + x] = s2;
+    const long long o = (long long)(y - p.out_y0) * p.W + x;
+    p.out[o] = s0;
+    p.out[p.out_plane + o] = s1;
+    p.out[2 * p.out_plane + o] = s2;
   }
 }
 

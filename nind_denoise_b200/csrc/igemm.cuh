@@ -17,12 +17,13 @@
 // issuing thread pays one barrier round-trip per 12 MMAs; when the whole weight tensor of the layer
 // fits in shared memory it is loaded once per CTA and kept ("weights stationary").
 //
-// Warp roles (256 threads, 1 CTA/SM, persistent over tiles):
+// Warp roles (384 threads, 1 CTA/SM, persistent over tiles):
 //   warp 0: TMA producer for activation patches      warp 1: TMA producer for weight tiles
 //   warp 2: tcgen05.mma issuer (one elected lane)    warp 3: TMEM allocator
-//   warps 4-7: epilogue: tcgen05.ld -> bias/activation -> bf16 -> swizzled smem staging ->
-//              coalesced 16-byte global stores (4 pixels x 128 B per warp instruction);
-//              TMEM accumulators are double-buffered so the epilogue overlaps the next tile's MMAs.
+//   warps 4-7 / 8-11: two epilogue sets, one per TMEM accumulator buffer (even / odd tiles):
+//              tcgen05.ld -> bias/activation -> bf16 -> swizzled smem staging -> coalesced 16-byte
+//              global stores (8 pixels x 64 B per warp instruction); the epilogue of a tile overlaps
+//              the MMAs of the next two tiles.
 #pragma once
 #include "ptx.cuh"
 
@@ -33,9 +34,9 @@ enum ActKind : int { ACT_NONE = 0, ACT_PRELU = 1, ACT_ELU = 2, ACT_HARDSWISH = 3
 
 constexpr int IG_MAX_STAGES = 32;
 constexpr int IG_BAR_BYTES = 2048;     // mbarriers + TMEM base slot
-constexpr int IG_EPI_BYTES = 3072;     // staged bias [2][256] fp32 + head weights [3][64]+[3]
-constexpr int IG_STAGE_BYTES = 16384;  // epilogue staging: 4 warps x 32 rows x 128 B
-constexpr int IG_THREADS = 256;
+constexpr int IG_EPI_BYTES = 6144;     // per epilogue set: staged bias [2][256] fp32, head weights [3][64]+[3]
+constexpr int IG_STAGE_BYTES = 16384;  // epilogue staging: 2 sets x 4 warps x 32 rows x 64 B
+constexpr int IG_THREADS = 384;
 constexpr int IG_TILE_H = 16;
 constexpr int IG_TILE_W = 8;
 
@@ -242,24 +243,29 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     }
   } else if (warp >= 4) {
     // ------------------------------------------------ epilogue
-    const int quarter = warp & 3;
-    const int etid = threadIdx.x - 128;  // 0..127 among the epilogue warps
+    // Two independent sets of four warps: set 0 drains accumulator 0 (even tiles of this CTA), set 1
+    // accumulator 1 (odd tiles), so each set has two tile periods to finish its tile.
+    const int eset = (warp - 4) >> 2;        // 0 / 1
+    const int quarter = warp & 3;            // TMEM lane quarter this warp may read
+    const int etid = threadIdx.x - 128 - eset * 128;  // 0..127 inside the set
     uint8_t* smem_gen = smem_raw + (sbase - smem_u32(smem_raw));
-    float* bias_s = reinterpret_cast<float*>(smem_gen + (epi_base - sbase));  // [2][256]
-    float* head_s = bias_s + 512;                                            // [3][64] + [3]
-    uint8_t* stg = smem_gen + (stg_base - sbase) + quarter * 4096;           // this warp's 32 rows x 128 B
+    float* bias_s = reinterpret_cast<float*>(smem_gen + (epi_base - sbase)) + eset * 512;  // [2][256] per set
+    float* head_s = reinterpret_cast<float*>(smem_gen + (epi_base - sbase)) + 1024 + eset * 256;  // [3][64]+[3]
+    uint8_t* stg = smem_gen + (stg_base - sbase) + (eset * 4 + quarter) * 2048;  // 32 rows x 64 B
     if (p.epi_mode == EPI_HEAD) {
       for (int i = etid; i < 195; i += 128) head_s[i] = i < 192 ? __ldg(p.head_w + i) : __ldg(p.head_b + i - 192);
     }
     const int n_groups = N_TILE / 64;
-    int tl = 0, prev_nt = -1, bsel = 1;
-    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++tl) {
+    const uint32_t acc = eset;
+    int prev_nt = -1, bsel = 1;
+    uint32_t aph = 0;
+    int tl = eset;
+    for (int tile = blockIdx.x + eset * gridDim.x; tile < p.total_tiles; tile += 2 * gridDim.x, tl += 2, aph ^= 1) {
       const int nt = tile / tiles_xy;
       const int r = tile % tiles_xy;
       const int yt = r / p.tiles_x, xt = r - yt * p.tiles_x;
-      const uint32_t acc = tl & 1, aph = (tl >> 1) & 1;
 
-      if (nt != prev_nt) {  // (re)stage this N-tile's bias; uniform over the four epilogue warps
+      if (nt != prev_nt) {  // (re)stage this N-tile's bias; uniform over the four warps of the set
         prev_nt = nt;
         bsel ^= 1;
         for (int i = etid; i < N_TILE; i += 128) {
@@ -268,7 +274,8 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
           if (n < p.n_total) bv = __ldg(p.bias + (p.epi_mode == EPI_D2S ? n % p.d2s_cout : n));
           bias_s[bsel * 256 + i] = bv;
         }
-        asm volatile("bar.sync 1, 128;" ::: "memory");
+        if (eset == 0) asm volatile("bar.sync 1, 128;" ::: "memory");
+        else asm volatile("bar.sync 2, 128;" ::: "memory");
       }
 
       const int row = quarter * 32 + lane;
@@ -294,31 +301,39 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
 #pragma unroll 1
       for (int c64 = 0; c64 < live; ++c64) {
         const int n = nt * N_TILE + c64 * 64;
+        uint32_t v[2][32];
+        tmem_ld_32x32(taddr + c64 * 64, v[0]);
+        tmem_ld_32x32(taddr + c64 * 64 + 32, v[1]);
+        tmem_wait_ld();
+        if (c64 == live - 1) {  // accumulator fully read: hand it back to the MMA warp
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(t_empty + 8 * acc);
+          if (quarter == 0) NIND_TRACE(tl, TR_EPI_TMEM);
+        }
+        long long off = pix_off;
+        if (p.epi_mode == EPI_D2S) {
+          const int q = n / p.d2s_cout;
+          off += (long long)(q >> 1) * p.o_row + (long long)(q & 1) * p.o_pix + (n - q * p.d2s_cout);
+        } else {
+          off += n;
+        }
 #pragma unroll
         for (int half = 0; half < 2; ++half) {
-          uint32_t v[32];
-          tmem_ld_32x32(taddr + c64 * 64 + half * 32, v);
-          tmem_wait_ld();
-          if (half == 1 && c64 == live - 1) {  // accumulator fully read: hand it back to the MMA warp
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(t_empty + 8 * acc);
-            if (quarter == 0) NIND_TRACE(tl, TR_EPI_TMEM);
-          }
           float f[32];
           const float4* bp = reinterpret_cast<const float4*>(bias_s + bsel * 256 + c64 * 64 + half * 32);
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
             const float4 bb = bp[j];
-            f[4 * j + 0] = __uint_as_float(v[4 * j + 0]) + bb.x;
-            f[4 * j + 1] = __uint_as_float(v[4 * j + 1]) + bb.y;
-            f[4 * j + 2] = __uint_as_float(v[4 * j + 2]) + bb.z;
-            f[4 * j + 3] = __uint_as_float(v[4 * j + 3]) + bb.w;
+            f[4 * j + 0] = __uint_as_float(v[half][4 * j + 0]) + bb.x;
+            f[4 * j + 1] = __uint_as_float(v[half][4 * j + 1]) + bb.y;
+            f[4 * j + 2] = __uint_as_float(v[half][4 * j + 2]) + bb.z;
+            f[4 * j + 3] = __uint_as_float(v[half][4 * j + 3]) + bb.w;
           }
-          if (p.act == ACT_PRELU) {  // also ReLU (slope 0); branch-free
+          if (p.act == ACT_PRELU) {  // also ReLU (slope 0)
             const float sl = p.slope;
 #pragma unroll
-            for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.f) + sl * fminf(f[j], 0.f);
+            for (int j = 0; j < 32; ++j) f[j] = f[j] > 0.f ? f[j] : f[j] * sl;
           } else if (p.act == ACT_ELU) {
 #pragma unroll
             for (int j = 0; j < 32; ++j) f[j] = f[j] > 0.f ? f[j] : (__expf(f[j]) - 1.f);
@@ -335,7 +350,8 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
               h2 = fmaf(f[j], w0[128 + j], h2);
             }
           } else {
-            // this thread's row -> staging, 16-byte chunks XOR-swizzled by (row & 7): conflict-free
+            // this thread's 32 channels (64 B) -> staging row; 16-byte chunks XOR-swizzled so that both
+            // the row-wise writes and the pixel-wise reads below are bank-conflict free
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
               uint4 o;
@@ -343,34 +359,23 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
               o.y = pack_bf16x2(f[8 * j + 2], f[8 * j + 3]);
               o.z = pack_bf16x2(f[8 * j + 4], f[8 * j + 5]);
               o.w = pack_bf16x2(f[8 * j + 6], f[8 * j + 7]);
-              const int chunk = half * 4 + j;
-              *reinterpret_cast<uint4*>(stg + lane * 128 + ((chunk ^ (lane & 7)) << 4)) = o;
+              *reinterpret_cast<uint4*>(stg + lane * 64 + ((j ^ ((lane >> 1) & 3)) << 4)) = o;
             }
-          }
-        }
-        if (p.epi_mode != EPI_HEAD) {
-          // coalesced write-out: 8 lanes cover one pixel's 64 channels (128 B), 4 pixels per instruction
-          long long off = pix_off;
-          if (p.epi_mode == EPI_D2S) {
-            const int q = n / p.d2s_cout;
-            off += (long long)(q >> 1) * p.o_row + (long long)(q & 1) * p.o_pix + (n - q * p.d2s_cout);
-          } else {
-            off += n;
-          }
-          __syncwarp();
-          const int sub = lane >> 3, ch = lane & 7;
+            __syncwarp();
+            // coalesced write-out: 4 lanes cover one pixel's 32 channels (64 B), 8 pixels per instruction
+            const int sub = lane >> 2, ch = lane & 3;
 #pragma unroll
-          for (int it = 0; it < 8; ++it) {
-            const int rr = it * 4 + sub;
-            const long long roff = __shfl_sync(0xffffffffu, off, rr);
-            const int rvalid = __shfl_sync(0xffffffffu, (int)valid, rr);
-            const uint4 o = *reinterpret_cast<const uint4*>(stg + rr * 128 + ((ch ^ (rr & 7)) << 4));
-            if (rvalid) *reinterpret_cast<uint4*>(p.out + roff + ch * 8) = o;
+            for (int it = 0; it < 4; ++it) {
+              const int rr = it * 8 + sub;
+              const long long roff = __shfl_sync(0xffffffffu, off, rr);
+              const int rvalid = __shfl_sync(0xffffffffu, (int)valid, rr);
+              const uint4 o = *reinterpret_cast<const uint4*>(stg + rr * 64 + ((ch ^ ((rr >> 1) & 3)) << 4));
+              if (rvalid) *reinterpret_cast<uint4*>(p.out + roff + half * 32 + ch * 8) = o;
+            }
+            __syncwarp();
           }
-          __syncwarp();
         }
       }
-
       if (quarter == 0) NIND_TRACE(tl, TR_EPI_DONE);
       if (p.epi_mode == EPI_HEAD) {
         const int oy = y - p.h_unpad, ox = x - p.h_unpad;

@@ -116,6 +116,8 @@ struct nind_net {
   float* img_dev = nullptr;
   float* out_dev = nullptr;
   size_t img_cap = 0, out_cap = 0;
+  cudaStream_t s_in = nullptr, s_comp = nullptr, s_out = nullptr;
+  std::vector<cudaEvent_t> ev_in, ev_done;
   // options
   int n_tile_deep = 256, max_ctas = 0;
   // timing
@@ -142,6 +144,9 @@ struct nind_net {
     cudaFree(origin_buf);
     cudaFree(img_dev);
     cudaFree(out_dev);
+    for (auto e : ev_in) cudaEventDestroy(e);
+    for (auto e : ev_done) cudaEventDestroy(e);
+    if (s_in) { cudaStreamDestroy(s_in); cudaStreamDestroy(s_comp); cudaStreamDestroy(s_out); }
   }
 };
 
@@ -786,18 +791,20 @@ static int upload_origins(nind_net* net, const GridGeom& g, int crop_begin, int 
   return 0;
 }
 
-static int launch_stitch(const GridGeom& g, const float* crops, int crop_begin, int crop_end, float* out_band,
-                         int* band_y0, int* band_y1, cudaStream_t st) {
+// Stitch rows [y0, y1) from `crops` (outputs of crops [crop_begin, crop_end)) into `out`.
+// whole_image: `out` is the full [3][H][W] image; else a dense band [3][y1-y0][W].
+static int launch_stitch(const GridGeom& g, const float* crops, int crop_begin, int crop_end, float* out,
+                         int y0, int y1, bool whole_image, cudaStream_t st) {
   StitchParams sp;
-  sp.crops = crops; sp.crop_begin = crop_begin; sp.crop_end = crop_end; sp.out = out_band;
-  band_of(g, crop_begin, crop_end, &sp.y_begin, &sp.y_end);
+  sp.crops = crops; sp.crop_begin = crop_begin; sp.crop_end = crop_end; sp.out = out;
+  sp.y_begin = y0; sp.y_end = y1;
+  sp.out_plane = whole_image ? (long long)g.H * g.W : (long long)(y1 - y0) * g.W;
+  sp.out_y0 = whole_image ? 0 : y0;
   sp.W = g.W; sp.H = g.H; sp.cs = g.cs; sp.ucs = g.ucs; sp.ol = g.ol; sp.pad = g.pad; sp.stride = g.stride;
   sp.nx = g.nx; sp.ny = g.ny;
-  stitch_kernel<<<grid_for((long long)(sp.y_end - sp.y_begin) * g.W), 256, 0, st>>>(sp);
+  stitch_kernel<<<grid_for((long long)(y1 - y0) * g.W), 256, 0, st>>>(sp);
   ++g_launches;
   CUDA_TRY(cudaGetLastError());
-  if (band_y0) *band_y0 = sp.y_begin;
-  if (band_y1) *band_y1 = sp.y_end;
   return 0;
 }
 
@@ -832,7 +839,11 @@ int nind_stitch_crops(const float* crops, int height, int width, int cs, int ucs
   GridGeom g;
   int rc;
   if ((rc = check_range(width, height, cs, ucs, ol, crop_begin, crop_end, &g))) return rc;
-  return launch_stitch(g, crops, crop_begin, crop_end, out_band, band_y0, band_y1, static_cast<cudaStream_t>(stream));
+  int y0, y1;
+  band_of(g, crop_begin, crop_end, &y0, &y1);
+  if (band_y0) *band_y0 = y0;
+  if (band_y1) *band_y1 = y1;
+  return launch_stitch(g, crops, crop_begin, crop_end, out_band, y0, y1, false, static_cast<cudaStream_t>(stream));
 }
 
 int nind_tiled_denoise(nind_net* net, const float* img_chw, float* out_band, int height, int width,
@@ -859,26 +870,83 @@ int nind_tiled_denoise(nind_net* net, const float* img_chw, float* out_band, int
     gp.origin = net->origin_buf + i0;
     if ((rc = run_plan(net, plan, gp, net->crops_buf + (size_t)i0 * 3 * cs * cs, st))) return rc;
   }
-  return launch_stitch(g, net->crops_buf, crop_begin, crop_end, out_band, band_y0, band_y1, st);
+  int y0, y1;
+  band_of(g, crop_begin, crop_end, &y0, &y1);
+  if (band_y0) *band_y0 = y0;
+  if (band_y1) *band_y1 = y1;
+  return launch_stitch(g, net->crops_buf, crop_begin, crop_end, out_band, y0, y1, false, st);
 }
 
 int nind_tiled_denoise_host(nind_net* net, const float* img_chw_host, float* out_chw_host, int height,
                             int width, int cs, int ucs, int ol, int batch) {
+  // Pipelined over grid rows of crops: the H2D copy of the image rows a grid row needs, the forward
+  // of its crops, the stitch of the output rows it completes and their D2H copy run on three
+  // streams, so PCIe traffic hides behind compute when the host buffers are pinned.
   if (!net || !img_chw_host || !out_chw_host) return fail(NIND_E_INVALID, "null argument");
+  if (batch <= 0) return fail(NIND_E_INVALID, "batch must be positive");
   GridGeom g;
   if (!make_grid(width, height, cs, ucs, ol, &g)) return fail(NIND_E_INVALID, "illegal crop geometry");
-  const size_t bytes = (size_t)3 * height * width * sizeof(float);
+  const size_t plane = (size_t)height * width;
+  const size_t bytes = 3 * plane * sizeof(float);
   int rc;
   if ((rc = ensure(reinterpret_cast<void**>(&net->img_dev), &net->img_cap, bytes))) return rc;
   if ((rc = ensure(reinterpret_cast<void**>(&net->out_dev), &net->out_cap, bytes))) return rc;
-  CUDA_TRY(cudaMemcpyAsync(net->img_dev, img_chw_host, bytes, cudaMemcpyHostToDevice, 0));
-  int y0 = 0, y1 = 0;
-  if ((rc = nind_tiled_denoise(net, net->img_dev, net->out_dev, height, width, cs, ucs, ol, 0, g.size(), batch,
-                               &y0, &y1, nullptr)))
+  const int n = g.size();
+  if ((rc = ensure(reinterpret_cast<void**>(&net->crops_buf), &net->crops_cap, (size_t)n * 3 * cs * cs * sizeof(float))))
     return rc;
-  if (y0 != 0 || y1 != height) return fail(NIND_E_INVALID, "internal: full crop range does not cover the image");
-  CUDA_TRY(cudaMemcpyAsync(out_chw_host, net->out_dev, bytes, cudaMemcpyDeviceToHost, 0));
-  CUDA_TRY(cudaStreamSynchronize(0));
+  if (!net->s_in) {
+    CUDA_TRY(cudaStreamCreateWithFlags(&net->s_in, cudaStreamNonBlocking));
+    CUDA_TRY(cudaStreamCreateWithFlags(&net->s_comp, cudaStreamNonBlocking));
+    CUDA_TRY(cudaStreamCreateWithFlags(&net->s_out, cudaStreamNonBlocking));
+  }
+  while ((int)net->ev_in.size() < g.ny) {
+    cudaEvent_t a, b;
+    CUDA_TRY(cudaEventCreateWithFlags(&a, cudaEventDisableTiming));
+    CUDA_TRY(cudaEventCreateWithFlags(&b, cudaEventDisableTiming));
+    net->ev_in.push_back(a);
+    net->ev_done.push_back(b);
+  }
+  if ((rc = upload_origins(net, g, 0, n, net->s_comp))) return rc;
+  // H2D: rows each grid row newly needs (planar image -> one 2-D copy of 3 plane segments)
+  int uploaded = 0;
+  for (int yi = 0; yi < g.ny; ++yi) {
+    const int need = std::min(height, g.stride * yi - g.pad + cs);
+    const int upto = yi == g.ny - 1 ? height : std::max(uploaded, need);
+    if (upto > uploaded) {
+      const size_t off = (size_t)uploaded * width;
+      CUDA_TRY(cudaMemcpy2DAsync(net->img_dev + off, plane * sizeof(float), img_chw_host + off, plane * sizeof(float),
+                                 (size_t)(upto - uploaded) * width * sizeof(float), 3, cudaMemcpyHostToDevice,
+                                 net->s_in));
+      uploaded = upto;
+    }
+    CUDA_TRY(cudaEventRecord(net->ev_in[yi], net->s_in));
+  }
+  for (int yi = 0; yi < g.ny; ++yi) {
+    CUDA_TRY(cudaStreamWaitEvent(net->s_comp, net->ev_in[yi], 0));
+    for (int i0 = yi * g.nx; i0 < (yi + 1) * g.nx; i0 += batch) {
+      const int b = std::min(batch, (yi + 1) * g.nx - i0);
+      Plan* plan = nullptr;
+      if ((rc = get_plan(net, b, cs, cs, &plan))) return rc;
+      GatherParams gp;
+      memset(&gp, 0, sizeof gp);
+      gp.src = net->img_dev; gp.src_img = 0; gp.src_plane = (long long)plane; gp.src_w = width; gp.src_h = height;
+      gp.origin = net->origin_buf + i0;
+      if ((rc = run_plan(net, plan, gp, net->crops_buf + (size_t)i0 * 3 * cs * cs, net->s_comp))) return rc;
+    }
+    // output rows completed by this grid row: every crop that touches them has index < (yi+1)*nx
+    const int r0 = g.stride * yi;
+    const int r1 = yi == g.ny - 1 ? height : std::min(height, g.stride * (yi + 1));
+    if (r1 > r0) {
+      if ((rc = launch_stitch(g, net->crops_buf, 0, n, net->out_dev, r0, r1, true, net->s_comp))) return rc;
+      CUDA_TRY(cudaEventRecord(net->ev_done[yi], net->s_comp));
+      CUDA_TRY(cudaStreamWaitEvent(net->s_out, net->ev_done[yi], 0));
+      const size_t off = (size_t)r0 * width;
+      CUDA_TRY(cudaMemcpy2DAsync(out_chw_host + off, plane * sizeof(float), net->out_dev + off, plane * sizeof(float),
+                                 (size_t)(r1 - r0) * width * sizeof(float), 3, cudaMemcpyDeviceToHost, net->s_out));
+    }
+  }
+  CUDA_TRY(cudaStreamSynchronize(net->s_out));
+  CUDA_TRY(cudaStreamSynchronize(net->s_comp));
   return check_err_flag(net);
 }
 
