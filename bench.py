@@ -197,7 +197,7 @@ def main():
     n = nb.n_crops(W_IMG, H_IMG, cs, ucs, ol)
     ranges = nb.shard_ranges(n, world)
     cb, ce = ranges[rank]
-    batch = args.batch or default_batch(ce - cb, cs)
+    batch = args.batch or default_batch(ce - cb, cs, -(-(W_IMG - ucs) // (ucs - ol)) + 1)
     lib = _capi.lib()
 
     def step():

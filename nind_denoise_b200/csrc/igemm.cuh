@@ -62,6 +62,10 @@ struct IgemmParams {
   long long o_img, o_row;  // element strides
   int o_pix;
   int d2s_cout;            // EPI_D2S: channels per sub-pixel
+  // EPI_STORE only: fused nn.MaxPool2d(2) of the stored tensor (UtNet.py:34,100-103) into a second buffer
+  __nv_bfloat16* pool_out; // already offset by halo; null = no pooling
+  long long pl_img, pl_row;
+  int pl_pix;
   // EPI_HEAD: 1x1 conv to 3 channels (+ optional sigmoid), fp32 planar output
   const float* head_w;     // [3][64]
   const float* head_b;     // [3]
@@ -83,21 +87,29 @@ enum { TR_A_ISSUE = 0, TR_MMA_TEMPTY = 1, TR_MMA_AFULL = 2, TR_MMA_DONE = 3, TR_
     if (p.trace && blockIdx.x == 0 && (tl) < 64 && lane == 0) p.trace[(tl) * 8 + (ev)] = clock64(); \
   } while (0)
 
-__host__ __device__ inline size_t igemm_smem_bytes(int n_tile, int tps, int sa, uint32_t a_stage_bytes, int sb) {
-  return 1024 + (size_t)sa * a_stage_bytes + (size_t)sb * tps * n_tile * 128 + IG_BAR_BYTES + IG_EPI_BYTES +
-         IG_STAGE_BYTES;
+__host__ __device__ inline size_t igemm_smem_bytes(int n_tile, int tps, int cg, int sa, uint32_t a_stage_bytes,
+                                                   int sb) {
+  return 1024 + (size_t)sa * a_stage_bytes + (size_t)sb * tps * (n_tile / cg) * 128 + IG_BAR_BYTES +
+         IG_EPI_BYTES + IG_STAGE_BYTES;
 }
 
-// N_TILE: GEMM N per CTA tile (64/128/256).  TPS: taps per weight pipeline stage (1 or 3).
-template <int N_TILE, int TPS>
+// N_TILE: GEMM N per tile (64/128/256).  TPS: taps per weight pipeline stage (1 or 3).
+// CG: 1 = one CTA per tile; 2 = CTA pair (cluster of 2, tcgen05 cta_group::2): the pair computes two
+// x-adjacent 16x8 pixel tiles as one M=256 MMA, each CTA holding its own activation patch and HALF of
+// the weight tile (N_TILE/2 rows), which halves the weight shared-memory reads and L2 traffic per SM.
+// In a pair all "full" barriers and the TMEM-empty barriers live in CTA 0 (the leader, which issues
+// the MMAs); "empty" / TMEM-full barriers are per CTA and signalled by multicast commits.
+template <int N_TILE, int TPS, int CG>
 __global__ void __launch_bounds__(IG_THREADS, 1)
 igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
              const IgemmParams p) {
   extern __shared__ uint8_t smem_raw[];
-  constexpr uint32_t B_TAP_BYTES = N_TILE * 128;
+  constexpr uint32_t B_ROWS = N_TILE / CG;           // weight rows held by this CTA
+  constexpr uint32_t B_TAP_BYTES = B_ROWS * 128;
   constexpr uint32_t B_BYTES = TPS * B_TAP_BYTES;
   constexpr uint32_t TMEM_COLS = 2 * N_TILE;
-  constexpr uint32_t IDESC = umma_idesc_bf16(128, N_TILE);
+  constexpr uint32_t IDESC = umma_idesc_bf16(128 * CG, N_TILE);
+  const uint32_t cg_rank = CG == 2 ? cluster_ctarank() : 0u;
 
   const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t a_base = sbase;
@@ -129,37 +141,52 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(t_full + 8 * s, 1);
-      mbar_init(t_empty + 8 * s, 4);
+      mbar_init(t_empty + 8 * s, 4 * CG);
     }
     mbar_fence_init();
   }
   if (warp == 3) {
-    tmem_alloc(tmem_slot, TMEM_COLS);
-    tmem_relinquish();
+    if (CG == 2) {
+      tmem_alloc_cg2(tmem_slot, TMEM_COLS);
+      tmem_relinquish_cg2();
+    } else {
+      tmem_alloc(tmem_slot, TMEM_COLS);
+      tmem_relinquish();
+    }
   }
   tc_fence_before();
-  __syncthreads();
+  if (CG == 2) cluster_sync_all();
+  else __syncthreads();
   tc_fence_after();
   uint32_t tmem_base;
   asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
 
+  // p.tiles_x / p.total_tiles count (super-)tiles: CG x-adjacent 16x8 pixel tiles each
   const int tiles_xy = p.tiles_x * p.tiles_y;
   const int groups = p.taps / TPS;  // weight stages per 64-channel chunk
+  const int tile0 = blockIdx.x / CG, tstep = gridDim.x / CG;
 
   if (warp == 0) {
     // ------------------------------------------------ activation-patch producer
     if (lane == 0) {
       uint32_t s = 0, ph = 0;
       int tl = 0;
-      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++tl) {
+      for (int tile = tile0; tile < p.total_tiles; tile += tstep, ++tl) {
         const int r = tile % tiles_xy;
-        const int yt = r / p.tiles_x, xt = r - yt * p.tiles_x;
+        const int yt = r / p.tiles_x, xt = (r - yt * p.tiles_x) * CG + (int)cg_rank;
         for (int kc = 0; kc < p.kchunks; ++kc) {
           mbar_wait(a_empty + 8 * s, ph ^ 1, p.err, 1);
           if (kc == 0) NIND_TRACE(tl, TR_A_ISSUE);
-          mbar_arrive_expect_tx(a_full + 8 * s, p.a_tx_bytes);
-          tma_load_3d(a_base + s * p.a_stage_bytes, &tmA, a_full + 8 * s, kc * 64, xt * IG_TILE_W,
-                      yt * IG_TILE_H);
+          if (CG == 2) {
+            // both CTAs' patches complete on the leader's barrier; only the leader arms it
+            if (cg_rank == 0) mbar_arrive_expect_tx(a_full + 8 * s, 2 * p.a_tx_bytes);
+            tma_load_3d_cg2(a_base + s * p.a_stage_bytes, &tmA, mapa_shared(a_full + 8 * s, 0), kc * 64,
+                            xt * IG_TILE_W, yt * IG_TILE_H);
+          } else {
+            mbar_arrive_expect_tx(a_full + 8 * s, p.a_tx_bytes);
+            tma_load_3d(a_base + s * p.a_stage_bytes, &tmA, a_full + 8 * s, kc * 64, xt * IG_TILE_W,
+                        yt * IG_TILE_H);
+          }
           if (++s == (uint32_t)p.sa) { s = 0; ph ^= 1; }
         }
       }
@@ -169,24 +196,33 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     if (lane == 0) {
       uint32_t s = 0, ph = 0;
       int tl = 0;
-      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++tl) {
+      for (int tile = tile0; tile < p.total_tiles; tile += tstep, ++tl) {
         if (p.ws && tl > 0) break;
         const int nt = tile / tiles_xy;
         for (int kc = 0; kc < p.kchunks; ++kc) {
           for (int g = 0; g < groups; ++g) {
             if (!p.ws) mbar_wait(b_empty + 8 * s, ph ^ 1, p.err, 2);
-            mbar_arrive_expect_tx(b_full + 8 * s, B_BYTES);
+            if (CG == 2) {
+              if (cg_rank == 0) mbar_arrive_expect_tx(b_full + 8 * s, 2 * B_BYTES);
+              const uint32_t bar = mapa_shared(b_full + 8 * s, 0);
 #pragma unroll
-            for (int j = 0; j < TPS; ++j)
-              tma_load_2d(b_base + s * B_BYTES + j * B_TAP_BYTES, &tmB, b_full + 8 * s, kc * 64,
-                          (g * TPS + j) * p.n_total + nt * N_TILE);
+              for (int j = 0; j < TPS; ++j)
+                tma_load_2d_cg2(b_base + s * B_BYTES + j * B_TAP_BYTES, &tmB, bar, kc * 64,
+                                (g * TPS + j) * p.n_total + nt * N_TILE + (int)(cg_rank * B_ROWS));
+            } else {
+              mbar_arrive_expect_tx(b_full + 8 * s, B_BYTES);
+#pragma unroll
+              for (int j = 0; j < TPS; ++j)
+                tma_load_2d(b_base + s * B_BYTES + j * B_TAP_BYTES, &tmB, b_full + 8 * s, kc * 64,
+                            (g * TPS + j) * p.n_total + nt * N_TILE);
+            }
             if (++s == (uint32_t)p.sb) { s = 0; ph ^= 1; }
           }
         }
       }
     }
-  } else if (warp == 2) {
-    // ------------------------------------------------ MMA issuer
+  } else if (warp == 2 && cg_rank == 0) {
+    // ------------------------------------------------ MMA issuer (leader CTA only in a pair)
     // The whole warp walks the loop (warp-uniform control flow and addresses, so descriptors live
     // in uniform registers); one elected lane issues tcgen05.mma / tcgen05.commit.
     constexpr uint32_t DESC_HI_B = (1024u >> 4) | (1u << 14) | (2u << 29);
@@ -194,7 +230,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     const uint32_t pitch16 = (p.a_sbo >> 4);  // one patch row, in 16-byte units
     uint32_t sa_i = 0, pha = 0, sb_i = 0, phb = 0;
     int tl = 0;
-    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++tl) {
+    for (int tile = tile0; tile < p.total_tiles; tile += tstep, ++tl) {
       const uint32_t acc = tl & 1, aph = (tl >> 1) & 1;
       mbar_wait(t_empty + 8 * acc, aph ^ 1, p.err, 3);
       tc_fence_after();
@@ -216,12 +252,19 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
             for (uint32_t j = 0; j < (uint32_t)TPS; ++j) {
 #pragma unroll
               for (uint32_t k = 0; k < 4; ++k) {
-                umma_bf16_lohi(d, a_lo + j * 8 + 2 * k, desc_hi_a, b_lo + j * (B_TAP_BYTES >> 4) + 2 * k,
-                               DESC_HI_B, IDESC, accum);
+                if (CG == 2)
+                  umma_bf16_lohi_cg2(d, a_lo + j * 8 + 2 * k, desc_hi_a, b_lo + j * (B_TAP_BYTES >> 4) + 2 * k,
+                                     DESC_HI_B, IDESC, accum);
+                else
+                  umma_bf16_lohi(d, a_lo + j * 8 + 2 * k, desc_hi_a, b_lo + j * (B_TAP_BYTES >> 4) + 2 * k,
+                                 DESC_HI_B, IDESC, accum);
                 accum = 1;
               }
             }
-            if (!p.ws) umma_commit(b_empty + 8 * sb_i);
+            if (!p.ws) {
+              if (CG == 2) umma_commit_cg2(b_empty + 8 * sb_i);
+              else umma_commit(b_empty + 8 * sb_i);
+            }
           }
           __syncwarp();
           accum = 1;
@@ -233,11 +276,17 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
             ++ky;
           }
         }
-        if (elect_one_sync()) umma_commit(a_empty + 8 * sa_i);
+        if (elect_one_sync()) {
+          if (CG == 2) umma_commit_cg2(a_empty + 8 * sa_i);
+          else umma_commit(a_empty + 8 * sa_i);
+        }
         __syncwarp();
         if (++sa_i == (uint32_t)p.sa) { sa_i = 0; pha ^= 1; }
       }
-      if (elect_one_sync()) umma_commit(t_full + 8 * acc);
+      if (elect_one_sync()) {
+        if (CG == 2) umma_commit_cg2(t_full + 8 * acc);
+        else umma_commit(t_full + 8 * acc);
+      }
       __syncwarp();
       NIND_TRACE(tl, TR_MMA_DONE);
     }
@@ -260,10 +309,11 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     int prev_nt = -1, bsel = 1;
     uint32_t aph = 0;
     int tl = eset;
-    for (int tile = blockIdx.x + eset * gridDim.x; tile < p.total_tiles; tile += 2 * gridDim.x, tl += 2, aph ^= 1) {
+    const uint32_t t_empty_addr = CG == 2 ? mapa_shared(t_empty + 8 * acc, 0) : (t_empty + 8 * acc);
+    for (int tile = tile0 + eset * tstep; tile < p.total_tiles; tile += 2 * tstep, tl += 2, aph ^= 1) {
       const int nt = tile / tiles_xy;
       const int r = tile % tiles_xy;
-      const int yt = r / p.tiles_x, xt = r - yt * p.tiles_x;
+      const int yt = r / p.tiles_x, xt = (r - yt * p.tiles_x) * CG + (int)cg_rank;
 
       if (nt != prev_nt) {  // (re)stage this N-tile's bias; uniform over the four warps of the set
         prev_nt = nt;
@@ -288,6 +338,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       const long long pix_off = p.epi_mode == EPI_D2S
                                     ? b * p.o_img + (long long)(2 * y) * p.o_row + (long long)(2 * x) * p.o_pix
                                     : b * p.o_img + (long long)y * p.o_row + (long long)x * p.o_pix;
+      const long long pool_off = b * p.pl_img + (long long)(y >> 1) * p.pl_row + (long long)(x >> 1) * p.pl_pix;
       // number of 64-column groups of this tile that hold real output columns
       int live = (p.n_total - nt * N_TILE + 63) / 64;
       live = live > n_groups ? n_groups : live;
@@ -308,7 +359,10 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         if (c64 == live - 1) {  // accumulator fully read: hand it back to the MMA warp
           tc_fence_before();
           __syncwarp();
-          if (lane == 0) mbar_arrive(t_empty + 8 * acc);
+          if (lane == 0) {
+            if (CG == 2) mbar_arrive_cluster(t_empty_addr);
+            else mbar_arrive(t_empty_addr);
+          }
           if (quarter == 0) NIND_TRACE(tl, TR_EPI_TMEM);
         }
         long long off = pix_off;
@@ -372,6 +426,26 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
               const uint4 o = *reinterpret_cast<const uint4*>(stg + rr * 64 + ((ch ^ ((rr >> 1) & 3)) << 4));
               if (rvalid) *reinterpret_cast<uint4*>(p.out + roff + half * 32 + ch * 8) = o;
             }
+            if (p.pool_out) {
+              // fused 2x2 max-pool: this warp's 32 rows are 4 tile rows x 8 pixels = 2 x 4 pooled pixels;
+              // lane -> (pooled pixel, 16-byte chunk); tile origins and map sizes are even, so the
+              // validity of the top-left source pixel covers all four
+              const int pp = lane >> 2;
+              const int r00 = (pp >> 2) * 16 + (pp & 3) * 2;
+              const long long poff = __shfl_sync(0xffffffffu, pool_off, r00);
+              const int pvalid = __shfl_sync(0xffffffffu, (int)valid, r00);
+              uint4 m = *reinterpret_cast<const uint4*>(stg + r00 * 64 + ((ch ^ ((r00 >> 1) & 3)) << 4));
+              const int rs[3] = {r00 + 1, r00 + 8, r00 + 9};
+#pragma unroll
+              for (int k = 0; k < 3; ++k) {
+                const uint4 t = *reinterpret_cast<const uint4*>(stg + rs[k] * 64 + ((ch ^ ((rs[k] >> 1) & 3)) << 4));
+                __nv_bfloat162* pm = reinterpret_cast<__nv_bfloat162*>(&m);
+                const __nv_bfloat162* pt = reinterpret_cast<const __nv_bfloat162*>(&t);
+#pragma unroll
+                for (int e = 0; e < 4; ++e) pm[e] = __hmax2(pm[e], pt[e]);
+              }
+              if (pvalid) *reinterpret_cast<uint4*>(p.pool_out + poff + n + half * 32 + ch * 8) = m;
+            }
             __syncwarp();
           }
         }
@@ -396,8 +470,13 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
   }
 
   tc_fence_before();
-  __syncthreads();
-  if (warp == 3) tmem_dealloc(tmem_base, TMEM_COLS);
+  if (CG == 2) {
+    cluster_sync_all();  // the peer's smem / TMEM / barriers stay alive until both CTAs are done
+    if (warp == 3) tmem_dealloc_cg2(tmem_base, TMEM_COLS);
+  } else {
+    __syncthreads();
+    if (warp == 3) tmem_dealloc(tmem_base, TMEM_COLS);
+  }
 }
 
 }  // namespace nind

@@ -1,6 +1,7 @@
 // Host side of the implicit-GEMM kernel: tensor-map encoding, tiling/pipeline choices, launch.
 #pragma once
 #include <cstdio>
+#include <algorithm>
 #include <cstring>
 #include <string>
 #include "igemm.cuh"
@@ -27,6 +28,8 @@ struct ConvSpec {
   ActBuf out;  // EPI_STORE / EPI_D2S destination
   int out_coff = 0, out_halo = 0;
   int d2s_cout = 0;
+  ActBuf pool;  // optional fused 2x2 max-pool destination (EPI_STORE), written at halo pool_halo, channel 0
+  int pool_halo = 0;
   // EPI_HEAD
   const float* head_w = nullptr;
   const float* head_b = nullptr;
@@ -34,6 +37,7 @@ struct ConvSpec {
   int head_unpad = 0, head_hy = 0, head_hx = 0, head_sigmoid = 0;
   // tuning
   int n_tile = 0;     // 0 = auto
+  int cg = 0;         // CTAs per tile group: 0 = auto, 1, or 2 (cta_group::2 pair)
   int force_ws = -1;  // -1 = auto
   int max_ctas = 0;   // 0 = number of SMs
 };
@@ -41,7 +45,7 @@ struct ConvSpec {
 struct IgemmLaunch {
   CUtensorMap tmA, tmB;
   IgemmParams p;
-  int n_tile = 0, tps = 1;
+  int n_tile = 0, tps = 1, cg = 1;
   size_t smem = 0;
   int grid = 0;
   double flops = 0;  // algorithmic 2*MAC actually useful (valid outputs only)
@@ -135,7 +139,17 @@ inline bool build_igemm(const ConvSpec& s, IgemmLaunch* L, std::string* why) {
   p.h_valid = s.in.hs - shrink;
   p.hs_in = s.in.hs;
   p.rows_total = s.in.b * s.in.hs;
-  p.tiles_x = (p.w_valid + IG_TILE_W - 1) / IG_TILE_W;
+  const int tiles_x_real = (p.w_valid + IG_TILE_W - 1) / IG_TILE_W;
+  int cg = s.cg;
+  // measured on B200 (profiles/r01_probe_cta_pair.log): the CTA pair wins on every 3x3 layer except
+  // 64->128 (-3 %), and on the 1x1 / 2x2-s2 GEMMs only when K is large (C_in >= 512)
+  if (cg == 0) {
+    const bool pair = s.taps == 9 ? (s.cin >= 128 || s.n_total <= 64) : (s.cin >= 512);
+    cg = (pair && tiles_x_real >= 2) ? 2 : 1;
+  }
+  if (cg != 1 && cg != 2) return fail("cg must be 1 or 2");
+  L->cg = cg;
+  p.tiles_x = (tiles_x_real + cg - 1) / cg;  // (super-)tiles: cg x-adjacent 16x8 tiles
   p.tiles_y = (p.rows_total - shrink + IG_TILE_H - 1) / IG_TILE_H;
   p.tiles_n = (s.n_total + n_tile - 1) / n_tile;
   p.total_tiles = p.tiles_x * p.tiles_y * p.tiles_n;
@@ -160,10 +174,12 @@ inline bool build_igemm(const ConvSpec& s, IgemmLaunch* L, std::string* why) {
   const int kt = p.kchunks * (p.taps / tps);
   bool ws = false;
   if (s.force_ws != 0 && p.tiles_n == 1 && kt <= IG_MAX_STAGES &&
-      igemm_smem_bytes(n_tile, tps, 2, p.a_stage_bytes, kt) <= IG_SMEM_LIMIT)
+      igemm_smem_bytes(n_tile, tps, cg, 2, p.a_stage_bytes, kt) <= IG_SMEM_LIMIT)
     ws = true;
   if (s.force_ws == 1 && !ws) return fail("weights do not fit in shared memory");
-  auto fits = [&](int sa, int sb) { return igemm_smem_bytes(n_tile, tps, sa, p.a_stage_bytes, sb) <= IG_SMEM_LIMIT; };
+  auto fits = [&](int sa, int sb) {
+    return igemm_smem_bytes(n_tile, tps, cg, sa, p.a_stage_bytes, sb) <= IG_SMEM_LIMIT;
+  };
   if (ws) {
     p.sb = kt;
     p.sa = 2;
@@ -179,7 +195,7 @@ inline bool build_igemm(const ConvSpec& s, IgemmLaunch* L, std::string* why) {
     while (p.sa < 4 && fits(p.sa + 1, p.sb)) ++p.sa;
   }
   p.ws = ws ? 1 : 0;
-  L->smem = igemm_smem_bytes(n_tile, tps, p.sa, p.a_stage_bytes, p.sb);
+  L->smem = igemm_smem_bytes(n_tile, tps, cg, p.sa, p.a_stage_bytes, p.sb);
 
   // tensor maps
   {
@@ -188,7 +204,7 @@ inline bool build_igemm(const ConvSpec& s, IgemmLaunch* L, std::string* why) {
     if (!encode_tmap_bf16(&L->tmA, s.in.ptr + s.in_coff, 3, dims, strides, boxA, why)) return false;
     const uint64_t dimsB[2] = {(uint64_t)s.cin, (uint64_t)s.taps * s.n_total};
     const uint64_t stridesB[1] = {(uint64_t)s.cin * 2};
-    const uint32_t boxB[2] = {64, (uint32_t)n_tile};
+    const uint32_t boxB[2] = {64, (uint32_t)(n_tile / cg)};
     if (!encode_tmap_bf16(&L->tmB, s.w, 2, dimsB, stridesB, boxB, why)) return false;
   }
 
@@ -215,25 +231,50 @@ inline bool build_igemm(const ConvSpec& s, IgemmLaunch* L, std::string* why) {
     p.o_img = (long long)s.out.hs * p.o_row;
     p.out = s.out.ptr + (long long)s.out_halo * p.o_row + (long long)s.out_halo * p.o_pix + s.out_coff;
     p.d2s_cout = s.d2s_cout;
+    if (s.pool.ptr) {
+      if (s.epi_mode != EPI_STORE) return fail("fused pooling needs a plain store epilogue");
+      if ((p.h_valid | p.w_valid | p.hs_in) & 1) return fail("fused pooling needs even map sizes");
+      if (s.pool.hs < p.h_valid / 2 + 2 * s.pool_halo || s.pool.ws < p.w_valid / 2 + 2 * s.pool_halo ||
+          s.pool.c < s.n_total || s.pool.b != s.in.b)
+        return fail("pooled destination buffer too small");
+      p.pl_pix = s.pool.c;
+      p.pl_row = (long long)s.pool.ws * s.pool.c;
+      p.pl_img = (long long)s.pool.hs * p.pl_row;
+      p.pool_out = s.pool.ptr + (long long)s.pool_halo * p.pl_row + (long long)s.pool_halo * p.pl_pix;
+    }
   }
-  L->grid = p.total_tiles < (s.max_ctas > 0 ? s.max_ctas : device_sm_count())
-                ? p.total_tiles
-                : (s.max_ctas > 0 ? s.max_ctas : device_sm_count());
+  {
+    const int sms = s.max_ctas > 0 ? s.max_ctas : device_sm_count();
+    const int groups_max = std::max(1, sms / cg);
+    L->grid = cg * (p.total_tiles < groups_max ? p.total_tiles : groups_max);
+  }
   L->flops = 2.0 * s.in.b * (double)p.h_valid * p.w_valid * s.n_total * s.cin * s.taps;
   return true;
 }
 
-template <int N, int T>
+template <int N, int T, int CG>
 inline cudaError_t igemm_launch_t(const IgemmLaunch& L, const IgemmParams& p, cudaStream_t st) {
   static bool attr_done = false;
   if (!attr_done) {
-    cudaError_t e = cudaFuncSetAttribute(igemm_kernel<N, T>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    cudaError_t e = cudaFuncSetAttribute(igemm_kernel<N, T, CG>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)IG_SMEM_LIMIT);
     if (e != cudaSuccess) return e;
     attr_done = true;
   }
-  igemm_kernel<N, T><<<L.grid, IG_THREADS, L.smem, st>>>(L.tmA, L.tmB, p);
-  return cudaGetLastError();
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof cfg);
+  cfg.gridDim = dim3(L.grid);
+  cfg.blockDim = dim3(IG_THREADS);
+  cfg.dynamicSmemBytes = L.smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CG;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, igemm_kernel<N, T, CG>, L.tmA, L.tmB, p);
 }
 
 inline cudaError_t launch_igemm(const IgemmLaunch& L, int* err_flag, cudaStream_t st,
@@ -241,13 +282,18 @@ inline cudaError_t launch_igemm(const IgemmLaunch& L, int* err_flag, cudaStream_
   IgemmParams p = L.p;
   p.err = err_flag;
   p.trace = trace;
-  const int key = L.n_tile * 10 + L.tps;
+  const int key = L.n_tile * 100 + L.tps * 10 + L.cg;
   switch (key) {
-    case 641: return igemm_launch_t<64, 1>(L, p, st);
-    case 643: return igemm_launch_t<64, 3>(L, p, st);
-    case 1281: return igemm_launch_t<128, 1>(L, p, st);
-    case 1283: return igemm_launch_t<128, 3>(L, p, st);
-    case 2561: return igemm_launch_t<256, 1>(L, p, st);
+    case 6411: return igemm_launch_t<64, 1, 1>(L, p, st);
+    case 6431: return igemm_launch_t<64, 3, 1>(L, p, st);
+    case 12811: return igemm_launch_t<128, 1, 1>(L, p, st);
+    case 12831: return igemm_launch_t<128, 3, 1>(L, p, st);
+    case 25611: return igemm_launch_t<256, 1, 1>(L, p, st);
+    case 6412: return igemm_launch_t<64, 1, 2>(L, p, st);
+    case 6432: return igemm_launch_t<64, 3, 2>(L, p, st);
+    case 12812: return igemm_launch_t<128, 1, 2>(L, p, st);
+    case 12832: return igemm_launch_t<128, 3, 2>(L, p, st);
+    case 25612: return igemm_launch_t<256, 1, 2>(L, p, st);
     default: return cudaErrorInvalidValue;
   }
 }

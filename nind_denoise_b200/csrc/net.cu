@@ -119,7 +119,7 @@ struct nind_net {
   cudaStream_t s_in = nullptr, s_comp = nullptr, s_out = nullptr;
   std::vector<cudaEvent_t> ev_in, ev_done;
   // options
-  int n_tile_deep = 256, max_ctas = 0;
+  int n_tile_deep = 256, max_ctas = 0, cg = 0, fuse_pool = 1;
   // timing
   int timing = 0;
   std::vector<std::string> t_names;
@@ -398,7 +398,7 @@ struct PlanBuilder {
 
   // 3x3 / 1x1 layer writing bf16 (EPI_STORE or EPI_D2S)
   void conv(const std::string& name, const ActBuf& in, int in_coff, const ActBuf& out, int out_coff,
-            int out_halo, int epi) {
+            int out_halo, int epi, const ActBuf* pool = nullptr, int pool_halo = 0) {
     if (rc) return;
     auto it = net->layers.find(name);
     if (it == net->layers.end()) { rc = fail(NIND_E_WEIGHTS, "layer not loaded: " + name); return; }
@@ -407,7 +407,9 @@ struct PlanBuilder {
     s.in = in; s.in_coff = in_coff; s.cin = L.cin; s.taps = L.taps; s.w = L.w; s.n_total = L.n_total;
     s.bias = L.bias; s.act = L.act; s.slope = L.slope; s.epi_mode = epi;
     s.out = out; s.out_coff = out_coff; s.out_halo = out_halo; s.d2s_cout = L.cout;
+    if (pool && net->fuse_pool) { s.pool = *pool; s.pool_halo = pool_halo; }
     s.max_ctas = net->max_ctas;
+    s.cg = net->cg;
     if (L.n_total >= 256) s.n_tile = net->n_tile_deep;
     Step st;
     st.kind = STEP_IGEMM; st.name = name;
@@ -428,6 +430,7 @@ struct PlanBuilder {
     s.head_w = net->head_w; s.head_b = net->head_b; s.head_out = nullptr;
     s.head_unpad = unpad; s.head_hy = hy; s.head_hx = hx; s.head_sigmoid = sigmoid;
     s.max_ctas = net->max_ctas;
+    s.cg = net->cg;
     Step st;
     st.kind = STEP_IGEMM; st.name = name + "+head";
     std::string why;
@@ -493,9 +496,9 @@ int build_utnet_plan(nind_net* net, Plan* plan, int B, int H, int W) {
     if (l == 1) pb.conv(p + ".0", x0, 0, a, 0, 0, EPI_STORE);
     else pb.conv(p + ".0", cur, 0, a, 0, 0, EPI_STORE);
     cat[l] = pb.alloc(B, eh[l] + 4, ew[l] + 4, 2 * c);  // [up | skip], 2-px zero frame for the ConvT
-    pb.conv(p + ".2", a, 0, cat[l], c, 2, EPI_STORE);
     cur = pb.alloc(B, ph[l], pw[l], c);
-    pb.pool("maxpool" + std::to_string(l), cat[l], 2, c, c, cur, 0);
+    pb.conv(p + ".2", a, 0, cat[l], c, 2, EPI_STORE, &cur, 0);  // + fused MaxPool2d(2) into `cur`
+    if (!net->fuse_pool) pb.pool("maxpool" + std::to_string(l), cat[l], 2, c, c, cur, 0);
   }
   // bottom
   ActBuf bt0 = pb.alloc(B, ph[4] - 2 + 4, pw[4] - 2 + 4, 16 * f);
@@ -543,9 +546,9 @@ int build_unet_plan(nind_net* net, Plan* plan, int B, int H, int W) {
     else pb.conv(p + ".0", cur, 0, mid, 0, 1, EPI_STORE);
     if (l < 4) {
       cat[l] = pb.alloc(B, sh[l] + 2, sw[l] + 2, 2 * ch[l]);
-      pb.conv(p + ".3", mid, 0, cat[l], 0, 1, EPI_STORE);
       cur = pb.alloc(B, sh[l + 1] + 2, sw[l + 1] + 2, ch[l]);
-      pb.pool("maxpool" + std::to_string(l + 1), cat[l], 1, 0, ch[l], cur, 1);
+      pb.conv(p + ".3", mid, 0, cat[l], 0, 1, EPI_STORE, &cur, 1);  // + fused MaxPool2d(2)
+      if (!net->fuse_pool) pb.pool("maxpool" + std::to_string(l + 1), cat[l], 1, 0, ch[l], cur, 1);
     } else {
       cur = pb.alloc(B, sh[l], sw[l], ch[l]);
       pb.conv(p + ".3", mid, 0, cur, 0, 0, EPI_STORE);
@@ -729,6 +732,11 @@ int nind_set_option(nind_net* net, const char* key, int value) {
     net->n_tile_deep = value;
   } else if (k == "max_ctas") {
     net->max_ctas = value;
+  } else if (k == "cta_group") {
+    if (value < 0 || value > 2) return fail(NIND_E_INVALID, "cta_group must be 0 (auto), 1 or 2");
+    net->cg = value;
+  } else if (k == "fuse_pool") {
+    net->fuse_pool = value ? 1 : 0;
   } else {
     return fail(NIND_E_INVALID, "unknown option " + k);
   }
@@ -921,10 +929,12 @@ int nind_tiled_denoise_host(nind_net* net, const float* img_chw_host, float* out
     }
     CUDA_TRY(cudaEventRecord(net->ev_in[yi], net->s_in));
   }
-  for (int yi = 0; yi < g.ny; ++yi) {
-    CUDA_TRY(cudaStreamWaitEvent(net->s_comp, net->ev_in[yi], 0));
-    for (int i0 = yi * g.nx; i0 < (yi + 1) * g.nx; i0 += batch) {
-      const int b = std::min(batch, (yi + 1) * g.nx - i0);
+  const int rg = std::max(1, batch / g.nx);  // grid rows per pipeline step (batches may span rows)
+  for (int ya = 0; ya < g.ny; ya += rg) {
+    const int yb = std::min(g.ny, ya + rg);
+    CUDA_TRY(cudaStreamWaitEvent(net->s_comp, net->ev_in[yb - 1], 0));
+    for (int i0 = ya * g.nx; i0 < yb * g.nx; i0 += batch) {
+      const int b = std::min(batch, yb * g.nx - i0);
       Plan* plan = nullptr;
       if ((rc = get_plan(net, b, cs, cs, &plan))) return rc;
       GatherParams gp;
@@ -933,13 +943,13 @@ int nind_tiled_denoise_host(nind_net* net, const float* img_chw_host, float* out
       gp.origin = net->origin_buf + i0;
       if ((rc = run_plan(net, plan, gp, net->crops_buf + (size_t)i0 * 3 * cs * cs, net->s_comp))) return rc;
     }
-    // output rows completed by this grid row: every crop that touches them has index < (yi+1)*nx
-    const int r0 = g.stride * yi;
-    const int r1 = yi == g.ny - 1 ? height : std::min(height, g.stride * (yi + 1));
+    // output rows completed by these grid rows: every crop that touches them has index < yb*nx
+    const int r0 = g.stride * ya;
+    const int r1 = yb == g.ny ? height : std::min(height, g.stride * yb);
     if (r1 > r0) {
       if ((rc = launch_stitch(g, net->crops_buf, 0, n, net->out_dev, r0, r1, true, net->s_comp))) return rc;
-      CUDA_TRY(cudaEventRecord(net->ev_done[yi], net->s_comp));
-      CUDA_TRY(cudaStreamWaitEvent(net->s_out, net->ev_done[yi], 0));
+      CUDA_TRY(cudaEventRecord(net->ev_done[ya], net->s_comp));
+      CUDA_TRY(cudaStreamWaitEvent(net->s_out, net->ev_done[ya], 0));
       const size_t off = (size_t)r0 * width;
       CUDA_TRY(cudaMemcpy2DAsync(out_chw_host + off, plane * sizeof(float), net->out_dev + off, plane * sizeof(float),
                                  (size_t)(r1 - r0) * width * sizeof(float), 3, cudaMemcpyDeviceToHost, net->s_out));

@@ -30,14 +30,22 @@ def crop_table(width: int, height: int, cs: int, ucs: int, ol: int):
     return _capi.crop_table(width, height, cs, ucs, ol)
 
 
+def _nx(width: int, ucs: int, ol: int) -> int:
+    return math.ceil((width - ucs) / (ucs - ol)) + 1
+
+
 def n_crops(width: int, height: int, cs: int, ucs: int, ol: int) -> int:
     stride = ucs - ol
     return (math.ceil((width - ucs) / stride) + 1) * (math.ceil((height - ucs) / stride) + 1)
 
 
-def default_batch(n: int, cs: int) -> int:
-    """Crops per forward: enough to fill 148 SMs on the deep layers, and a divisor-friendly size."""
-    target = 16 if cs <= 264 else (13 if cs <= 520 else 4)
+def default_batch(n: int, cs: int, nx: int = 0) -> int:
+    """Crops per forward.  Large enough that the deep (small-map) layers fill 148 SMs for several waves
+    (B200 sweep: cs 248 -> 451/473/484/489 MP/s at 16/28/56/84 crops; cs 504 -> 524/528/534 at 13/26/39),
+    rounded to whole grid rows so the host pipeline (H2D | compute | D2H) steps row by row."""
+    target = int(max(4, min(160, round(9.5e6 / float(cs * cs)))))
+    if nx and target >= nx:
+        target = max(1, round(target / nx)) * nx
     return max(1, min(n, target))
 
 
@@ -76,7 +84,7 @@ def denoise_tiled(img: torch.Tensor, model, cs: Optional[int] = None, ucs: Optio
     img = img.detach().float().contiguous()
     n = n_crops(img.shape[2], img.shape[1], cs, ucs, ol)
     if batch is None:
-        batch = default_batch(n, cs)
+        batch = default_batch(n, cs, _nx(img.shape[2], ucs, ol))
     out, y0, y1 = _band(model, img, cs, ucs, ol, 0, n, batch)
     assert y0 == 0 and y1 == img.shape[1]
     return out
@@ -93,7 +101,7 @@ def denoise_tiled_host(img_host: torch.Tensor, model, cs: int, ucs: int, ol: int
     if out is None:
         out = torch.empty_like(img_host)
     if batch is None:
-        batch = default_batch(n_crops(W, H, cs, ucs, ol), cs)
+        batch = default_batch(n_crops(W, H, cs, ucs, ol), cs, _nx(W, ucs, ol))
     h = model.native_handle()
     with torch.cuda.device(model._device):
         _capi.check(_capi.lib().nind_tiled_denoise_host(h, img_host.data_ptr(), out.data_ptr(), H, W, cs, ucs, ol,
@@ -130,7 +138,7 @@ def denoise_tiled_distributed(img: torch.Tensor, model, cs: int, ucs: int, ol: i
     cb, ce = ranges[rank]
     if band_fn is None:
         if batch is None:
-            batch = default_batch(max(1, ce - cb), cs)
+            batch = default_batch(max(1, ce - cb), cs, _nx(W, ucs, ol))
         band_fn = lambda im, a, b: _band(model, im, cs, ucs, ol, a, b, batch)
     # band extents are pure geometry: every rank can compute everybody's (no metadata exchange)
     extents = []

@@ -241,4 +241,24 @@ def test_kernel_launch_counter(utnet):
     n0 = _capi.lib().nind_kernel_launches()
     utnet(torch.rand(1, 3, 120, 120, device=dev()))
     torch.cuda.synchronize()
-    assert _capi.lib().nind_kernel_launches() - n0 == 27  # 1 gather + 22 conv launches (1x1 head fused into tconvs4.2) + 4 pools
+    # 1 gather + 22 conv launches; the four max-pools and the 1x1 head are fused into conv epilogues
+    assert _capi.lib().nind_kernel_launches() - n0 == 23
+
+
+def test_kernel_variants_agree():
+    """Fused vs separate max-pool and CTA-pair (cta_group::2) vs single-CTA tiles compute the same
+    function: identical bf16 pooling, and fp32 accumulation orders that differ only inside the MMA."""
+    sd = on.init_state_dict("UtNet", seed=0)
+    torch.manual_seed(6)
+    x = torch.rand(2, 3, 120, 136, device=dev())
+    outs = {}
+    for name, opts in (("default", {}), ("unfused_pool", {"fuse_pool": 0}), ("cta1", {"cta_group": 1}),
+                       ("cta2", {"cta_group": 2}), ("n128", {"n_tile_deep": 128})):
+        m = nb.UtNet().to(dev()).eval()
+        m.load_state_dict(sd)
+        for k, v in opts.items():
+            m.set_option(k, v)
+        outs[name] = m(x).cpu().numpy()
+    assert np.array_equal(outs["default"], outs["unfused_pool"])
+    for k in ("cta1", "cta2", "n128"):
+        assert np.abs(outs[k] - outs["default"]).max() <= 2e-5, k
