@@ -34,6 +34,13 @@ MP = W_IMG * H_IMG / 1e6
 OL = 6
 
 
+# dram__bytes_read.sum + dram__bytes_write.sum of the heaviest igemm launch, from the committed
+# `ncu --set full` capture of this command (profiles/r01_ncu_summary.md)
+NCU_TRAFFIC = {(248, 168): 4.16e9}
+NCU_TRAFFIC_NOTE = ("tconvs4.0 launch (168 crops, 128->64 ch @250^2): 4.16 GB measured vs 4.07 GB algorithmic "
+                    "(bf16 in + out once); all four captured launches are within 3 % of algorithmic")
+
+
 def workload(cs):
     return dict(cs=cs, ucs=cs - 24, ol=OL)
 
@@ -238,11 +245,7 @@ def main():
         if world == 1:
             nb.denoise_tiled_host(img_host, model, cs, ucs, ol, batch=batch, out=out_host)
         else:
-            d_img = img_host.to(dev, non_blocking=True)
-            o = nb.denoise_tiled_distributed(d_img, model, cs, ucs, ol, batch=batch)
-            if o is not None:
-                out_host.copy_(o, non_blocking=True)
-            torch.cuda.synchronize()
+            nb.denoise_tiled_distributed_host(img_host, model, cs, ucs, ol, batch=batch, out=out_host)
 
     e2e_step()
     sync_all()
@@ -258,7 +261,12 @@ def main():
     if world > 1:
         dist.all_reduce(t2, op=dist.ReduceOp.MAX)
     e2e_ms = float(t2.item())
-    h2d = img_host.numel() * 4 * (world if world > 1 else 1)
+    if world == 1:
+        h2d = img_host.numel() * 4
+    else:  # every rank uploads only the rows its crops read
+        from nind_denoise_b200.tiler import rows_needed
+        h2d = sum((lambda r: (r[1] - r[0]) * W_IMG * 12)(rows_needed(W_IMG, H_IMG, cs, ucs, ol, a, b))
+                  for a, b in ranges if b > a)
     d2h = out_host.numel() * 4
 
     # ---- roofline of the dominant kernel (igemm conv): per-layer CUDA-event times over one image
@@ -292,7 +300,8 @@ def main():
         roof = {"bound": "tensor", "kernel": "nind::igemm_kernel<N_TILE> (all conv layers)",
                 "achieved": achieved, "peak": pk["sustained"], "unit": "TFLOP/s", "frac": achieved / pk["sustained"],
                 "frac_of_burst": achieved / pk["burst"], "peak_source": pk["source"] + " (bf16_tflops_sustained)",
-                "traffic": None, "launches": n_launch, "avg_launch_ms": conv_ms / max(1, n_launch),
+                "traffic": NCU_TRAFFIC.get((cs, batch)), "traffic_note": NCU_TRAFFIC_NOTE if (cs, batch) in NCU_TRAFFIC else None,
+                "launches": n_launch, "avg_launch_ms": conv_ms / max(1, n_launch),
                 "kernel_share_of_step": conv_ms / all_ms if all_ms else None}
         layer_rows = sorted(((k, v[0], v[1]) for k, v in agg.items()), key=lambda r: -r[1])
         if args.layers:

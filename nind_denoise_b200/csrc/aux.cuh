@@ -40,56 +40,66 @@ __device__ __forceinline__ int sym_index(int t, int n) {
 
 __global__ void __launch_bounds__(256) gather_im2col_kernel(const GatherParams p) {
   // One thread per output pixel of the first convolution: 6 index computations, 27 coalesced loads
-  // (neighbouring threads read neighbouring pixels), one 128-byte row of bf16 written.
+  // (neighbouring threads read neighbouring pixels).  The 128-byte bf16 row of each pixel goes through
+  // an XOR-swizzled shared staging tile so that a warp writes its 32 pixels as 4 KB of contiguous,
+  // fully coalesced 16-byte stores (the destination is dense [crops][out_h][out_w][64]).
+  __shared__ __align__(16) uint8_t stage[8][4096];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const long long total = (long long)p.n_crops * p.out_h * p.out_w;
-  for (long long gid = blockIdx.x * (long long)blockDim.x + threadIdx.x; gid < total;
+  const long long total_r = (total + 31) & ~31LL;  // whole warps
+  for (long long gid = blockIdx.x * (long long)blockDim.x + threadIdx.x; gid < total_r;
        gid += (long long)gridDim.x * blockDim.x) {
-    long long pix = gid;
-    const int x = (int)(pix % p.out_w);
-    pix /= p.out_w;
-    const int y = (int)(pix % p.out_h);
-    const int b = (int)(pix / p.out_h);
-    int x0 = 0, y0 = 0;
-    if (p.origin) {
-      const int2 o = p.origin[b];
-      x0 = o.x;
-      y0 = o.y;
-    }
-    const float* img = p.src + b * p.src_img;
-    long long rowoff[3];
-    int col[3];
-    bool vy[3], vx[3];
-#pragma unroll
-    for (int k = 0; k < 3; ++k) {
-      int r = y + k - p.pad, q = x + k - p.pad;  // crop coordinates
-      if (p.reflect) {
-        r = r < 0 ? -r : (r >= p.crop_h ? 2 * p.crop_h - 2 - r : r);
-        q = q < 0 ? -q : (q >= p.crop_w ? 2 * p.crop_w - 2 - q : q);
-        vy[k] = vx[k] = true;
-      } else {
-        vy[k] = r >= 0 && r < p.crop_h;
-        vx[k] = q >= 0 && q < p.crop_w;
-      }
-      rowoff[k] = (long long)sym_index(y0 + r, p.src_h) * p.src_w;
-      col[k] = sym_index(x0 + q, p.src_w);
-    }
     float h[64];
+    if (gid < total) {
+      long long pix = gid;
+      const int x = (int)(pix % p.out_w);
+      pix /= p.out_w;
+      const int y = (int)(pix % p.out_h);
+      const int b = (int)(pix / p.out_h);
+      int x0 = 0, y0 = 0;
+      if (p.origin) {
+        const int2 o = p.origin[b];
+        x0 = o.x;
+        y0 = o.y;
+      }
+      const float* img = p.src + b * p.src_img;
+      long long rowoff[3];
+      int col[3];
+      bool vy[3], vx[3];
 #pragma unroll
-    for (int ky = 0; ky < 3; ++ky)
-#pragma unroll
-      for (int kx = 0; kx < 3; ++kx)
-#pragma unroll
-        for (int c = 0; c < 3; ++c) {
-          const int e = (ky * 3 + kx) * 3 + c;
-          float f = 0.f;
-          if (vy[ky] && vx[kx]) f = __ldg(img + c * p.src_plane + rowoff[ky] + col[kx]);
-          const float hi = __bfloat162float(__float2bfloat16_rn(f));
-          h[e] = hi;
-          h[27 + e] = f - hi;
+      for (int k = 0; k < 3; ++k) {
+        int r = y + k - p.pad, q = x + k - p.pad;  // crop coordinates
+        if (p.reflect) {
+          r = r < 0 ? -r : (r >= p.crop_h ? 2 * p.crop_h - 2 - r : r);
+          q = q < 0 ? -q : (q >= p.crop_w ? 2 * p.crop_w - 2 - q : q);
+          vy[k] = vx[k] = true;
+        } else {
+          vy[k] = r >= 0 && r < p.crop_h;
+          vx[k] = q >= 0 && q < p.crop_w;
         }
+        rowoff[k] = (long long)sym_index(y0 + r, p.src_h) * p.src_w;
+        col[k] = sym_index(x0 + q, p.src_w);
+      }
 #pragma unroll
-    for (int k = 54; k < 64; ++k) h[k] = 0.f;
-    uint4* dst = reinterpret_cast<uint4*>(p.dst + gid * 64);
+      for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+        for (int kx = 0; kx < 3; ++kx)
+#pragma unroll
+          for (int c = 0; c < 3; ++c) {
+            const int e = (ky * 3 + kx) * 3 + c;
+            float f = 0.f;
+            if (vy[ky] && vx[kx]) f = __ldg(img + c * p.src_plane + rowoff[ky] + col[kx]);
+            const float hi = __bfloat162float(__float2bfloat16_rn(f));
+            h[e] = hi;
+            h[27 + e] = f - hi;
+          }
+#pragma unroll
+      for (int k = 54; k < 64; ++k) h[k] = 0.f;
+    } else {
+#pragma unroll
+      for (int k = 0; k < 64; ++k) h[k] = 0.f;
+    }
+    uint8_t* st = stage[warp];
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       uint4 o;
@@ -97,8 +107,19 @@ __global__ void __launch_bounds__(256) gather_im2col_kernel(const GatherParams p
       o.y = pack_bf16x2(h[8 * j + 2], h[8 * j + 3]);
       o.z = pack_bf16x2(h[8 * j + 4], h[8 * j + 5]);
       o.w = pack_bf16x2(h[8 * j + 6], h[8 * j + 7]);
-      dst[j] = o;
+      *reinterpret_cast<uint4*>(st + lane * 128 + ((j ^ (lane & 7)) << 4)) = o;
     }
+    __syncwarp();
+    const long long warp_first = gid - lane;  // first pixel of this warp
+    uint8_t* dst = reinterpret_cast<uint8_t*>(p.dst) + warp_first * 128;
+    const int sub = lane >> 3, ch = lane & 7;
+#pragma unroll
+    for (int it = 0; it < 8; ++it) {
+      const int rr = it * 4 + sub;
+      const uint4 o = *reinterpret_cast<const uint4*>(st + rr * 128 + ((ch ^ (rr & 7)) << 4));
+      if (warp_first + rr < total) *reinterpret_cast<uint4*>(dst + it * 512 + lane * 16) = o;
+    }
+    __syncwarp();
   }
 }
 

@@ -172,6 +172,39 @@ def denoise_tiled_distributed(img: torch.Tensor, model, cs: int, ucs: int, ol: i
     return None
 
 
+def rows_needed(width: int, height: int, cs: int, ucs: int, ol: int, crop_begin: int, crop_end: int) -> Tuple[int, int]:
+    """Image rows [r0, r1) that crops [crop_begin, crop_end) read (mirror padding reflects inside them)."""
+    t = crop_table(width, height, cs, ucs, ol)
+    return max(0, int(t[crop_begin, 1])), min(height, int(t[crop_end - 1, 1]) + cs)
+
+
+def denoise_tiled_distributed_host(img_host: torch.Tensor, model, cs: int, ucs: int, ol: int = DEFAULT_OVERLAP,
+                                   batch: Optional[int] = None, group=None, dst: int = 0,
+                                   out: Optional[torch.Tensor] = None) -> Optional[torch.Tensor]:
+    """Multi-GPU host-buffer entry: every rank holds the same CPU image (pinned for full PCIe speed),
+    uploads only the rows its crop range reads, stitches its band on its GPU; bands are gathered to
+    rank ``dst`` over NCCL and copied to ``out`` (CPU) there.  Other ranks return None."""
+    import torch.distributed as dist
+
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    _, H, W = img_host.shape
+    n = n_crops(W, H, cs, ucs, ol)
+    cb, ce = shard_ranges(n, world)[rank]
+    dev = model._device if getattr(model, "_handle", None) else next(model.parameters()).device
+    d_img = torch.empty((3, H, W), dtype=torch.float32, device=dev)
+    if ce > cb:
+        r0, r1 = rows_needed(W, H, cs, ucs, ol, cb, ce)
+        d_img[:, r0:r1].copy_(img_host[:, r0:r1], non_blocking=True)
+    res = denoise_tiled_distributed(d_img, model, cs, ucs, ol, batch=batch, group=group, dst=dst)
+    if rank != dst:
+        return None
+    if out is None:
+        out = torch.empty((3, H, W), dtype=torch.float32, pin_memory=True)
+    out.copy_(res, non_blocking=True)
+    torch.cuda.synchronize(dev)
+    return out
+
+
 # ------------------------------------------------------------------------------ geometry ops
 def gather_crops(model, img: torch.Tensor, cs: int, ucs: int, ol: int, crop_begin: int = 0,
                  crop_end: Optional[int] = None) -> torch.Tensor:

@@ -23,5 +23,10 @@ for cs, ucs, ol in ((248, 224, 6), (120, 96, 6)):
         err = float((out - ref).abs().max())
         print(f"world {dist.get_world_size()} cs {cs}: max |distributed - single| = {err:.3e}")
         assert err <= 1e-6
+    outh = nb.denoise_tiled_distributed_host(img.cpu().pin_memory(), model, cs, ucs, ol)
+    if dist.get_rank() == 0:
+        errh = float((outh.to(dev) - ref).abs().max())
+        print(f"world {dist.get_world_size()} cs {cs}: host entry max diff = {errh:.3e}")
+        assert errh <= 1e-6
 dist.barrier()
 dist.destroy_process_group()
