@@ -173,7 +173,7 @@ def main():
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     if args.ref_sample <= 0:
-        args.ref_sample = 48 if args.cs <= 264 else 10
+        args.ref_sample = 48 if args.cs <= 264 else 6
     if args.impl == "reference":
         return run_reference(args)
 
@@ -287,9 +287,11 @@ def main():
             tms = (C.c_float * 128)()
             fl = (C.c_double * 128)()
             _capi.check(lib.nind_get_layer_times(model.native_handle(), 128, names, tms, fl, C.byref(cnt)))
+            by = (C.c_double * 128)()
+            _capi.check(lib.nind_get_layer_bytes(model.native_handle(), 128, by, C.byref(cnt)))
             for k in range(cnt.value):
-                a = agg.setdefault(names[k].decode(), [0.0, 0.0, 0])
-                a[0] += tms[k]; a[1] += fl[k]; a[2] += 1
+                a = agg.setdefault(names[k].decode(), [0.0, 0.0, 0, 0.0])
+                a[0] += tms[k]; a[1] += fl[k]; a[2] += 1; a[3] += by[k]
             nb_ += 1
         _capi.check(lib.nind_set_timing(model.native_handle(), 0))
         conv_ms = sum(v[0] for k, v in agg.items() if v[1] > 0)
@@ -303,15 +305,21 @@ def main():
                 "traffic": NCU_TRAFFIC.get((cs, batch)), "traffic_note": NCU_TRAFFIC_NOTE if (cs, batch) in NCU_TRAFFIC else None,
                 "launches": n_launch, "avg_launch_ms": conv_ms / max(1, n_launch),
                 "kernel_share_of_step": conv_ms / all_ms if all_ms else None}
-        layer_rows = sorted(((k, v[0], v[1]) for k, v in agg.items()), key=lambda r: -r[1])
+        layer_rows = sorted(((k, v[0], v[1], v[3]) for k, v in agg.items()), key=lambda r: -r[1])
+        # HBM-bound kernels of the step (gather, 2x2/s2 upsamplers, first layer): achieved GB/s
+        g_ms, g_by = agg.get("gather+im2col", [0, 0, 0, 0])[0], agg.get("gather+im2col", [0, 0, 0, 0])[3]
+        if g_ms > 0:
+            roof["memory_bound_kernels"] = {
+                k: {"GB/s": v[3] / (v[0] * 1e-3) / 1e9, "frac_of_hbm_peak": v[3] / (v[0] * 1e-3) / 1e9 / pk["hbm"]}
+                for k, v in agg.items() if k in ("gather+im2col", "up4", "up3", "convs1.0") and v[0] > 0}
         if args.layers:
-            for k, tm, f in layer_rows:
-                print(f"{k:28s} {tm:8.3f} ms  {f / 1e9:10.1f} GFLOP  {f / (tm * 1e-3) / 1e12 if tm else 0:8.1f} TF/s",
-                      file=sys.stderr)
+            for k, tm, f, b_ in layer_rows:
+                print(f"{k:28s} {tm:8.3f} ms  {f / 1e9:10.1f} GFLOP  {f / (tm * 1e-3) / 1e12 if tm else 0:8.1f} TF/s"
+                      f"  {b_ / 1e9:8.2f} GB  {b_ / (tm * 1e-3) / 1e9 if tm else 0:8.0f} GB/s", file=sys.stderr)
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        r, dt, n_s, n_all, threads = cpu_reference_rate(cs, args.ref_sample)
+        r, dt, n_s, n_all, threads = cpu_reference_rate(cs, 4 * args.ref_sample)  # ~10-20 s of CPU work
         cpu = {"value": r, "unit": "MP/s", "cores": threads, "kind": "port",
                "sample": f"{n_s} of {n_all} crops (gather + fp32 torch forward + trim/seam/add, {dt:.1f} s), "
                          f"extrapolated by crop count"}

@@ -112,9 +112,11 @@ int64_t nind_kernel_launches(void);
 int nind_set_timing(nind_net* net, int enabled);
 int nind_get_layer_times(nind_net* net, int max_layers, const char** names, float* ms, double* flops,
                          int* n_layers);
+/* Algorithmic HBM bytes (inputs read once + outputs written once) of the same layers. */
+int nind_get_layer_bytes(nind_net* net, int max_layers, double* bytes, int* n_layers);
 
 /* Tuning knobs (affect plans built afterwards): "n_tile_deep" (128|256), "max_ctas",
- * "cta_group" (0 auto | 1 | 2), "fuse_pool" (0|1). */
+ * "cta_group" (0 auto | 1 | 2), "fuse_pool" (0|1), "fuse_first" (0|1). */
 int nind_set_option(nind_net* net, const char* key, int value);
 
 const char* nind_last_error(void);

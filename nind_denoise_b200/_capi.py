@@ -47,6 +47,7 @@ SIGNATURES = {
     "nind_set_timing": (C.c_int, [C.c_void_p, C.c_int]),
     "nind_get_layer_times": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_char_p), C.POINTER(C.c_float),
                                        C.POINTER(C.c_double), C.POINTER(C.c_int)]),
+    "nind_get_layer_bytes": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_int)]),
     "nind_set_option": (C.c_int, [C.c_void_p, C.c_char_p, C.c_int]),
     "nind_last_error": (C.c_char_p, []),
 }

@@ -38,6 +38,8 @@ struct ConvSpec {
   // tuning
   int n_tile = 0;     // 0 = auto
   int cg = 0;         // CTAs per tile group: 0 = auto, 1, or 2 (cta_group::2 pair)
+  bool gather = false;  // fused first layer; `in` then only describes the geometry [B, out_h, out_w, 64]
+  GatherParams g;
   int force_ws = -1;  // -1 = auto
   int max_ctas = 0;   // 0 = number of SMs
 };
@@ -46,6 +48,7 @@ struct IgemmLaunch {
   CUtensorMap tmA, tmB;
   IgemmParams p;
   int n_tile = 0, tps = 1, cg = 1;
+  bool gather = false;  // fused first layer: A tiles built in shared memory from the fp32 image
   size_t smem = 0;
   int grid = 0;
   double flops = 0;  // algorithmic 2*MAC actually useful (valid outputs only)
@@ -143,6 +146,11 @@ inline bool build_igemm(const ConvSpec& s, IgemmLaunch* L, std::string* why) {
   int cg = s.cg;
   // measured on B200 (profiles/r01_probe_cta_pair.log): the CTA pair wins on every 3x3 layer except
   // 64->128 (-3 %), and on the 1x1 / 2x2-s2 GEMMs only when K is large (C_in >= 512)
+  if (s.gather) {
+    if (s.taps != 1 || s.cin != 64 || s.n_total != 64) return fail("fused gather needs taps=1, K=64, N=64");
+    cg = 1;
+  }
+  L->gather = s.gather;
   if (cg == 0) {
     const bool pair = s.taps == 9 ? (s.cin >= 128 || s.n_total <= 64) : (s.cin >= 512);
     cg = (pair && tiles_x_real >= 2) ? 2 : 1;
@@ -201,13 +209,17 @@ inline bool build_igemm(const ConvSpec& s, IgemmLaunch* L, std::string* why) {
   {
     const uint64_t dims[3] = {(uint64_t)s.cin, (uint64_t)s.in.ws, (uint64_t)p.rows_total};
     const uint64_t strides[2] = {(uint64_t)s.in.c * 2, (uint64_t)s.in.ws * s.in.c * 2};
-    if (!encode_tmap_bf16(&L->tmA, s.in.ptr + s.in_coff, 3, dims, strides, boxA, why)) return false;
+    if (!s.gather && !encode_tmap_bf16(&L->tmA, s.in.ptr + s.in_coff, 3, dims, strides, boxA, why)) return false;
     const uint64_t dimsB[2] = {(uint64_t)s.cin, (uint64_t)s.taps * s.n_total};
     const uint64_t stridesB[1] = {(uint64_t)s.cin * 2};
     const uint32_t boxB[2] = {64, (uint32_t)(n_tile / cg)};
     if (!encode_tmap_bf16(&L->tmB, s.w, 2, dimsB, stridesB, boxB, why)) return false;
   }
 
+  if (s.gather) {
+    L->tmA = L->tmB;  // unused by the kernel
+    p.g = s.g;
+  }
   // epilogue
   p.n_total = s.n_total;
   p.epi_mode = s.epi_mode;
@@ -252,11 +264,11 @@ inline bool build_igemm(const ConvSpec& s, IgemmLaunch* L, std::string* why) {
   return true;
 }
 
-template <int N, int T, int CG>
+template <int N, int T, int CG, bool G = false>
 inline cudaError_t igemm_launch_t(const IgemmLaunch& L, const IgemmParams& p, cudaStream_t st) {
   static bool attr_done = false;
   if (!attr_done) {
-    cudaError_t e = cudaFuncSetAttribute(igemm_kernel<N, T, CG>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    cudaError_t e = cudaFuncSetAttribute(igemm_kernel<N, T, CG, G>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)IG_SMEM_LIMIT);
     if (e != cudaSuccess) return e;
     attr_done = true;
@@ -274,7 +286,7 @@ inline cudaError_t igemm_launch_t(const IgemmLaunch& L, const IgemmParams& p, cu
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  return cudaLaunchKernelEx(&cfg, igemm_kernel<N, T, CG>, L.tmA, L.tmB, p);
+  return cudaLaunchKernelEx(&cfg, igemm_kernel<N, T, CG, G>, L.tmA, L.tmB, p);
 }
 
 inline cudaError_t launch_igemm(const IgemmLaunch& L, int* err_flag, cudaStream_t st,
@@ -282,6 +294,7 @@ inline cudaError_t launch_igemm(const IgemmLaunch& L, int* err_flag, cudaStream_
   IgemmParams p = L.p;
   p.err = err_flag;
   p.trace = trace;
+  if (L.gather) return igemm_launch_t<64, 1, 1, true>(L, p, st);
   const int key = L.n_tile * 100 + L.tps * 10 + L.cg;
   switch (key) {
     case 6411: return igemm_launch_t<64, 1, 1>(L, p, st);

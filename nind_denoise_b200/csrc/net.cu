@@ -119,12 +119,12 @@ struct nind_net {
   cudaStream_t s_in = nullptr, s_comp = nullptr, s_out = nullptr;
   std::vector<cudaEvent_t> ev_in, ev_done;
   // options
-  int n_tile_deep = 256, max_ctas = 0, cg = 0, fuse_pool = 1;
+  int n_tile_deep = 256, max_ctas = 0, cg = 0, fuse_pool = 1, fuse_first = 1;
   // timing
   int timing = 0;
   std::vector<std::string> t_names;
   std::vector<float> t_ms;
-  std::vector<double> t_flops;
+  std::vector<double> t_flops, t_bytes;
 
   void free_layers() {
     for (auto& kv : layers) {
@@ -398,7 +398,8 @@ struct PlanBuilder {
 
   // 3x3 / 1x1 layer writing bf16 (EPI_STORE or EPI_D2S)
   void conv(const std::string& name, const ActBuf& in, int in_coff, const ActBuf& out, int out_coff,
-            int out_halo, int epi, const ActBuf* pool = nullptr, int pool_halo = 0) {
+            int out_halo, int epi, const ActBuf* pool = nullptr, int pool_halo = 0,
+            const GatherParams* fused_gather = nullptr) {
     if (rc) return;
     auto it = net->layers.find(name);
     if (it == net->layers.end()) { rc = fail(NIND_E_WEIGHTS, "layer not loaded: " + name); return; }
@@ -408,6 +409,7 @@ struct PlanBuilder {
     s.bias = L.bias; s.act = L.act; s.slope = L.slope; s.epi_mode = epi;
     s.out = out; s.out_coff = out_coff; s.out_halo = out_halo; s.d2s_cout = L.cout;
     if (pool && net->fuse_pool) { s.pool = *pool; s.pool_halo = pool_halo; }
+    if (fused_gather) { s.gather = true; s.g = *fused_gather; }
     s.max_ctas = net->max_ctas;
     s.cg = net->cg;
     if (L.n_total >= 256) s.n_tile = net->n_tile_deep;
@@ -416,6 +418,16 @@ struct PlanBuilder {
     std::string why;
     if (!build_igemm(s, &st.ig, &why)) { rc = fail(NIND_E_INVALID, name + ": " + why); return; }
     st.flops = st.ig.flops;
+    if (fused_gather) {
+      plan->gather_step = (int)plan->steps.size();
+      st.name = name + "+gather";
+    }
+    {
+      const IgemmParams& q = st.ig.p;
+      const double in_b = (double)in.b * in.hs * in.ws * L.cin * 2;
+      const double out_px = (double)in.b * q.h_valid * q.w_valid * (epi == EPI_D2S ? 4 : 1);
+      st.bytes = in_b + out_px * (epi == EPI_D2S ? L.cout : L.n_total) * 2 + (s.pool.ptr ? out_px / 4 * L.n_total * 2 : 0);
+    }
     plan->steps.push_back(st);
   }
 
@@ -455,14 +467,20 @@ struct PlanBuilder {
     plan->steps.push_back(st);
   }
 
+  static GatherParams gather_geom(const ActBuf& x0, int crop_h, int crop_w, int pad, int reflect) {
+    GatherParams g;
+    memset(&g, 0, sizeof g);
+    g.crop_h = crop_h; g.crop_w = crop_w; g.pad = pad; g.reflect = reflect;
+    g.out_h = x0.hs; g.out_w = x0.ws; g.n_crops = x0.b; g.dst = x0.ptr;
+    return g;
+  }
+
   void gather(const ActBuf& x0, int crop_h, int crop_w, int pad, int reflect) {
     if (rc) return;
     Step st;
     st.kind = STEP_GATHER; st.name = "gather+im2col";
     GatherParams& g = st.g;
-    memset(&g, 0, sizeof g);
-    g.crop_h = crop_h; g.crop_w = crop_w; g.pad = pad; g.reflect = reflect;
-    g.out_h = x0.hs; g.out_w = x0.ws; g.n_crops = x0.b; g.dst = x0.ptr;
+    g = gather_geom(x0, crop_h, crop_w, pad, reflect);
     st.bytes = (double)x0.b * (3.0 * crop_h * crop_w * 4 + (double)x0.hs * x0.ws * 128);
     plan->gather_step = (int)plan->steps.size();
     plan->steps.push_back(st);
@@ -485,15 +503,20 @@ int build_utnet_plan(nind_net* net, Plan* plan, int B, int H, int W) {
     if (l < 4) { eh[l + 1] = ph[l] - 4; ew[l + 1] = pw[l] - 4; }
   }
   // encoder
-  ActBuf x0 = pb.alloc(B, H + 2, W + 2, 64);
-  pb.gather(x0, H, W, 2, 1);
+  ActBuf x0;  // im2col of the padded crops; only materialised when the first layer is not fused
+  x0.b = B; x0.hs = H + 2; x0.ws = W + 2; x0.c = 64;
+  GatherParams g0 = PlanBuilder::gather_geom(x0, H, W, 2, 1);
+  if (!net->fuse_first) {
+    x0 = pb.alloc(B, H + 2, W + 2, 64);
+    pb.gather(x0, H, W, 2, 1);
+  }
   ActBuf cat[5];
   ActBuf cur;  // input of the level's first conv
   for (int l = 1; l <= 4; ++l) {
     const int c = f << (l - 1);
     const std::string p = "convs" + std::to_string(l);
     ActBuf a = pb.alloc(B, eh[l] + 2, ew[l] + 2, c);
-    if (l == 1) pb.conv(p + ".0", x0, 0, a, 0, 0, EPI_STORE);
+    if (l == 1) pb.conv(p + ".0", x0, 0, a, 0, 0, EPI_STORE, nullptr, 0, net->fuse_first ? &g0 : nullptr);
     else pb.conv(p + ".0", cur, 0, a, 0, 0, EPI_STORE);
     cat[l] = pb.alloc(B, eh[l] + 4, ew[l] + 4, 2 * c);  // [up | skip], 2-px zero frame for the ConvT
     cur = pb.alloc(B, ph[l], pw[l], c);
@@ -532,8 +555,13 @@ int build_unet_plan(nind_net* net, Plan* plan, int B, int H, int W) {
   int sh[5], sw[5];
   for (int l = 0; l < 5; ++l) { sh[l] = H >> l; sw[l] = W >> l; }
   const int ch[5] = {64, 128, 256, 512, 512};
-  ActBuf x0 = pb.alloc(B, H, W, 64);
-  pb.gather(x0, H, W, 1, 0);
+  ActBuf x0;
+  x0.b = B; x0.hs = H; x0.ws = W; x0.c = 64;
+  GatherParams g0 = PlanBuilder::gather_geom(x0, H, W, 1, 0);
+  if (!net->fuse_first) {
+    x0 = pb.alloc(B, H, W, 64);
+    pb.gather(x0, H, W, 1, 0);
+  }
   // every 3x3 conv is padding=1: its input buffer carries a 1-px zero frame
   ActBuf cat[4];  // [skip | up] for decoder levels, skip written by the encoder
   ActBuf cur;
@@ -542,7 +570,7 @@ int build_unet_plan(nind_net* net, Plan* plan, int B, int H, int W) {
   for (int l = 0; l < 5; ++l) {
     const std::string p = enc_name[l];
     ActBuf mid = pb.alloc(B, sh[l] + 2, sw[l] + 2, ch[l]);
-    if (l == 0) pb.conv(p + ".0", x0, 0, mid, 0, 1, EPI_STORE);
+    if (l == 0) pb.conv(p + ".0", x0, 0, mid, 0, 1, EPI_STORE, nullptr, 0, net->fuse_first ? &g0 : nullptr);
     else pb.conv(p + ".0", cur, 0, mid, 0, 1, EPI_STORE);
     if (l < 4) {
       cat[l] = pb.alloc(B, sh[l] + 2, sw[l] + 2, 2 * ch[l]);
@@ -612,6 +640,10 @@ int run_plan(nind_net* net, Plan* plan, const GatherParams& gsrc, float* head_ou
     } else {
       IgemmLaunch L = s.ig;
       if ((int)i == plan->head_step) L.p.head_out = head_out;
+      if (L.gather) {
+        L.p.g.src = gsrc.src; L.p.g.src_img = gsrc.src_img; L.p.g.src_plane = gsrc.src_plane;
+        L.p.g.src_w = gsrc.src_w; L.p.g.src_h = gsrc.src_h; L.p.g.origin = gsrc.origin;
+      }
       cudaError_t e = launch_igemm(L, net->err_flag, st);
       if (e != cudaSuccess) return fail(NIND_E_CUDA, s.name + ": " + cudaGetErrorString(e));
     }
@@ -621,13 +653,14 @@ int run_plan(nind_net* net, Plan* plan, const GatherParams& gsrc, float* head_ou
   CUDA_TRY(cudaGetLastError());
   if (net->timing) {
     CUDA_TRY(cudaStreamSynchronize(st));
-    net->t_names.clear(); net->t_ms.clear(); net->t_flops.clear();
+    net->t_names.clear(); net->t_ms.clear(); net->t_flops.clear(); net->t_bytes.clear();
     for (size_t i = 0; i < plan->steps.size(); ++i) {
       float ms = 0;
       cudaEventElapsedTime(&ms, ev[i], ev[i + 1]);
       net->t_names.push_back(plan->steps[i].name);
       net->t_ms.push_back(ms);
       net->t_flops.push_back(plan->steps[i].flops);
+      net->t_bytes.push_back(plan->steps[i].bytes);
     }
     for (auto& e : ev) cudaEventDestroy(e);
   }
@@ -724,6 +757,15 @@ int nind_get_layer_times(nind_net* net, int max_layers, const char** names, floa
   return 0;
 }
 
+int nind_get_layer_bytes(nind_net* net, int max_layers, double* bytes, int* n_layers) {
+  if (!net || !n_layers) return fail(NIND_E_INVALID, "null argument");
+  const int n = (int)net->t_bytes.size();
+  *n_layers = n;
+  for (int i = 0; i < n && i < max_layers; ++i)
+    if (bytes) bytes[i] = net->t_bytes[i];
+  return 0;
+}
+
 int nind_set_option(nind_net* net, const char* key, int value) {
   if (!net || !key) return fail(NIND_E_INVALID, "null argument");
   const std::string k = key;
@@ -737,6 +779,8 @@ int nind_set_option(nind_net* net, const char* key, int value) {
     net->cg = value;
   } else if (k == "fuse_pool") {
     net->fuse_pool = value ? 1 : 0;
+  } else if (k == "fuse_first") {
+    net->fuse_first = value ? 1 : 0;
   } else {
     return fail(NIND_E_INVALID, "unknown option " + k);
   }

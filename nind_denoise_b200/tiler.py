@@ -194,7 +194,8 @@ def denoise_tiled_distributed_host(img_host: torch.Tensor, model, cs: int, ucs: 
     d_img = torch.empty((3, H, W), dtype=torch.float32, device=dev)
     if ce > cb:
         r0, r1 = rows_needed(W, H, cs, ucs, ol, cb, ce)
-        d_img[:, r0:r1].copy_(img_host[:, r0:r1], non_blocking=True)
+        for c in range(3):  # per plane: contiguous pinned source -> true async DMA (a strided CPU view is staged)
+            d_img[c, r0:r1].copy_(img_host[c, r0:r1], non_blocking=True)
     res = denoise_tiled_distributed(d_img, model, cs, ucs, ol, batch=batch, group=group, dst=dst)
     if rank != dst:
         return None

@@ -44,14 +44,14 @@ def _worker(rank, world, port, q):
     dist.destroy_process_group()
 
 
-def test_two_rank_gather_equals_single():
+def _run(world):
     s = socket.socket()
     s.bind(("127.0.0.1", 0))
     port = s.getsockname()[1]
     s.close()
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
-    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    procs = [ctx.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
     for p in procs:
         p.start()
     err = q.get(timeout=120)
@@ -59,3 +59,13 @@ def test_two_rank_gather_equals_single():
         p.join(timeout=60)
         assert p.exitcode == 0
     assert err <= 1e-6
+
+
+def test_two_rank_gather_equals_single():
+    _run(2)
+
+
+def test_eight_ranks_with_an_empty_shard():
+    # 20 crops over 8 ranks -> ceil = 3 per rank, rank 7 gets nothing
+    assert nb.shard_ranges(nb.n_crops(W, H, CS, UCS, OL), 8)[-1] == (20, 20)
+    _run(8)
