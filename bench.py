@@ -32,6 +32,16 @@ sys.path.insert(0, ROOT)
 W_IMG, H_IMG = 6000, 4000
 MP = W_IMG * H_IMG / 1e6
 OL = 6
+NETWORK = "UtNet"
+
+
+def set_workload(network):
+    """BASELINE.json configs[3]: UNet on a 45 MP (8256x5504) image, cs 512 / ucs 384 (extra, not the headline)."""
+    global W_IMG, H_IMG, MP, NETWORK
+    NETWORK = network
+    if network == "UNet":
+        W_IMG, H_IMG = 8256, 5504
+        MP = W_IMG * H_IMG / 1e6
 
 
 # dram__bytes_read.sum + dram__bytes_write.sum of the heaviest igemm launch, from the committed
@@ -42,6 +52,8 @@ NCU_TRAFFIC_NOTE = ("tconvs4.0 launch (168 crops, 128->64 ch @250^2): 4.16 GB me
 
 
 def workload(cs):
+    if NETWORK == "UNet":
+        return dict(cs=cs, ucs=(cs * 3) // 4, ol=OL)
     return dict(cs=cs, ucs=cs - 24, ol=OL)
 
 
@@ -108,16 +120,17 @@ def cpu_reference_rate(cs, sample_crops, threads=None):
     torch.set_num_threads(threads)
     wl = workload(cs)
     g = og.crop_grid(W_IMG, H_IMG, wl["cs"], wl["ucs"], wl["ol"])
-    sd = on.init_state_dict("UtNet", seed=0)
+    sd = on.init_state_dict(NETWORK, seed=0)
+    fwd = on.utnet_forward if NETWORK == "UtNet" else on.unet_forward
     img = np.random.default_rng(1).random((3, H_IMG, W_IMG), dtype=np.float32)
     idx = list(range(0, g.size, max(1, g.size // sample_crops)))[:sample_crops]
     with torch.no_grad():
-        on.utnet_forward(sd, torch.from_numpy(og.gather_crop(img, g, 0)).unsqueeze(0))  # warm-up
+        fwd(sd, torch.from_numpy(og.gather_crop(img, g, 0)).unsqueeze(0))  # warm-up
         t0 = time.perf_counter()
         out = np.zeros((3, H_IMG, W_IMG), np.float32)
         for i in idx:
             e = og.crop_entry(g, i)
-            y = on.utnet_forward(sd, torch.from_numpy(og.gather_crop(img, g, i)).unsqueeze(0))[0].numpy()
+            y = fwd(sd, torch.from_numpy(og.gather_crop(img, g, i)).unsqueeze(0))[0].numpy()
             xlo, ylo, xhi, yhi = e["usefuldim"]
             ax, ay = e["usefulstart"]
             t = y[:, ylo:yhi, xlo:xhi] * og.seam_weights(g, i)
@@ -147,7 +160,7 @@ def run_reference(args):
         "impl": "reference", "metric": "megapixels/sec denoised", "value": val, "unit": "MP/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total_t / max(1, args.steps),
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"UtNet(funit 64) 6000x4000 synthetic image, cs {wl['cs']} ucs {wl['ucs']} overlap {OL}"},
+        "config": {"workload": f"{NETWORK}(funit 64) {W_IMG}x{H_IMG} synthetic image, cs {wl['cs']} ucs {wl['ucs']} overlap {OL}"},
         "cpu_baseline": {"value": val, "unit": "MP/s", "cores": threads, "kind": "port",
                          "sample": f"{n_s} of {n_all} crops per step (gather + fp32 forward + trim/seam/add), "
                                    f"extrapolated by crop count"},
@@ -164,13 +177,18 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--cs", type=int, default=248, help="crop size (legal UtNet size: 120, 248, 504, 1016)")
+    ap.add_argument("--cs", type=int, default=0, help="crop size (legal UtNet sizes: 120, 248 [default], 504, 1016; "
+                                                       "UNet: multiple of 16, default 512)")
+    ap.add_argument("--network", default="UtNet", choices=["UtNet", "UNet"])
     ap.add_argument("--batch", type=int, default=0, help="crops per forward (0 = auto)")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--ref-sample", type=int, default=0, help="crops per step of the CPU reference arm")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--layers", action="store_true", help="print the per-layer timing table to stderr")
     args = ap.parse_args()
+    set_workload(args.network)
+    if args.cs <= 0:
+        args.cs = 248 if args.network == "UtNet" else 512
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     if args.ref_sample <= 0:
         args.ref_sample = 48 if args.cs <= 264 else 6
@@ -182,7 +200,7 @@ def main():
     import nind_denoise_b200 as nb
     from nind_denoise_b200 import _capi
     from nind_denoise_b200.tiler import _band, default_batch
-    from nind_denoise_b200.flops import utnet_flops
+    from nind_denoise_b200.flops import unet_flops, utnet_flops
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -196,7 +214,7 @@ def main():
     cs, ucs, ol = wl["cs"], wl["ucs"], wl["ol"]
 
     torch.manual_seed(0)  # default init == the reference class's default init under the same seed
-    model = nb.UtNet().to(dev).eval()
+    model = (nb.UtNet() if NETWORK == "UtNet" else nb.UNet()).to(dev).eval()
     g = torch.Generator(device="cpu").manual_seed(1)
     img_host = torch.rand((3, H_IMG, W_IMG), generator=g).pin_memory()
     out_host = torch.empty_like(img_host).pin_memory()
@@ -270,7 +288,7 @@ def main():
     d2h = out_host.numel() * 4
 
     # ---- roofline of the dominant kernel (igemm conv): per-layer CUDA-event times over one image
-    flops_image = utnet_flops(cs) * n
+    flops_image = (utnet_flops(cs) if NETWORK == "UtNet" else unet_flops(cs)) * n
     pk = peaks()
     roof = None
     layer_rows = []
@@ -307,11 +325,10 @@ def main():
                 "kernel_share_of_step": conv_ms / all_ms if all_ms else None}
         layer_rows = sorted(((k, v[0], v[1], v[3]) for k, v in agg.items()), key=lambda r: -r[1])
         # HBM-bound kernels of the step (gather, 2x2/s2 upsamplers, first layer): achieved GB/s
-        g_ms, g_by = agg.get("gather+im2col", [0, 0, 0, 0])[0], agg.get("gather+im2col", [0, 0, 0, 0])[3]
-        if g_ms > 0:
+        if True:
             roof["memory_bound_kernels"] = {
                 k: {"GB/s": v[3] / (v[0] * 1e-3) / 1e9, "frac_of_hbm_peak": v[3] / (v[0] * 1e-3) / 1e9 / pk["hbm"]}
-                for k, v in agg.items() if k in ("gather+im2col", "up4", "up3", "convs1.0") and v[0] > 0}
+                for k, v in agg.items() if k in ("gather+im2col", "convs1.0+gather", "up4", "up3", "convs1.0") and v[0] > 0}
         if args.layers:
             for k, tm, f, b_ in layer_rows:
                 print(f"{k:28s} {tm:8.3f} ms  {f / 1e9:10.1f} GFLOP  {f / (tm * 1e-3) / 1e12 if tm else 0:8.1f} TF/s"
@@ -330,7 +347,7 @@ def main():
             "metric": "megapixels/sec denoised", "value": value, "unit": "MP/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-            "config": {"workload": f"UtNet(funit 64, random init) 6000x4000 synthetic image, cs {cs} ucs {ucs} overlap {ol} "
+            "config": {"workload": f"{NETWORK}(funit 64, random init) {W_IMG}x{H_IMG} synthetic image, cs {cs} ucs {ucs} overlap {ol} "
                                    f"-> {n} crops, batch {batch} crops/forward; crops sharded over {world} GPU(s)"
                                    + (", NCCL send/recv gather of row bands to rank 0" if world > 1 else ""),
                        "l2": "inputs larger than L2 (288 MB image, >1 GB activation arena per batch)",

@@ -173,9 +173,17 @@ def denoise_tiled_distributed(img: torch.Tensor, model, cs: int, ucs: int, ol: i
 
 
 def rows_needed(width: int, height: int, cs: int, ucs: int, ol: int, crop_begin: int, crop_end: int) -> Tuple[int, int]:
-    """Image rows [r0, r1) that crops [crop_begin, crop_end) read (mirror padding reflects inside them)."""
+    """Image rows [r0, r1) that crops [crop_begin, crop_end) read, INCLUDING the rows the tiler's mirror
+    padding reflects to when a crop window sticks out of the image (at the bottom edge the window can
+    overshoot by most of a crop, so the mirrored rows lie above the window's own first row)."""
     t = crop_table(width, height, cs, ucs, ol)
-    return max(0, int(t[crop_begin, 1])), min(height, int(t[crop_end - 1, 1]) + cs)
+    y_first, y_last_end = int(t[crop_begin, 1]), int(t[crop_end - 1, 1]) + cs
+    r0, r1 = max(0, y_first), min(height, y_last_end)
+    if y_last_end > height:   # rows height-1 ... 2*height - y_last_end are mirrored in
+        r0 = min(r0, max(0, 2 * height - y_last_end))
+    if y_first < 0:           # rows 0 ... -y_first-1 are mirrored in
+        r1 = max(r1, min(height, -y_first))
+    return r0, r1
 
 
 def denoise_tiled_distributed_host(img_host: torch.Tensor, model, cs: int, ucs: int, ol: int = DEFAULT_OVERLAP,
