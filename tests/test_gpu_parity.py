@@ -241,8 +241,8 @@ def test_kernel_launch_counter(utnet):
     n0 = _capi.lib().nind_kernel_launches()
     utnet(torch.rand(1, 3, 120, 120, device=dev()))
     torch.cuda.synchronize()
-    # 22 conv launches; the crop gather, the four max-pools and the 1x1 head are fused into them
-    assert _capi.lib().nind_kernel_launches() - n0 == 22
+    # 1 gather + 22 conv launches; the four max-pools and the 1x1 head are fused into conv epilogues
+    assert _capi.lib().nind_kernel_launches() - n0 == 23
 
 
 def test_kernel_variants_agree():
@@ -252,7 +252,7 @@ def test_kernel_variants_agree():
     torch.manual_seed(6)
     x = torch.rand(2, 3, 120, 136, device=dev())
     outs = {}
-    for name, opts in (("default", {}), ("unfused_pool", {"fuse_pool": 0}), ("unfused_first", {"fuse_first": 0}),
+    for name, opts in (("default", {}), ("unfused_pool", {"fuse_pool": 0}), ("fused_first", {"fuse_first": 1}),
                        ("cta1", {"cta_group": 1}),
                        ("cta2", {"cta_group": 2}), ("n128", {"n_tile_deep": 128})):
         m = nb.UtNet().to(dev()).eval()
@@ -261,6 +261,6 @@ def test_kernel_variants_agree():
             m.set_option(k, v)
         outs[name] = m(x).cpu().numpy()
     assert np.array_equal(outs["default"], outs["unfused_pool"])
-    assert np.array_equal(outs["default"], outs["unfused_first"])
+    assert np.array_equal(outs["default"], outs["fused_first"])
     for k in ("cta1", "cta2", "n128"):
         assert np.abs(outs[k] - outs["default"]).max() <= 2e-5, k

@@ -110,3 +110,18 @@ def test_module_pickles_without_native_handle(tmp_path):
     torch.save(m, tmp_path / "m.pth")  # nn_common.py:73 saves whole modules as .pth
     m2 = torch.load(tmp_path / "m.pth", weights_only=False)
     assert list(m2.state_dict().keys()) == list(m.state_dict().keys())
+
+
+def test_rows_needed_covers_mirror_padding():
+    from nind_denoise_b200.tiler import rows_needed
+    for (W, H, cs, ucs, ol) in [(1500, 1100, 248, 224, 6), (1500, 1100, 120, 96, 6), (6000, 4000, 504, 480, 6),
+                                (700, 333, 248, 224, 6)]:
+        g = og.crop_grid(W, H, cs, ucs, ol)
+        t = og.crop_table(g)
+        for world in (1, 3, 8):
+            for a, b in nb.shard_ranges(g.size, world):
+                if b <= a:
+                    continue
+                r0, r1 = rows_needed(W, H, cs, ucs, ol, a, b)
+                used = np.concatenate([og._sym(np.arange(t[i, 1], t[i, 1] + cs), H) for i in range(a, b)])
+                assert used.min() >= r0 and used.max() < r1, (W, H, cs, world, a, b)
