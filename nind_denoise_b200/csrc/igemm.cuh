@@ -44,6 +44,7 @@ constexpr int IG_TILE_W = 8;
 struct IgemmParams {
   // tile grid
   int tiles_x, tiles_y, tiles_n, total_tiles;
+  int pair_y;              // CG = 2: the two tiles of a pair are y-adjacent (else x-adjacent)
   // K loop
   int kchunks, taps;
   // shared-memory pipeline geometry
@@ -167,7 +168,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
   uint32_t tmem_base;
   asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
 
-  // p.tiles_x / p.total_tiles count (super-)tiles: CG x-adjacent 16x8 pixel tiles each
+  // p.tiles_x / p.tiles_y / p.total_tiles count (super-)tiles: CG adjacent 16x8 pixel tiles each
   const int tiles_xy = p.tiles_x * p.tiles_y;
   const int groups = p.taps / TPS;  // weight stages per 64-channel chunk
   const int tile0 = blockIdx.x / CG, tstep = gridDim.x / CG;
@@ -220,7 +221,8 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       int tl = 0;
       for (int tile = tile0; tile < p.total_tiles; tile += tstep, ++tl) {
         const int r = tile % tiles_xy;
-        const int yt = r / p.tiles_x, xt = (r - yt * p.tiles_x) * CG + (int)cg_rank;
+        int yt = r / p.tiles_x, xt = r - yt * p.tiles_x;
+        if (CG == 2) { if (p.pair_y) yt = yt * 2 + (int)cg_rank; else xt = xt * 2 + (int)cg_rank; }
         for (int kc = 0; kc < p.kchunks; ++kc) {
           mbar_wait(a_empty + 8 * s, ph ^ 1, p.err, 1);
           if (kc == 0) NIND_TRACE(tl, TR_A_ISSUE);
@@ -360,7 +362,8 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     for (int tile = tile0 + eset * tstep; tile < p.total_tiles; tile += 2 * tstep, tl += 2, aph ^= 1) {
       const int nt = tile / tiles_xy;
       const int r = tile % tiles_xy;
-      const int yt = r / p.tiles_x, xt = (r - yt * p.tiles_x) * CG + (int)cg_rank;
+      int yt = r / p.tiles_x, xt = r - yt * p.tiles_x;
+      if (CG == 2) { if (p.pair_y) yt = yt * 2 + (int)cg_rank; else xt = xt * 2 + (int)cg_rank; }
 
       if (nt != prev_nt) {  // (re)stage this N-tile's bias; uniform over the four warps of the set
         prev_nt = nt;

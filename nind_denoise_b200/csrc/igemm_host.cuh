@@ -153,12 +153,16 @@ inline bool build_igemm(const ConvSpec& s, IgemmLaunch* L, std::string* why) {
   L->gather = s.gather;
   if (cg == 0) {
     const bool pair = s.taps == 9 ? (s.cin >= 128 || s.n_total <= 64) : (s.cin >= 512);
-    cg = (pair && tiles_x_real >= 2) ? 2 : 1;
+    cg = pair ? 2 : 1;
   }
   if (cg != 1 && cg != 2) return fail("cg must be 1 or 2");
   L->cg = cg;
-  p.tiles_x = (tiles_x_real + cg - 1) / cg;  // (super-)tiles: cg x-adjacent 16x8 tiles
-  p.tiles_y = (p.rows_total - shrink + IG_TILE_H - 1) / IG_TILE_H;
+  // Pair the two tiles of a CTA pair along x when that wastes nothing (even tile count), else along y:
+  // rows are batch-flattened (hundreds of tile rows), so a padded odd row count costs < 1 %.
+  const int tiles_y_real = (p.rows_total - shrink + IG_TILE_H - 1) / IG_TILE_H;
+  p.pair_y = (cg == 2 && (tiles_x_real & 1)) ? 1 : 0;
+  p.tiles_x = p.pair_y ? tiles_x_real : (tiles_x_real + cg - 1) / cg;
+  p.tiles_y = p.pair_y ? (tiles_y_real + 1) / 2 : tiles_y_real;
   p.tiles_n = (s.n_total + n_tile - 1) / n_tile;
   p.total_tiles = p.tiles_x * p.tiles_y * p.tiles_n;
   p.kchunks = s.cin / 64;

@@ -264,3 +264,37 @@ def test_kernel_variants_agree():
     assert np.array_equal(outs["default"], outs["fused_first"])
     for k in ("cta1", "cta2", "n128"):
         assert np.abs(outs[k] - outs["default"]).max() <= 2e-5, k
+
+
+def test_cli_shim_roundtrip(tmp_path, golden_networks):
+    """nind_denoise_b200.denoise_image: the reference script's flags and file conventions
+    (denoise_image.py:181-200; np_imgops.py:12-29; pt_helpers.py:22-40) around the GPU tiler."""
+    import cv2
+    from nind_denoise_b200 import denoise_image as cli
+
+    N = golden_networks
+    W, H, cs, ucs, ol = (int(v) for v in N["tiled_params"])
+    img16 = (np.clip(N["tiled_img"], 0, 1) * 65535).round().astype(np.uint16)          # [3,H,W] RGB
+    src = str(tmp_path / "in_s1.tif")
+    cv2.imwrite(src, cv2.cvtColor(img16.transpose(1, 2, 0), cv2.COLOR_RGB2BGR))
+    model_path = str(tmp_path / "generator_650.pt")
+    sd = on.init_state_dict("UtNet", seed=0)
+    torch.save(sd, model_path)
+    dst = str(tmp_path / "out_s1_denoised.tiff")
+    rc = cli.main(["--network", "UtNet", "--model_path", model_path, "--input", src, "--output", dst,
+                   "--cs", str(cs), "--ucs", str(ucs), "--overlap", str(ol)])
+    assert rc == 0
+    got = cv2.cvtColor(cv2.imread(dst, cv2.IMREAD_UNCHANGED), cv2.COLOR_BGR2RGB).transpose(2, 0, 1)
+    assert got.dtype == np.float32 and got.shape == (3, H, W)
+    x = img16.astype(np.float32) / 65535                                                # what the reader returns
+    with torch.no_grad():
+        ref = og.denoise_tiled(x, lambda c: on.utnet_forward(sd, torch.from_numpy(c).unsqueeze(0))[0].numpy(),
+                               cs, ucs, ol)
+    check_pixels(got, ref, "CLI shim (.tif in, float .tiff out)")
+    # 16-bit output path clamps and quantises like pt_helpers.tensor_to_imgfile
+    dst16 = str(tmp_path / "out.png")
+    cli.main(["--network", "UtNet", "--model_path", model_path, "--input", src, "--output", dst16,
+              "--cs", str(cs), "--ucs", str(ucs)])
+    got16 = cv2.cvtColor(cv2.imread(dst16, cv2.IMREAD_UNCHANGED), cv2.COLOR_BGR2RGB).transpose(2, 0, 1)
+    assert got16.dtype == np.uint16
+    assert np.abs(got16.astype(np.int64) - (np.clip(ref, 0, 1) * 65535).round().astype(np.int64)).max() <= 16

@@ -8,6 +8,9 @@ run conv 9 128 128 2 41 43 0 0 0 0 -1 0 $cg
 run conv 1 64 64 2 40 40 0 0 0 0 -1 0 $cg
 run conv 9 256 512 3 30 30 0 0 0 0 -1 0 $cg
 run conv 9 64 64 2 60 60 0 0 2 0 -1 0 $cg
+run conv 9 64 64 2 60 58 0 0 2 0 -1 0 $cg
+run conv 9 256 256 3 24 24 0 0 0 0 -1 0 $cg
+run conv 9 512 512 16 26 26 0 0 0 0 -1 0 $cg
 run conv 1 128 256 2 40 40 0 0 1 0 -1 0 $cg
 run conv 1 64 64 1 506 506 0 0 0 0 -1 0 $cg
 run conv 9 64 64 1 510 510 0 0 0 0 -1 0 $cg
