@@ -381,6 +381,7 @@ struct PlanBuilder {
   nind_net* net;
   Plan* plan;
   int rc = 0;
+  bool last_pool_fused = false;
 
   ActBuf alloc(int b, int hs, int ws, int c) {
     ActBuf a;
@@ -411,7 +412,12 @@ struct PlanBuilder {
     s.in = in; s.in_coff = in_coff; s.cin = L.cin; s.taps = L.taps; s.w = L.w; s.n_total = L.n_total;
     s.bias = L.bias; s.act = L.act; s.slope = L.slope; s.epi_mode = epi;
     s.out = out; s.out_coff = out_coff; s.out_halo = out_halo; s.d2s_cout = L.cout;
-    if (pool && net->fuse_pool) { s.pool = *pool; s.pool_halo = pool_halo; }
+    // the fused pool pairs tile rows/columns, which needs even map sizes (UNet at cs 440 has a 55-wide level)
+    last_pool_fused = false;
+    if (pool && net->fuse_pool && !((in.hs | in.ws) & 1)) {
+      s.pool = *pool; s.pool_halo = pool_halo;
+      last_pool_fused = true;
+    }
     if (fused_gather) { s.gather = true; s.g = *fused_gather; }
     s.max_ctas = net->max_ctas;
     s.cg = net->cg;
@@ -524,7 +530,7 @@ int build_utnet_plan(nind_net* net, Plan* plan, int B, int H, int W) {
     cat[l] = pb.alloc(B, eh[l] + 4, ew[l] + 4, 2 * c);  // [up | skip], 2-px zero frame for the ConvT
     cur = pb.alloc(B, ph[l], pw[l], c);
     pb.conv(p + ".2", a, 0, cat[l], c, 2, EPI_STORE, &cur, 0);  // + fused MaxPool2d(2) into `cur`
-    if (!net->fuse_pool) pb.pool("maxpool" + std::to_string(l), cat[l], 2, c, c, cur, 0);
+    if (!pb.last_pool_fused) pb.pool("maxpool" + std::to_string(l), cat[l], 2, c, c, cur, 0);
   }
   // bottom
   ActBuf bt0 = pb.alloc(B, ph[4] - 2 + 4, pw[4] - 2 + 4, 16 * f);
@@ -550,9 +556,12 @@ int build_utnet_plan(nind_net* net, Plan* plan, int B, int H, int W) {
 }
 
 int build_unet_plan(nind_net* net, Plan* plan, int B, int H, int W) {
-  if (H % 16 || W % 16 || H < 32 || W < 32)
-    return fail(NIND_E_INVALID, "UNet: this build needs crop height/width multiples of 16 (>= 32); got " +
-                                    std::to_string(H) + "x" + std::to_string(W));
+  // Any size works as in the reference: MaxPool2d floors, and the F.pad of the upsampled tensor to the
+  // skip's size (ThirdPartyNets.py:114-118: zeros on the right/bottom) is the never-written, zero-filled
+  // remainder of the concat buffer's up half.
+  if (H < 16 || W < 16)
+    return fail(NIND_E_INVALID, "UNet: crop height/width must be at least 16; got " + std::to_string(H) + "x" +
+                                    std::to_string(W));
   PlanBuilder pb{net, plan};
   // level l (0..4) spatial size
   int sh[5], sw[5];
@@ -579,7 +588,7 @@ int build_unet_plan(nind_net* net, Plan* plan, int B, int H, int W) {
       cat[l] = pb.alloc(B, sh[l] + 2, sw[l] + 2, 2 * ch[l]);
       cur = pb.alloc(B, sh[l + 1] + 2, sw[l + 1] + 2, ch[l]);
       pb.conv(p + ".3", mid, 0, cat[l], 0, 1, EPI_STORE, &cur, 1);  // + fused MaxPool2d(2)
-      if (!net->fuse_pool) pb.pool("maxpool" + std::to_string(l + 1), cat[l], 1, 0, ch[l], cur, 1);
+      if (!pb.last_pool_fused) pb.pool("maxpool" + std::to_string(l + 1), cat[l], 1, 0, ch[l], cur, 1);
     } else {
       cur = pb.alloc(B, sh[l], sw[l], ch[l]);
       pb.conv(p + ".3", mid, 0, cur, 0, 0, EPI_STORE);

@@ -298,3 +298,61 @@ def test_cli_shim_roundtrip(tmp_path, golden_networks):
     got16 = cv2.cvtColor(cv2.imread(dst16, cv2.IMREAD_UNCHANGED), cv2.COLOR_BGR2RGB).transpose(2, 0, 1)
     assert got16.dtype == np.uint16
     assert np.abs(got16.astype(np.int64) - (np.clip(ref, 0, 1) * 65535).round().astype(np.int64)).max() <= 16
+
+
+def test_unet_tiled_vs_oracle(unet):
+    """BASELINE config 4 in miniature: UNet over a tiled image (cs multiple of 16, ucs = 0.75 cs)."""
+    sd = on.randomize_bn_(on.init_state_dict("UNet", seed=0), seed=7)
+    W, H, cs, ucs, ol = 230, 170, 96, 72, 6
+    img = np.random.default_rng(8).random((3, H, W), dtype=np.float32)
+    out = nb.denoise_tiled(torch.from_numpy(img).to(dev()), unet, cs, ucs, ol, batch=5).cpu().numpy()
+    with torch.no_grad():
+        ref = og.denoise_tiled(img, lambda c: on.unet_forward(sd, torch.from_numpy(c).unsqueeze(0))[0].numpy(),
+                               cs, ucs, ol)
+    check_pixels(out, ref, "tiled UNet 230x170")
+
+
+def test_zero_overlap_and_large_crop(utnet):
+    sd = on.init_state_dict("UtNet", seed=0)
+    fwd = lambda c: on.utnet_forward(sd, torch.from_numpy(c).unsqueeze(0))[0].numpy()
+    # overlap 0: no seam halving at all
+    W, H, cs, ucs, ol = 250, 250, 120, 96, 0
+    img = np.random.default_rng(9).random((3, H, W), dtype=np.float32)
+    out = nb.denoise_tiled(torch.from_numpy(img).to(dev()), utnet, cs, ucs, ol).cpu().numpy()
+    with torch.no_grad():
+        ref = og.denoise_tiled(img, fwd, cs, ucs, ol)
+    check_pixels(out, ref, "tiled UtNet overlap 0")
+    # the largest benchmark crop size (nominal 1024 -> 1016), one crop through forward()
+    torch.manual_seed(12)
+    x = torch.rand(1, 3, 1016, 1016)
+    with torch.no_grad():
+        ref = on.utnet_forward(sd, x).numpy()
+    check_pixels(utnet(x.to(dev())).cpu().numpy(), ref, "UtNet cs=1016")
+
+
+def test_unet_reference_default_crop_and_odd_levels(unet):
+    """The reference's own UNet tiling default is cs 440 (denoise_image.py:40): 440 -> 220 -> 110 -> 55 -> 27,
+    i.e. an odd level where MaxPool2d floors and the upsampled tensor is zero-padded to the skip's size
+    (ThirdPartyNets.py:114-118)."""
+    sd = on.randomize_bn_(on.init_state_dict("UNet", seed=0), seed=7)
+    for shape in ((1, 3, 440, 440), (2, 3, 88, 104), (1, 3, 50, 70)):
+        torch.manual_seed(13)
+        x = torch.rand(*shape)
+        with torch.no_grad():
+            ref = on.unet_forward(sd, x).numpy()
+        check_pixels(unet(x.to(dev())).cpu().numpy(), ref, f"UNet {shape}")
+
+
+def test_crop_overlap_sweep(utnet):
+    """BASELINE config 5's sweep in miniature: crop sizes x overlaps, tiled result vs the oracle loop."""
+    sd = on.init_state_dict("UtNet", seed=0)
+    fwd = lambda c: on.utnet_forward(sd, torch.from_numpy(c).unsqueeze(0))[0].numpy()
+    img = np.random.default_rng(10).random((3, 301, 402), dtype=np.float32)
+    dimg = torch.from_numpy(img).to(dev())
+    for cs, ucs in ((120, 96), (136, 100), (248, 224)):
+        for ol in (0, 6, 16, 32):
+            out = nb.denoise_tiled(dimg, utnet, cs, ucs, ol).cpu().numpy()
+            with torch.no_grad():
+                ref = og.denoise_tiled(img, fwd, cs, ucs, ol)
+            err = np.abs(out - ref).max()
+            assert err <= MAX_ABS and err <= MAX_REL_SIGMA * ref.std(), (cs, ucs, ol, err)
