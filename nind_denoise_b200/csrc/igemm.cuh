@@ -35,9 +35,13 @@ enum ActKind : int { ACT_NONE = 0, ACT_PRELU = 1, ACT_ELU = 2, ACT_HARDSWISH = 3
 
 constexpr int IG_MAX_STAGES = 32;
 constexpr int IG_BAR_BYTES = 2048;     // mbarriers + TMEM base slot
-constexpr int IG_EPI_BYTES = 6144;     // per epilogue set: staged bias [2][256] fp32, head weights [3][64]+[3]
-constexpr int IG_STAGE_BYTES = 16384;  // epilogue staging: 2 sets x 4 warps x 32 rows x 64 B
-constexpr int IG_THREADS = 384;
+constexpr int IG_MAX_SETS = 3;         // epilogue warp sets (= TMEM accumulator stages)
+constexpr int IG_EPI_BYTES = IG_MAX_SETS * 3072;  // per set: staged bias [2][256] fp32 + head weights [3][64]+[3]
+constexpr int IG_SET_STAGE_BYTES = 8192;          // per set: 4 warps x 32 rows x 64 B of store staging
+// Epilogue sets per kernel: N_TILE = 64 layers are epilogue-bound with two sets (their MMA phase per tile
+// is short), and their accumulators are small, so they get three.
+__host__ __device__ constexpr int ig_sets(int n_tile) { return n_tile == 64 ? 3 : 2; }
+__host__ __device__ constexpr int ig_threads(int n_tile) { return 128 + 128 * ig_sets(n_tile); }
 constexpr int IG_TILE_H = 16;
 constexpr int IG_TILE_W = 8;
 
@@ -93,7 +97,7 @@ enum { TR_A_ISSUE = 0, TR_MMA_TEMPTY = 1, TR_MMA_AFULL = 2, TR_MMA_DONE = 3, TR_
 __host__ __device__ inline size_t igemm_smem_bytes(int n_tile, int tps, int cg, int sa, uint32_t a_stage_bytes,
                                                    int sb) {
   return 1024 + (size_t)sa * a_stage_bytes + (size_t)sb * tps * (n_tile / cg) * 128 + IG_BAR_BYTES +
-         IG_EPI_BYTES + IG_STAGE_BYTES;
+         IG_EPI_BYTES + (size_t)ig_sets(n_tile) * IG_SET_STAGE_BYTES;
 }
 
 // N_TILE: GEMM N per tile (64/128/256).  TPS: taps per weight pipeline stage (1 or 3).
@@ -107,14 +111,15 @@ __host__ __device__ inline size_t igemm_smem_bytes(int n_tile, int tps, int cg, 
 // mirror padding, in-network reflect/zero pad and the hi/lo bf16 split included — so the 128 B/pixel
 // im2col tensor never exists in HBM.  (taps = 1, one 64-wide K chunk, CG = 1, weights stationary.)
 template <int N_TILE, int TPS, int CG, bool GATHER = false>
-__global__ void __launch_bounds__(IG_THREADS, 1)
+__global__ void __launch_bounds__(ig_threads(N_TILE), 1)
 igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
              const IgemmParams p) {
   extern __shared__ uint8_t smem_raw[];
   constexpr uint32_t B_ROWS = N_TILE / CG;           // weight rows held by this CTA
   constexpr uint32_t B_TAP_BYTES = B_ROWS * 128;
   constexpr uint32_t B_BYTES = TPS * B_TAP_BYTES;
-  constexpr uint32_t TMEM_COLS = 2 * N_TILE;
+  constexpr int ES = ig_sets(N_TILE);  // epilogue sets = accumulator stages
+  constexpr uint32_t TMEM_COLS = ES * N_TILE <= 128 ? 128 : (ES * N_TILE <= 256 ? 256 : 512);
   constexpr uint32_t IDESC = umma_idesc_bf16(128 * CG, N_TILE);
   const uint32_t cg_rank = CG == 2 ? cluster_ctarank() : 0u;
 
@@ -122,14 +127,14 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
   const uint32_t a_base = sbase;
   const uint32_t b_base = a_base + (uint32_t)p.sa * p.a_stage_bytes;
   const uint32_t stg_base = b_base + (uint32_t)p.sb * B_BYTES;  // 1024-aligned
-  const uint32_t bar_base = stg_base + IG_STAGE_BYTES;
+  const uint32_t bar_base = stg_base + ES * IG_SET_STAGE_BYTES;
   const uint32_t a_full = bar_base;
   const uint32_t a_empty = bar_base + 8 * IG_MAX_STAGES;
   const uint32_t b_full = bar_base + 16 * IG_MAX_STAGES;
   const uint32_t b_empty = bar_base + 24 * IG_MAX_STAGES;
   const uint32_t t_full = bar_base + 32 * IG_MAX_STAGES;
-  const uint32_t t_empty = t_full + 16;
-  const uint32_t tmem_slot = t_full + 32;
+  const uint32_t t_empty = t_full + 32;
+  const uint32_t tmem_slot = t_full + 64;
   const uint32_t epi_base = bar_base + IG_BAR_BYTES;
 
   const int warp = threadIdx.x >> 5;
@@ -146,7 +151,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       mbar_init(b_full + 8 * s, 1);
       mbar_init(b_empty + 8 * s, 1);
     }
-    for (int s = 0; s < 2; ++s) {
+    for (int s = 0; s < ES; ++s) {
       mbar_init(t_full + 8 * s, 1);
       mbar_init(t_empty + 8 * s, 4 * CG);
     }
@@ -277,10 +282,9 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     constexpr uint32_t DESC_HI_B = (1024u >> 4) | (1u << 14) | (2u << 29);
     const uint32_t desc_hi_a = (p.a_sbo >> 4) | (1u << 14) | (2u << 29);
     const uint32_t pitch16 = (p.a_sbo >> 4);  // one patch row, in 16-byte units
-    uint32_t sa_i = 0, pha = 0, sb_i = 0, phb = 0;
+    uint32_t sa_i = 0, pha = 0, sb_i = 0, phb = 0, acc = 0, aph = 0;
     int tl = 0;
     for (int tile = tile0; tile < p.total_tiles; tile += tstep, ++tl) {
-      const uint32_t acc = tl & 1, aph = (tl >> 1) & 1;
       mbar_wait(t_empty + 8 * acc, aph ^ 1, p.err, 3);
       tc_fence_after();
       NIND_TRACE(tl, TR_MMA_TEMPTY);
@@ -338,17 +342,18 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       }
       __syncwarp();
       NIND_TRACE(tl, TR_MMA_DONE);
+      if (++acc == (uint32_t)ES) { acc = 0; aph ^= 1; }
     }
   } else if (warp >= 4) {
     // ------------------------------------------------ epilogue
-    // Two independent sets of four warps: set 0 drains accumulator 0 (even tiles of this CTA), set 1
-    // accumulator 1 (odd tiles), so each set has two tile periods to finish its tile.
-    const int eset = (warp - 4) >> 2;        // 0 / 1
+    // ES independent sets of four warps: set s drains accumulator stage s (tiles s, s+ES, ... of this CTA),
+    // so each set has ES tile periods to finish its tile.
+    const int eset = (warp - 4) >> 2;
     const int quarter = warp & 3;            // TMEM lane quarter this warp may read
     const int etid = threadIdx.x - 128 - eset * 128;  // 0..127 inside the set
     uint8_t* smem_gen = smem_raw + (sbase - smem_u32(smem_raw));
-    float* bias_s = reinterpret_cast<float*>(smem_gen + (epi_base - sbase)) + eset * 512;  // [2][256] per set
-    float* head_s = reinterpret_cast<float*>(smem_gen + (epi_base - sbase)) + 1024 + eset * 256;  // [3][64]+[3]
+    float* bias_s = reinterpret_cast<float*>(smem_gen + (epi_base - sbase) + eset * 3072);  // [2][256] per set
+    float* head_s = bias_s + 512;                                                            // [3][64]+[3]
     uint8_t* stg = smem_gen + (stg_base - sbase) + (eset * 4 + quarter) * 2048;  // 32 rows x 64 B
     if (p.epi_mode == EPI_HEAD) {
       for (int i = etid; i < 195; i += 128) head_s[i] = i < 192 ? __ldg(p.head_w + i) : __ldg(p.head_b + i - 192);
@@ -359,7 +364,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     uint32_t aph = 0;
     int tl = eset;
     const uint32_t t_empty_addr = CG == 2 ? mapa_shared(t_empty + 8 * acc, 0) : (t_empty + 8 * acc);
-    for (int tile = tile0 + eset * tstep; tile < p.total_tiles; tile += 2 * tstep, tl += 2, aph ^= 1) {
+    for (int tile = tile0 + eset * tstep; tile < p.total_tiles; tile += ES * tstep, tl += ES, aph ^= 1) {
       const int nt = tile / tiles_xy;
       const int r = tile % tiles_xy;
       int yt = r / p.tiles_x, xt = r - yt * p.tiles_x;
@@ -374,8 +379,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
           if (n < p.n_total) bv = __ldg(p.bias + (p.epi_mode == EPI_D2S ? n % p.d2s_cout : n));
           bias_s[bsel * 256 + i] = bv;
         }
-        if (eset == 0) asm volatile("bar.sync 1, 128;" ::: "memory");
-        else asm volatile("bar.sync 2, 128;" ::: "memory");
+        asm volatile("bar.sync %0, 128;" ::"r"(eset + 1) : "memory");
       }
 
       const int row = quarter * 32 + lane;
@@ -402,19 +406,6 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
 #pragma unroll 1
       for (int c64 = 0; c64 < live; ++c64) {
         const int n = nt * N_TILE + c64 * 64;
-        uint32_t v[2][32];
-        tmem_ld_32x32(taddr + c64 * 64, v[0]);
-        tmem_ld_32x32(taddr + c64 * 64 + 32, v[1]);
-        tmem_wait_ld();
-        if (c64 == live - 1) {  // accumulator fully read: hand it back to the MMA warp
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) {
-            if (CG == 2) mbar_arrive_cluster(t_empty_addr);
-            else mbar_arrive(t_empty_addr);
-          }
-          if (quarter == 0) NIND_TRACE(tl, TR_EPI_TMEM);
-        }
         long long off = pix_off;
         if (p.epi_mode == EPI_D2S) {
           const int q = n / p.d2s_cout;
@@ -422,22 +413,39 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         } else {
           off += n;
         }
-#pragma unroll
+#pragma unroll 1
         for (int half = 0; half < 2; ++half) {
+          uint32_t v[32];
+          tmem_ld_32x32(taddr + c64 * 64 + half * 32, v);
+          tmem_wait_ld();
+          if (half == 1 && c64 == live - 1) {  // accumulator fully read: hand it back to the MMA warp
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) {
+              if (CG == 2) mbar_arrive_cluster(t_empty_addr);
+              else mbar_arrive(t_empty_addr);
+            }
+            if (quarter == 0) NIND_TRACE(tl, TR_EPI_TMEM);
+          }
           float f[32];
           const float4* bp = reinterpret_cast<const float4*>(bias_s + bsel * 256 + c64 * 64 + half * 32);
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
             const float4 bb = bp[j];
-            f[4 * j + 0] = __uint_as_float(v[half][4 * j + 0]) + bb.x;
-            f[4 * j + 1] = __uint_as_float(v[half][4 * j + 1]) + bb.y;
-            f[4 * j + 2] = __uint_as_float(v[half][4 * j + 2]) + bb.z;
-            f[4 * j + 3] = __uint_as_float(v[half][4 * j + 3]) + bb.w;
+            f[4 * j + 0] = __uint_as_float(v[4 * j + 0]) + bb.x;
+            f[4 * j + 1] = __uint_as_float(v[4 * j + 1]) + bb.y;
+            f[4 * j + 2] = __uint_as_float(v[4 * j + 2]) + bb.z;
+            f[4 * j + 3] = __uint_as_float(v[4 * j + 3]) + bb.w;
           }
           if (p.act == ACT_PRELU) {  // also ReLU (slope 0)
             const float sl = p.slope;
+            if (sl >= 0.f && sl <= 1.f) {  // max(x, a*x) == PReLU for 0 <= a <= 1: FMUL + FMNMX
 #pragma unroll
-            for (int j = 0; j < 32; ++j) f[j] = f[j] > 0.f ? f[j] : f[j] * sl;
+              for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], f[j] * sl);
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) f[j] = f[j] > 0.f ? f[j] : f[j] * sl;
+            }
           } else if (p.act == ACT_ELU) {
 #pragma unroll
             for (int j = 0; j < 32; ++j) f[j] = f[j] > 0.f ? f[j] : (__expf(f[j]) - 1.f);

@@ -280,7 +280,7 @@ inline cudaError_t igemm_launch_t(const IgemmLaunch& L, const IgemmParams& p, cu
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof cfg);
   cfg.gridDim = dim3(L.grid);
-  cfg.blockDim = dim3(IG_THREADS);
+  cfg.blockDim = dim3(ig_threads(N));
   cfg.dynamicSmemBytes = L.smem;
   cfg.stream = st;
   cudaLaunchAttribute attr[1];
