@@ -35,12 +35,15 @@ enum ActKind : int { ACT_NONE = 0, ACT_PRELU = 1, ACT_ELU = 2, ACT_HARDSWISH = 3
 
 constexpr int IG_MAX_STAGES = 32;
 constexpr int IG_BAR_BYTES = 2048;     // mbarriers + TMEM base slot
-constexpr int IG_MAX_SETS = 3;         // epilogue warp sets (= TMEM accumulator stages)
+#ifndef NIND_SETS64
+#define NIND_SETS64 4
+#endif
+constexpr int IG_MAX_SETS = 4;         // epilogue warp sets (= TMEM accumulator stages)
 constexpr int IG_EPI_BYTES = IG_MAX_SETS * 3072;  // per set: staged bias [2][256] fp32 + head weights [3][64]+[3]
 constexpr int IG_SET_STAGE_BYTES = 8192;          // per set: 4 warps x 32 rows x 64 B of store staging
 // Epilogue sets per kernel: N_TILE = 64 layers are epilogue-bound with two sets (their MMA phase per tile
-// is short), and their accumulators are small, so they get three.
-__host__ __device__ constexpr int ig_sets(int n_tile) { return n_tile == 64 ? 3 : 2; }
+// is short), and their accumulators are small, so they get four (B200 A/B, same box: 64->64 572 / 651 / 680 TFLOP/s with 2 / 3 / 4 sets).
+__host__ __device__ constexpr int ig_sets(int n_tile) { return n_tile == 64 ? NIND_SETS64 : 2; }
 __host__ __device__ constexpr int ig_threads(int n_tile) { return 128 + 128 * ig_sets(n_tile); }
 constexpr int IG_TILE_H = 16;
 constexpr int IG_TILE_W = 8;
