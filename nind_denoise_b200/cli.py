@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Drop-in for the reference's tiled-inference script:
 
-    python -m nind_denoise_b200.denoise_image --network UtNet --model_path generator_650.pt \\
+    python -m nind_denoise_b200.cli --network UtNet --model_path generator_650.pt \\
            --input in_s1.tif --output out_s1_denoised.tiff
 
 Same flags and file conventions as /root/reference/src/nind_denoise/denoise_image.py:181-200 (so

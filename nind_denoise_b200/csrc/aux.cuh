@@ -53,6 +53,53 @@ __global__ void __launch_bounds__(256) gather_im2col_kernel(const GatherParams p
   }
 }
 
+// ------------------------------------------------------------------ crop gather -> padded 8-channel tensor
+// Same indexing as gather_im2col_kernel, but writes the PADDED crop itself (no im2col) as 8 bf16 channels
+// per pixel — R,G,B hi parts, R,G,B lo parts (x - bf16(x)), two zeros = 16 B — for the first layer's
+// 3x3 implicit GEMM (igemm_kernel C8 mode).  out_h/out_w = crop + 2*pad.
+__global__ void __launch_bounds__(256) gather_pad8_kernel(const GatherParams p) {
+  const long long total = (long long)p.n_crops * p.out_h * p.out_w;
+  for (long long gid = blockIdx.x * (long long)blockDim.x + threadIdx.x; gid < total;
+       gid += (long long)gridDim.x * blockDim.x) {
+    long long pix = gid;
+    const int px = (int)(pix % p.out_w);
+    pix /= p.out_w;
+    const int py = (int)(pix % p.out_h);
+    const int b = (int)(pix / p.out_h);
+    int x0 = 0, y0 = 0;
+    if (p.origin) {
+      const int2 o = p.origin[b];
+      x0 = o.x;
+      y0 = o.y;
+    }
+    int r = py - p.pad, q = px - p.pad;  // crop coordinates
+    bool inside = true;
+    if (p.reflect) {
+      r = r < 0 ? -r : (r >= p.crop_h ? 2 * p.crop_h - 2 - r : r);
+      q = q < 0 ? -q : (q >= p.crop_w ? 2 * p.crop_w - 2 - q : q);
+    } else {
+      inside = r >= 0 && r < p.crop_h && q >= 0 && q < p.crop_w;
+    }
+    float hi[3] = {0.f, 0.f, 0.f}, lo[3] = {0.f, 0.f, 0.f};
+    if (inside) {
+      const float* img = p.src + b * p.src_img + (long long)sym_index(y0 + r, p.src_h) * p.src_w +
+                         sym_index(x0 + q, p.src_w);
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        const float f = __ldg(img + c * p.src_plane);
+        hi[c] = __bfloat162float(__float2bfloat16_rn(f));
+        lo[c] = f - hi[c];
+      }
+    }
+    uint4 o;
+    o.x = pack_bf16x2(hi[0], hi[1]);
+    o.y = pack_bf16x2(hi[2], lo[0]);
+    o.z = pack_bf16x2(lo[1], lo[2]);
+    o.w = 0u;
+    reinterpret_cast<uint4*>(p.dst)[gid] = o;
+  }
+}
+
 // ------------------------------------------------------------------ 2x2 max-pool (NHWC bf16)
 // nn.MaxPool2d(2) (UtNet.py:34, ThirdPartyNets.py:93).  `in`/`out` are already offset to the first
 // interior pixel and the channel sub-range; strides in elements.

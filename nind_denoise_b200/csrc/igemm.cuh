@@ -25,7 +25,6 @@
 //              global stores (8 pixels x 64 B per warp instruction); the epilogue of a tile overlaps
 //              the MMAs of the next two tiles.
 #pragma once
-#include "gather_common.cuh"
 #include "ptx.cuh"
 
 namespace nind {
@@ -86,7 +85,6 @@ struct IgemmParams {
   int head_sigmoid;
   int* err;
   long long* trace;        // optional [64 tiles][8 events] clock64 stamps written by CTA 0 (debug)
-  GatherParams g;          // GATHER kernels only: source image / crop table of the fused first layer
 };
 
 // pipeline trace events (CTA 0 only, first 64 tiles): see tools/probe.cu "trace"
@@ -109,11 +107,12 @@ __host__ __device__ inline size_t igemm_smem_bytes(int n_tile, int tps, int cg, 
 // the weight tile (N_TILE/2 rows), which halves the weight shared-memory reads and L2 traffic per SM.
 // In a pair all "full" barriers and the TMEM-empty barriers live in CTA 0 (the leader, which issues
 // the MMAs); "empty" / TMEM-full barriers are per CTA and signalled by multicast commits.
-// GATHER: the first layer (C_in = 3).  Instead of TMA-loading an im2col tensor from HBM, warps 0 and 3
-// build each 128 x 64 A tile directly in (128B-swizzled) shared memory from the fp32 image — crop
-// mirror padding, in-network reflect/zero pad and the hi/lo bf16 split included — so the 128 B/pixel
-// im2col tensor never exists in HBM.  (taps = 1, one 64-wide K chunk, CG = 1, weights stationary.)
-template <int N_TILE, int TPS, int CG, bool GATHER = false>
+// C8: the first layer (C_in = 3) as a true 3x3 implicit GEMM over an 8-channel NHWC tensor (RGB hi, RGB lo,
+// two zeros = 16 B per pixel) instead of a 64-wide im2col: the patch is a [8 ch, 10 px, 18 rows] TMA box
+// WITHOUT swizzle, and one K=16 MMA covers two taps x 8 channels through the no-swizzle descriptor's
+// leading-dimension offset (LBO = distance between the two taps' pixels, SBO = one patch row); five MMAs
+// per tile (the tenth half-K has zero weights).  Descriptor semantics verified by `tools/probe desc0`.
+template <int N_TILE, int TPS, int CG, bool C8 = false>
 __global__ void __launch_bounds__(ig_threads(N_TILE), 1)
 igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
              const IgemmParams p) {
@@ -147,7 +146,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
     for (int s = 0; s < p.sa; ++s) {
-      mbar_init(a_full + 8 * s, GATHER ? 2 : 1);  // GATHER: one arrival per builder warp
+      mbar_init(a_full + 8 * s, 1);
       mbar_init(a_empty + 8 * s, 1);
     }
     for (int s = 0; s < p.sb; ++s) {
@@ -181,48 +180,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
   const int groups = p.taps / TPS;  // weight stages per 64-channel chunk
   const int tile0 = blockIdx.x / CG, tstep = gridDim.x / CG;
 
-  if (GATHER && (warp == 0 || warp == 3)) {
-    // ------------------------------------------------ software A-tile builders (fused gather + im2col)
-    const int half = warp == 0 ? 0 : 1;  // rows [0,64) / [64,128) of every tile
-    uint8_t* smem_gen = smem_raw + (sbase - smem_u32(smem_raw));
-    uint32_t s = 0, ph = 0;
-    int tl = 0;
-    for (int tile = tile0; tile < p.total_tiles; tile += tstep, ++tl) {
-      const int r = tile % tiles_xy;
-      const int yt = r / p.tiles_x, xt = r - yt * p.tiles_x;
-      mbar_wait(a_empty + 8 * s, ph ^ 1, p.err, 1);
-      if (half == 0) NIND_TRACE(tl, TR_A_ISSUE);
-      uint8_t* stage = smem_gen + (size_t)s * p.a_stage_bytes;
-#pragma unroll 1
-      for (int rr = 0; rr < 2; ++rr) {
-        const int row = half * 64 + rr * 32 + lane;
-        const int yflat = yt * IG_TILE_H + (row >> 3);
-        const int x = xt * IG_TILE_W + (row & 7);
-        const int b = yflat / p.hs_in;
-        const int y = yflat - b * p.hs_in;
-        float h[64];
-        if (yflat < p.rows_total && x < p.w_valid) {
-          im2col_row(p.g, b, y, x, h);
-        } else {
-#pragma unroll
-          for (int k = 0; k < 64; ++k) h[k] = 0.f;
-        }
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          uint4 o;
-          o.x = pack_bf16x2(h[8 * j + 0], h[8 * j + 1]);
-          o.y = pack_bf16x2(h[8 * j + 2], h[8 * j + 3]);
-          o.z = pack_bf16x2(h[8 * j + 4], h[8 * j + 5]);
-          o.w = pack_bf16x2(h[8 * j + 6], h[8 * j + 7]);
-          *reinterpret_cast<uint4*>(stage + row * 128 + ((j ^ (row & 7)) << 4)) = o;  // SWIZZLE_128B
-        }
-      }
-      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic writes -> UMMA (async proxy)
-      __syncwarp();
-      if (lane == 0) mbar_arrive(a_full + 8 * s);
-      if (++s == (uint32_t)p.sa) { s = 0; ph ^= 1; }
-    }
-  } else if (warp == 0) {
+  if (warp == 0) {
     // ------------------------------------------------ activation-patch producer
     if (lane == 0) {
       uint32_t s = 0, ph = 0;
@@ -253,7 +211,11 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     if (lane == 0) {
       uint32_t s = 0, ph = 0;
       int tl = 0;
-      for (int tile = tile0; tile < p.total_tiles; tile += tstep, ++tl) {
+      if (C8) {  // all five (tap pair) x (two K halves) weight blocks: [10][64][8] bf16, loaded once
+        mbar_arrive_expect_tx(b_full, 10240);
+        tma_load_3d(b_base, &tmB, b_full, 0, 0, 0);
+      }
+      for (int tile = tile0; tile < p.total_tiles && !C8; tile += tstep, ++tl) {
         if (p.ws && tl > 0) break;
         const int nt = tile / tiles_xy;
         for (int kc = 0; kc < p.kchunks; ++kc) {
@@ -293,7 +255,31 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       NIND_TRACE(tl, TR_MMA_TEMPTY);
       const uint32_t d = tmem_base + acc * N_TILE;
       uint32_t accum = 0;
-      for (int kc = 0; kc < p.kchunks; ++kc) {
+      if (C8) {
+        mbar_wait(a_full + 8 * sa_i, pha, p.err, 4);
+        NIND_TRACE(tl, TR_MMA_AFULL);
+        if (tl == 0) mbar_wait(b_full, 0, p.err, 5);
+        tc_fence_after();
+        // patch pixel (py, px) lives at (py*10 + px) * 16 B; tap t = ky*3 + kx
+        constexpr uint32_t HI_A = (160u >> 4) | (1u << 14);            // SBO = one patch row (10 px), no swizzle
+        constexpr uint32_t HI_B = (128u >> 4) | (1u << 14);            // SBO = 8 weight rows
+        const uint32_t a0 = ((a_base + sa_i * p.a_stage_bytes) >> 4) & 0x3FFF;
+        const uint32_t b0 = (b_base >> 4) & 0x3FFF;
+        if (elect_one_sync()) {
+          // (first tap pixel offset, LBO in pixels): taps (0,1) (2,3) (4,5) (6,7) (7*,8); 7* has zero weights
+          const uint32_t off[5] = {0, 2, 11, 20, 21}, lbo[5] = {1, 8, 1, 1, 1};
+#pragma unroll
+          for (int j = 0; j < 5; ++j) {
+            umma_bf16_lohi(d, (a0 + off[j]) | (lbo[j] << 16), HI_A, (b0 + j * 128) | ((1024u >> 4) << 16), HI_B, IDESC,
+                           accum);
+            accum = 1;
+          }
+          umma_commit(a_empty + 8 * sa_i);
+        }
+        __syncwarp();
+        if (++sa_i == (uint32_t)p.sa) { sa_i = 0; pha ^= 1; }
+      }
+      for (int kc = 0; kc < p.kchunks && !C8; ++kc) {
         mbar_wait(a_full + 8 * sa_i, pha, p.err, 4);
         if (kc == 0) NIND_TRACE(tl, TR_MMA_AFULL);
         const uint32_t a_lo0 = (((a_base + sa_i * p.a_stage_bytes) >> 4) & 0x3FFF) | (1u << 16);

@@ -38,8 +38,7 @@ struct ConvSpec {
   // tuning
   int n_tile = 0;     // 0 = auto
   int cg = 0;         // CTAs per tile group: 0 = auto, 1, or 2 (cta_group::2 pair)
-  bool gather = false;  // fused first layer; `in` then only describes the geometry [B, out_h, out_w, 64]
-  GatherParams g;
+  bool c8 = false;    // first layer over the 8-channel padded-crop tensor (C_in = 3 as hi/lo bf16)
   int force_ws = -1;  // -1 = auto
   int max_ctas = 0;   // 0 = number of SMs
 };
@@ -48,7 +47,7 @@ struct IgemmLaunch {
   CUtensorMap tmA, tmB;
   IgemmParams p;
   int n_tile = 0, tps = 1, cg = 1;
-  bool gather = false;  // fused first layer: A tiles built in shared memory from the fp32 image
+  bool c8 = false;  // first layer: 3x3 conv over an 8-channel (16 B/pixel) tensor, no-swizzle descriptors
   size_t smem = 0;
   int grid = 0;
   double flops = 0;  // algorithmic 2*MAC actually useful (valid outputs only)
@@ -74,7 +73,7 @@ inline PFN_tmapEncodeTiled tmap_encoder() {
 // bf16 tensor map, 128-byte swizzle, zero OOB fill.  dims/strides innermost first.
 inline bool encode_tmap_bf16(CUtensorMap* m, const void* base, int rank, const uint64_t* dims,
                              const uint64_t* strides_bytes /* rank-1 */, const uint32_t* box,
-                             std::string* why) {
+                             std::string* why, bool swizzle128 = true) {
   PFN_tmapEncodeTiled enc = tmap_encoder();
   if (!enc) {
     if (why) *why = "cuTensorMapEncodeTiled entry point not available";
@@ -89,7 +88,8 @@ inline bool encode_tmap_bf16(CUtensorMap* m, const void* base, int rank, const u
     if (i + 1 < rank) gs[i] = strides_bytes[i];
   }
   CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), gd, gs,
-                   bx, es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                   bx, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE,
                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     if (why) {
@@ -124,7 +124,9 @@ inline bool build_igemm(const ConvSpec& s, IgemmLaunch* L, std::string* why) {
     return false;
   };
   if (s.taps != 9 && s.taps != 1) return fail("taps must be 1 or 9");
-  if (s.cin % 64 != 0 || s.cin <= 0) return fail("input channels must be a multiple of 64");
+  if (!s.c8 && (s.cin % 64 != 0 || s.cin <= 0)) return fail("input channels must be a multiple of 64");
+  if (s.c8 && (s.taps != 9 || s.cin != 8 || s.n_total != 64 || s.in.c != 8 || s.in_coff != 0))
+    return fail("the 8-channel first-layer path needs taps=9, C=8, N=64");
   if (s.n_total % 64 != 0) return fail("output columns must be a multiple of 64");
   if (s.epi_mode == EPI_D2S && (s.d2s_cout % 64 != 0)) return fail("depth-to-space needs C_out multiple of 64");
   if (s.in.c % 8 != 0) return fail("buffer channel count must be a multiple of 8");
@@ -146,11 +148,8 @@ inline bool build_igemm(const ConvSpec& s, IgemmLaunch* L, std::string* why) {
   int cg = s.cg;
   // measured on B200 (profiles/r01_probe_cta_pair.log): the CTA pair wins on every 3x3 layer except
   // 64->128 (-3 %), and on the 1x1 / 2x2-s2 GEMMs only when K is large (C_in >= 512)
-  if (s.gather) {
-    if (s.taps != 1 || s.cin != 64 || s.n_total != 64) return fail("fused gather needs taps=1, K=64, N=64");
-    cg = 1;
-  }
-  L->gather = s.gather;
+  if (s.c8) cg = 1;
+  L->c8 = s.c8;
   if (cg == 0) {
     const bool pair = s.taps == 9 ? (s.cin >= 128 || s.n_total <= 64) : (s.cin >= 512);
     cg = pair ? 2 : 1;
@@ -165,7 +164,7 @@ inline bool build_igemm(const ConvSpec& s, IgemmLaunch* L, std::string* why) {
   p.tiles_y = p.pair_y ? (tiles_y_real + 1) / 2 : tiles_y_real;
   p.tiles_n = (s.n_total + n_tile - 1) / n_tile;
   p.total_tiles = p.tiles_x * p.tiles_y * p.tiles_n;
-  p.kchunks = s.cin / 64;
+  p.kchunks = s.c8 ? 1 : s.cin / 64;
   p.taps = s.taps;
 
   // A operand: one TMA box per (tile, 64-channel chunk).  3x3: the (16+2) x (8+2) pixel patch, whose
@@ -175,15 +174,18 @@ inline bool build_igemm(const ConvSpec& s, IgemmLaunch* L, std::string* why) {
   if (s.taps == 1) {
     boxA[0] = 64; boxA[1] = 8; boxA[2] = 16;
     p.a_tx_bytes = 16384; p.a_stage_bytes = 16384; p.a_sbo = 1024;
+  } else if (s.c8) {
+    boxA[0] = 8; boxA[1] = 10; boxA[2] = 18;
+    p.a_tx_bytes = 10 * 18 * 16; p.a_stage_bytes = 3072; p.a_sbo = 160;
   } else {
     boxA[0] = 64; boxA[1] = 10; boxA[2] = 18;
     p.a_tx_bytes = 10 * 18 * 128; p.a_stage_bytes = 23552; p.a_sbo = 1280;
   }
 
   // pipeline depth / weights-stationary decision
-  const int tps = (s.taps == 9 && n_tile <= 128) ? 3 : 1;  // taps per weight stage
+  const int tps = s.c8 ? 1 : ((s.taps == 9 && n_tile <= 128) ? 3 : 1);  // taps per weight stage
   L->tps = tps;
-  const int kt = p.kchunks * (p.taps / tps);
+  const int kt = s.c8 ? 2 : p.kchunks * (p.taps / tps);  // c8: 10 KB of weights in two 8 KB "stages"
   bool ws = false;
   if (s.force_ws != 0 && p.tiles_n == 1 && kt <= IG_MAX_STAGES &&
       igemm_smem_bytes(n_tile, tps, cg, 2, p.a_stage_bytes, kt) <= IG_SMEM_LIMIT)
@@ -213,17 +215,20 @@ inline bool build_igemm(const ConvSpec& s, IgemmLaunch* L, std::string* why) {
   {
     const uint64_t dims[3] = {(uint64_t)s.cin, (uint64_t)s.in.ws, (uint64_t)p.rows_total};
     const uint64_t strides[2] = {(uint64_t)s.in.c * 2, (uint64_t)s.in.ws * s.in.c * 2};
-    if (!s.gather && !encode_tmap_bf16(&L->tmA, s.in.ptr + s.in_coff, 3, dims, strides, boxA, why)) return false;
-    const uint64_t dimsB[2] = {(uint64_t)s.cin, (uint64_t)s.taps * s.n_total};
-    const uint64_t stridesB[1] = {(uint64_t)s.cin * 2};
-    const uint32_t boxB[2] = {64, (uint32_t)(n_tile / cg)};
-    if (!encode_tmap_bf16(&L->tmB, s.w, 2, dimsB, stridesB, boxB, why)) return false;
+    if (!encode_tmap_bf16(&L->tmA, s.in.ptr + s.in_coff, 3, dims, strides, boxA, why, !s.c8)) return false;
+    if (s.c8) {  // weights [10 half-K blocks][64 n][8 ch]
+      const uint64_t dimsB[3] = {8, 64, 10};
+      const uint64_t stridesB[2] = {16, 1024};
+      const uint32_t boxB[3] = {8, 64, 10};
+      if (!encode_tmap_bf16(&L->tmB, s.w, 3, dimsB, stridesB, boxB, why, false)) return false;
+    } else {
+      const uint64_t dimsB[2] = {(uint64_t)s.cin, (uint64_t)s.taps * s.n_total};
+      const uint64_t stridesB[1] = {(uint64_t)s.cin * 2};
+      const uint32_t boxB[2] = {64, (uint32_t)(n_tile / cg)};
+      if (!encode_tmap_bf16(&L->tmB, s.w, 2, dimsB, stridesB, boxB, why)) return false;
+    }
   }
 
-  if (s.gather) {
-    L->tmA = L->tmB;  // unused by the kernel
-    p.g = s.g;
-  }
   // epilogue
   p.n_total = s.n_total;
   p.epi_mode = s.epi_mode;
@@ -264,7 +269,7 @@ inline bool build_igemm(const ConvSpec& s, IgemmLaunch* L, std::string* why) {
     const int groups_max = std::max(1, sms / cg);
     L->grid = cg * (p.total_tiles < groups_max ? p.total_tiles : groups_max);
   }
-  L->flops = 2.0 * s.in.b * (double)p.h_valid * p.w_valid * s.n_total * s.cin * s.taps;
+  L->flops = 2.0 * s.in.b * (double)p.h_valid * p.w_valid * s.n_total * (s.c8 ? 3 : s.cin) * s.taps;
   return true;
 }
 
@@ -298,7 +303,7 @@ inline cudaError_t launch_igemm(const IgemmLaunch& L, int* err_flag, cudaStream_
   IgemmParams p = L.p;
   p.err = err_flag;
   p.trace = trace;
-  if (L.gather) return igemm_launch_t<64, 1, 1, true>(L, p, st);
+  if (L.c8) return igemm_launch_t<64, 1, 1, true>(L, p, st);
   const int key = L.n_tile * 100 + L.tps * 10 + L.cg;
   switch (key) {
     case 6411: return igemm_launch_t<64, 1, 1>(L, p, st);

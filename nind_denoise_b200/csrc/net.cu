@@ -50,6 +50,7 @@ struct Step {
   PoolParams pl;
   double flops = 0;
   double bytes = 0;  // algorithmic bytes moved (memory-bound steps)
+  bool pad8 = false; // STEP_GATHER: padded 8-channel crop (C8 first layer) instead of the 64-wide im2col
 };
 
 struct Plan {
@@ -120,9 +121,10 @@ struct nind_net {
   std::vector<cudaEvent_t> ev_in, ev_done;
   // options
   int n_tile_deep = 256, max_ctas = 0, cg = 0, fuse_pool = 1;
-  // Fused gather+first-conv (A tiles built in smem by two warps) is correct but latency-bound with so few
-  // builder warps: 7.5 ms vs 1.2 + 1.7 ms for the separate gather kernel + TMA-fed GEMM at cs 504 -> off.
-  int fuse_first = 0;
+  // First layer: 3x3 implicit GEMM over the 8-channel padded-crop tensor (1) or K=64 GEMM over an im2col (0).
+  // (A third variant, building the im2col tile in shared memory inside the GEMM kernel with two builder
+  // warps, was correct but latency-bound: 7.5 ms vs 2.9 ms per 24 MP image; removed.)
+  int first_c8 = 1;
   // timing
   int timing = 0;
   std::vector<std::string> t_names;
@@ -236,6 +238,25 @@ void pack_first(const float* w, int co, const float* scale, std::vector<__nv_bfl
     }
 }
 
+// First conv [co][3][3][3] for the 8-channel path: [5 MMAs][2 K-halves][co][8], K-half (j,h) = tap 2j+h except the
+// last MMA, whose halves are (zero block, tap 8); the 8 channels are R,G,B hi | R,G,B lo | 0 0, so hi and lo
+// parts meet the same weight.
+void pack_first_c8(const float* w, int co, const float* scale, std::vector<__nv_bfloat16>* out) {
+  out->assign((size_t)10 * co * 8, __float2bfloat16(0.f));
+  const int tap_of[10] = {0, 1, 2, 3, 4, 5, 6, 7, -1, 8};
+  for (int blk = 0; blk < 10; ++blk) {
+    const int t = tap_of[blk];
+    if (t < 0) continue;
+    for (int o = 0; o < co; ++o)
+      for (int c = 0; c < 3; ++c) {
+        float v = w[((size_t)o * 3 + c) * 9 + t];
+        if (scale) v *= scale[o];
+        (*out)[((size_t)blk * co + o) * 8 + c] = __float2bfloat16(v);
+        (*out)[((size_t)blk * co + o) * 8 + 3 + c] = __float2bfloat16(v);
+      }
+  }
+}
+
 int load_head(nind_net* net, const nind_tensor* ts, int n, const std::string& name) {
   HostTensor w, b;
   int rc;
@@ -287,6 +308,10 @@ int load_utnet(nind_net* net, const nind_tensor* ts, int n) {
     std::vector<__nv_bfloat16> pw;
     pack_first(w.v.data(), f, nullptr, &pw);
     if ((rc = upload_layer(net, "convs1.0", L, pw, b.v))) return rc;
+    PackedLayer L8 = L;
+    L8.w = nullptr; L8.bias = nullptr; L8.cin = 8; L8.taps = 9;
+    pack_first_c8(w.v.data(), f, nullptr, &pw);
+    if ((rc = upload_layer(net, "convs1.0@c8", L8, pw, b.v))) return rc;
   }
   if ((rc = conv("convs1.2", "convs1.3", f, f, false))) return rc;
   int c = f;
@@ -337,6 +362,10 @@ int load_unet(nind_net* net, const nind_tensor* ts, int n) {
     L.cout = co; L.n_total = co; L.act = ACT_PRELU; L.slope = 0.f;  // ReLU
     std::vector<__nv_bfloat16> pw;
     if (first) {
+      PackedLayer L8 = L;
+      L8.cin = 8; L8.taps = 9;
+      pack_first_c8(w.v.data(), co, scale.data(), &pw);
+      if ((rc = upload_layer(net, conv_name + "@c8", L8, pw, bias))) return rc;
       L.cin = 64; L.taps = 1;
       pack_first(w.v.data(), co, scale.data(), &pw);
     } else {
@@ -403,7 +432,7 @@ struct PlanBuilder {
   // 3x3 / 1x1 layer writing bf16 (EPI_STORE or EPI_D2S)
   void conv(const std::string& name, const ActBuf& in, int in_coff, const ActBuf& out, int out_coff,
             int out_halo, int epi, const ActBuf* pool = nullptr, int pool_halo = 0,
-            const GatherParams* fused_gather = nullptr) {
+            bool c8 = false) {
     if (rc) return;
     auto it = net->layers.find(name);
     if (it == net->layers.end()) { rc = fail(NIND_E_WEIGHTS, "layer not loaded: " + name); return; }
@@ -418,7 +447,7 @@ struct PlanBuilder {
       s.pool = *pool; s.pool_halo = pool_halo;
       last_pool_fused = true;
     }
-    if (fused_gather) { s.gather = true; s.g = *fused_gather; }
+    s.c8 = c8;
     s.max_ctas = net->max_ctas;
     s.cg = net->cg;
     if (L.n_total >= 256) s.n_tile = net->n_tile_deep;
@@ -427,10 +456,6 @@ struct PlanBuilder {
     std::string why;
     if (!build_igemm(s, &st.ig, &why)) { rc = fail(NIND_E_INVALID, name + ": " + why); return; }
     st.flops = st.ig.flops;
-    if (fused_gather) {
-      plan->gather_step = (int)plan->steps.size();
-      st.name = name + "+gather";
-    }
     {
       const IgemmParams& q = st.ig.p;
       const double in_b = (double)in.b * in.hs * in.ws * L.cin * 2;
@@ -484,13 +509,14 @@ struct PlanBuilder {
     return g;
   }
 
-  void gather(const ActBuf& x0, int crop_h, int crop_w, int pad, int reflect) {
+  void gather(const ActBuf& x0, int crop_h, int crop_w, int pad, int reflect, bool pad8 = false) {
     if (rc) return;
     Step st;
-    st.kind = STEP_GATHER; st.name = "gather+im2col";
+    st.kind = STEP_GATHER; st.name = pad8 ? "gather+pad8" : "gather+im2col";
+    st.pad8 = pad8;
     GatherParams& g = st.g;
     g = gather_geom(x0, crop_h, crop_w, pad, reflect);
-    st.bytes = (double)x0.b * (3.0 * crop_h * crop_w * 4 + (double)x0.hs * x0.ws * 128);
+    st.bytes = (double)x0.b * (3.0 * crop_h * crop_w * 4 + (double)x0.hs * x0.ws * x0.c * 2);
     plan->gather_step = (int)plan->steps.size();
     plan->steps.push_back(st);
   }
@@ -512,10 +538,12 @@ int build_utnet_plan(nind_net* net, Plan* plan, int B, int H, int W) {
     if (l < 4) { eh[l + 1] = ph[l] - 4; ew[l + 1] = pw[l] - 4; }
   }
   // encoder
-  ActBuf x0;  // im2col of the padded crops; only materialised when the first layer is not fused
-  x0.b = B; x0.hs = H + 2; x0.ws = W + 2; x0.c = 64;
-  GatherParams g0 = PlanBuilder::gather_geom(x0, H, W, 2, 1);
-  if (!net->fuse_first) {
+  // first layer input: the padded crops as 8 bf16 channels/pixel (default), or the 64-wide im2col
+  ActBuf x0;
+  if (net->first_c8) {
+    x0 = pb.alloc(B, H + 4, W + 4, 8);
+    pb.gather(x0, H, W, 2, 1, true);
+  } else {
     x0 = pb.alloc(B, H + 2, W + 2, 64);
     pb.gather(x0, H, W, 2, 1);
   }
@@ -525,7 +553,7 @@ int build_utnet_plan(nind_net* net, Plan* plan, int B, int H, int W) {
     const int c = f << (l - 1);
     const std::string p = "convs" + std::to_string(l);
     ActBuf a = pb.alloc(B, eh[l] + 2, ew[l] + 2, c);
-    if (l == 1) pb.conv(p + ".0", x0, 0, a, 0, 0, EPI_STORE, nullptr, 0, net->fuse_first ? &g0 : nullptr);
+    if (l == 1) pb.conv(net->first_c8 ? p + ".0@c8" : p + ".0", x0, 0, a, 0, 0, EPI_STORE, nullptr, 0, net->first_c8);
     else pb.conv(p + ".0", cur, 0, a, 0, 0, EPI_STORE);
     cat[l] = pb.alloc(B, eh[l] + 4, ew[l] + 4, 2 * c);  // [up | skip], 2-px zero frame for the ConvT
     cur = pb.alloc(B, ph[l], pw[l], c);
@@ -568,9 +596,10 @@ int build_unet_plan(nind_net* net, Plan* plan, int B, int H, int W) {
   for (int l = 0; l < 5; ++l) { sh[l] = H >> l; sw[l] = W >> l; }
   const int ch[5] = {64, 128, 256, 512, 512};
   ActBuf x0;
-  x0.b = B; x0.hs = H; x0.ws = W; x0.c = 64;
-  GatherParams g0 = PlanBuilder::gather_geom(x0, H, W, 1, 0);
-  if (!net->fuse_first) {
+  if (net->first_c8) {
+    x0 = pb.alloc(B, H + 2, W + 2, 8);
+    pb.gather(x0, H, W, 1, 0, true);
+  } else {
     x0 = pb.alloc(B, H, W, 64);
     pb.gather(x0, H, W, 1, 0);
   }
@@ -582,7 +611,7 @@ int build_unet_plan(nind_net* net, Plan* plan, int B, int H, int W) {
   for (int l = 0; l < 5; ++l) {
     const std::string p = enc_name[l];
     ActBuf mid = pb.alloc(B, sh[l] + 2, sw[l] + 2, ch[l]);
-    if (l == 0) pb.conv(p + ".0", x0, 0, mid, 0, 1, EPI_STORE, nullptr, 0, net->fuse_first ? &g0 : nullptr);
+    if (l == 0) pb.conv(net->first_c8 ? p + ".0@c8" : p + ".0", x0, 0, mid, 0, 1, EPI_STORE, nullptr, 0, net->first_c8);
     else pb.conv(p + ".0", cur, 0, mid, 0, 1, EPI_STORE);
     if (l < 4) {
       cat[l] = pb.alloc(B, sh[l] + 2, sw[l] + 2, 2 * ch[l]);
@@ -646,16 +675,14 @@ int run_plan(nind_net* net, Plan* plan, const GatherParams& gsrc, float* head_ou
       GatherParams g = s.g;
       g.src = gsrc.src; g.src_img = gsrc.src_img; g.src_plane = gsrc.src_plane;
       g.src_w = gsrc.src_w; g.src_h = gsrc.src_h; g.origin = gsrc.origin;
-      gather_im2col_kernel<<<grid_for((long long)g.n_crops * g.out_h * g.out_w), 256, 0, st>>>(g);
+      if (s.pad8) gather_pad8_kernel<<<grid_for((long long)g.n_crops * g.out_h * g.out_w), 256, 0, st>>>(g);
+      else gather_im2col_kernel<<<grid_for((long long)g.n_crops * g.out_h * g.out_w), 256, 0, st>>>(g);
     } else if (s.kind == STEP_POOL) {
       maxpool2_kernel<<<grid_for((long long)s.pl.n * s.pl.ho * s.pl.wo * (s.pl.c / 8)), 256, 0, st>>>(s.pl);
     } else {
       IgemmLaunch L = s.ig;
       if ((int)i == plan->head_step) L.p.head_out = head_out;
-      if (L.gather) {
-        L.p.g.src = gsrc.src; L.p.g.src_img = gsrc.src_img; L.p.g.src_plane = gsrc.src_plane;
-        L.p.g.src_w = gsrc.src_w; L.p.g.src_h = gsrc.src_h; L.p.g.origin = gsrc.origin;
-      }
+
       cudaError_t e = launch_igemm(L, net->err_flag, st);
       if (e != cudaSuccess) return fail(NIND_E_CUDA, s.name + ": " + cudaGetErrorString(e));
     }
@@ -791,8 +818,8 @@ int nind_set_option(nind_net* net, const char* key, int value) {
     net->cg = value;
   } else if (k == "fuse_pool") {
     net->fuse_pool = value ? 1 : 0;
-  } else if (k == "fuse_first") {
-    net->fuse_first = value ? 1 : 0;
+  } else if (k == "first_c8") {
+    net->first_c8 = value ? 1 : 0;
   } else {
     return fail(NIND_E_INVALID, "unknown option " + k);
   }

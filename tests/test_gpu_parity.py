@@ -252,7 +252,7 @@ def test_kernel_variants_agree():
     torch.manual_seed(6)
     x = torch.rand(2, 3, 120, 136, device=dev())
     outs = {}
-    for name, opts in (("default", {}), ("unfused_pool", {"fuse_pool": 0}), ("fused_first", {"fuse_first": 1}),
+    for name, opts in (("default", {}), ("unfused_pool", {"fuse_pool": 0}), ("im2col_first", {"first_c8": 0}),
                        ("cta1", {"cta_group": 1}),
                        ("cta2", {"cta_group": 2}), ("n128", {"n_tile_deep": 128})):
         m = nb.UtNet().to(dev()).eval()
@@ -261,16 +261,20 @@ def test_kernel_variants_agree():
             m.set_option(k, v)
         outs[name] = m(x).cpu().numpy()
     assert np.array_equal(outs["default"], outs["unfused_pool"])
-    assert np.array_equal(outs["default"], outs["fused_first"])
+    # a different first-layer formulation changes fp32 summation order, which can flip bf16 roundings
+    # downstream: allow a few output ulps of the bf16 pipeline (sigma_out is 7e-3)
+    d = np.abs(outs["im2col_first"] - outs["default"]).max()
+    print(f"8-channel vs im2col first layer: max diff {d:.3e}")
+    assert d <= 3e-4
     for k in ("cta1", "cta2", "n128"):
         assert np.abs(outs[k] - outs["default"]).max() <= 2e-5, k
 
 
 def test_cli_shim_roundtrip(tmp_path, golden_networks):
-    """nind_denoise_b200.denoise_image: the reference script's flags and file conventions
+    """nind_denoise_b200.cli: the reference script's flags and file conventions
     (denoise_image.py:181-200; np_imgops.py:12-29; pt_helpers.py:22-40) around the GPU tiler."""
     import cv2
-    from nind_denoise_b200 import denoise_image as cli
+    from nind_denoise_b200 import cli
 
     N = golden_networks
     W, H, cs, ucs, ol = (int(v) for v in N["tiled_params"])

@@ -151,6 +151,108 @@ static int run_desc(int r0, int sbo, int bo_mode) {
   return bad ? 1 : 0;
 }
 
+
+// ------------------------------------------------------------------ SWIZZLE_NONE descriptor probe
+// A: P "pixels" of 8 bf16 (16 B) contiguous in smem; K = 16 = two 8-wide halves LBO apart; 8-row core
+// matrices (rows 16 B apart) SBO apart.  B: [2 halves][64 n][8] (LBO 1024, SBO 128).
+__global__ void __launch_bounds__(128, 1)
+desc0_probe_kernel(const __nv_bfloat16* gA, const __nv_bfloat16* gB, float* out, int r0, int lbo_px, int sbo_px,
+                   int swap, int* err) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* sgen = smem_raw + (sbase - smem_u32(smem_raw));
+  const uint32_t a_s = sbase;              // 1024 pixels x 16 B
+  const uint32_t b_s = sbase + 16384;      // 2 x 64 x 16 B
+  const uint32_t bar_mma = b_s + 2048;
+  const uint32_t slot = bar_mma + 8;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int i = threadIdx.x; i < 1024; i += 128) reinterpret_cast<uint4*>(sgen)[i] = reinterpret_cast<const uint4*>(gA)[i];
+  for (int i = threadIdx.x; i < 128; i += 128) reinterpret_cast<uint4*>(sgen + 16384)[i] = reinterpret_cast<const uint4*>(gB)[i];
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  if (threadIdx.x == 0) {
+    mbar_init(bar_mma, 1);
+    mbar_fence_init();
+  }
+  if (warp == 0) {
+    tmem_alloc(slot, 64);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(slot));
+  if (threadIdx.x == 0) {
+    auto desc = [&](uint32_t addr, uint32_t lbo, uint32_t sbo) {
+      uint64_t d = 0;
+      d |= (uint64_t)((addr >> 4) & 0x3FFF);
+      d |= (uint64_t)((lbo >> 4) & 0x3FFF) << 16;
+      d |= (uint64_t)((sbo >> 4) & 0x3FFF) << 32;
+      d |= (uint64_t)1 << 46;  // version; layout type 0 = SWIZZLE_NONE
+      return d;
+    };
+    const uint32_t la = lbo_px * 16, sa = sbo_px * 16;
+    const uint64_t da = swap ? desc(a_s + r0 * 16, sa, la) : desc(a_s + r0 * 16, la, sa);
+    const uint64_t db = swap ? desc(b_s, 128, 1024) : desc(b_s, 1024, 128);
+    umma_bf16(tmem_base, da, db, umma_idesc_bf16(128, 64), 0);
+    umma_commit(bar_mma);
+  }
+  __syncwarp();
+  mbar_wait(bar_mma, 0, err, 2);
+  tc_fence_after();
+  for (int c = 0; c < 2; ++c) {
+    uint32_t v[32];
+    tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(warp * 32) << 16) + c * 32, v);
+    tmem_wait_ld();
+    for (int j = 0; j < 32; ++j) out[(warp * 32 + lane) * 64 + c * 32 + j] = __uint_as_float(v[j]);
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem_base, 64);
+}
+
+static int run_desc0(int r0, int lbo_px, int sbo_px, int swap) {
+  const int P = 1024;
+  std::vector<__nv_bfloat16> hA(P * 8), hB(2 * 64 * 8);
+  std::vector<float> fA(P * 8), fB(2 * 64 * 8);
+  for (int i = 0; i < P * 8; ++i) { hA[i] = __float2bfloat16(frand()); fA[i] = __bfloat162float(hA[i]); }
+  for (int i = 0; i < 2 * 64 * 8; ++i) { hB[i] = __float2bfloat16(frand()); fB[i] = __bfloat162float(hB[i]); }
+  __nv_bfloat16 *dA, *dB;
+  float* dO;
+  int* dErr;
+  CK(cudaMalloc(&dA, hA.size() * 2));
+  CK(cudaMalloc(&dB, hB.size() * 2));
+  CK(cudaMalloc(&dO, 128 * 64 * 4));
+  CK(cudaMalloc(&dErr, 4));
+  CK(cudaMemset(dErr, 0, 4));
+  CK(cudaMemcpy(dA, hA.data(), hA.size() * 2, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(dB, hB.data(), hB.size() * 2, cudaMemcpyHostToDevice));
+  const size_t smem = 1024 + 16384 + 2048 + 64;
+  CK(cudaFuncSetAttribute(desc0_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  desc0_probe_kernel<<<1, 128, smem>>>(dA, dB, dO, r0, lbo_px, sbo_px, swap, dErr);
+  CK(cudaGetLastError());
+  cudaError_t e = cudaDeviceSynchronize();
+  if (e != cudaSuccess) { printf("DESC0 kernel failed: %s\n", cudaGetErrorString(e)); return 1; }
+  std::vector<float> hO(128 * 64);
+  CK(cudaMemcpy(hO.data(), dO, hO.size() * 4, cudaMemcpyDeviceToHost));
+  int bad = 0;
+  double maxerr = 0;
+  for (int i = 0; i < 128; ++i)
+    for (int n = 0; n < 64; ++n) {
+      float acc = 0;
+      for (int h = 0; h < 2; ++h) {
+        const int px = r0 + (i / 8) * sbo_px + (i % 8) + h * lbo_px;
+        for (int c = 0; c < 8; ++c) acc += fA[px * 8 + c] * fB[(h * 64 + n) * 8 + c];
+      }
+      const double d = fabs(acc - hO[i * 64 + n]);
+      if (d > maxerr) maxerr = d;
+      if (d > 1e-2) ++bad;
+    }
+  printf("DESC0 r0=%d lbo_px=%d sbo_px=%d swap=%d : maxerr=%.5f bad=%d/8192 -> %s\n", r0, lbo_px, sbo_px, swap, maxerr,
+         bad, bad == 0 ? "PASS" : "FAIL");
+  return bad ? 1 : 0;
+}
+
 // ------------------------------------------------------------------ naive reference conv
 // in: NHWC bf16 [B][Hs][Ws][C] (channels coff..coff+cin used); w: [taps][n_total][cin] bf16;
 // out: fp32 [B][Hv][Wv][n_total] after bias + activation.
@@ -191,7 +293,8 @@ static int run_conv(int argc, char** argv) {
   const int cg = argc > 14 ? atoi(argv[14]) : 0;
   const int tw = taps == 9 ? 3 : 1;
   const int Hv = Hs - (tw - 1), Wv = Ws - (tw - 1);
-  const int Cbuf = cin + 64, coff = 64;  // read a channel sub-range to exercise offsets
+  const bool c8 = cin == 8;              // first-layer mode: 8-channel input, no-swizzle descriptors
+  const int Cbuf = c8 ? 8 : cin + 64, coff = c8 ? 0 : 64;  // read a channel sub-range to exercise offsets
   const int act = ACT_PRELU;
   const float slope = 0.25f;
 
@@ -225,7 +328,19 @@ static int run_conv(int argc, char** argv) {
 
   ConvSpec s;
   s.in = ActBuf{din, B, Hs, Ws, Cbuf};
-  s.in_coff = coff; s.cin = cin; s.taps = taps; s.w = dw; s.n_total = n_total; s.bias = dbias;
+  __nv_bfloat16* dw8 = nullptr;
+  if (c8) {  // repack [t][n][8] -> [10 half-K blocks][n][8] with blocks = taps 0..7, zero, tap 8
+    std::vector<__nv_bfloat16> w8((size_t)10 * n_total * 8, __float2bfloat16(0.f));
+    const int tap_of[10] = {0, 1, 2, 3, 4, 5, 6, 7, -1, 8};
+    for (int blk = 0; blk < 10; ++blk)
+      if (tap_of[blk] >= 0)
+        for (int n = 0; n < n_total; ++n)
+          for (int c = 0; c < 8; ++c) w8[((size_t)blk * n_total + n) * 8 + c] = hw[((size_t)tap_of[blk] * n_total + n) * 8 + c];
+    CK(cudaMalloc(&dw8, w8.size() * 2));
+    CK(cudaMemcpy(dw8, w8.data(), w8.size() * 2, cudaMemcpyHostToDevice));
+    s.c8 = true;
+  }
+  s.in_coff = coff; s.cin = cin; s.taps = taps; s.w = c8 ? dw8 : dw; s.n_total = n_total; s.bias = dbias;
   s.act = act; s.slope = slope; s.epi_mode = epi; (void)a_mode; (void)bo_mode;
   s.n_tile = n_tile; s.force_ws = ws; s.max_ctas = ctas; s.cg = cg;
   const int halo = 2, ocoff = 32;
@@ -367,6 +482,10 @@ int main(int argc, char** argv) {
   if (!strcmp(argv[1], "desc")) {
     if (argc < 5) return 2;
     return run_desc(atoi(argv[2]), atoi(argv[3]), atoi(argv[4]));
+  }
+  if (!strcmp(argv[1], "desc0")) {
+    if (argc < 6) return 2;
+    return run_desc0(atoi(argv[2]), atoi(argv[3]), atoi(argv[4]), atoi(argv[5]));
   }
   if (!strcmp(argv[1], "conv")) return run_conv(argc, argv);
   return 2;
