@@ -197,6 +197,10 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
             if (cg_rank == 0) mbar_arrive_expect_tx(a_full + 8 * s, 2 * p.a_tx_bytes);
             tma_load_3d_cg2(a_base + s * p.a_stage_bytes, &tmA, mapa_shared(a_full + 8 * s, 0), kc * 64,
                             xt * IG_TILE_W, yt * IG_TILE_H);
+          } else if (C8) {
+            // 8-channel pixels are 16 B: a patch row (10 px) is one contiguous 160-byte TMA row
+            mbar_arrive_expect_tx(a_full + 8 * s, p.a_tx_bytes);
+            tma_load_2d(a_base + s * p.a_stage_bytes, &tmA, a_full + 8 * s, xt * IG_TILE_W * 8, yt * IG_TILE_H);
           } else {
             mbar_arrive_expect_tx(a_full + 8 * s, p.a_tx_bytes);
             tma_load_3d(a_base + s * p.a_stage_bytes, &tmA, a_full + 8 * s, kc * 64, xt * IG_TILE_W,

@@ -215,7 +215,14 @@ inline bool build_igemm(const ConvSpec& s, IgemmLaunch* L, std::string* why) {
   {
     const uint64_t dims[3] = {(uint64_t)s.cin, (uint64_t)s.in.ws, (uint64_t)p.rows_total};
     const uint64_t strides[2] = {(uint64_t)s.in.c * 2, (uint64_t)s.in.ws * s.in.c * 2};
-    if (!encode_tmap_bf16(&L->tmA, s.in.ptr + s.in_coff, 3, dims, strides, boxA, why, !s.c8)) return false;
+    if (s.c8) {  // rows of (x, c) flattened: 10 px x 8 ch = 160 contiguous bytes per patch row
+      const uint64_t dimsA[2] = {(uint64_t)s.in.ws * 8, (uint64_t)p.rows_total};
+      const uint64_t stridesA[1] = {(uint64_t)s.in.ws * 16};
+      const uint32_t boxA2[2] = {80, 18};
+      if (!encode_tmap_bf16(&L->tmA, s.in.ptr, 2, dimsA, stridesA, boxA2, why, false)) return false;
+    } else if (!encode_tmap_bf16(&L->tmA, s.in.ptr + s.in_coff, 3, dims, strides, boxA, why)) {
+      return false;
+    }
     if (s.c8) {  // weights [10 half-K blocks][64 n][8 ch]
       const uint64_t dimsB[3] = {8, 64, 10};
       const uint64_t stridesB[2] = {16, 1024};
