@@ -155,7 +155,8 @@ def denoise_tiled_distributed(img: torch.Tensor, model, cs: int, ucs: int, ol: i
         band, y0, y1 = band_fn(img, cb, ce)
         assert (y0, y1) == extents[rank]
     if rank == dst:
-        bands = []
+        # post every receive at once (one batched NCCL group): the bands arrive concurrently through NVSwitch
+        bands, ops = [], []
         for r in range(world):
             y0, y1 = extents[r]
             if y1 <= y0:
@@ -164,11 +165,15 @@ def denoise_tiled_distributed(img: torch.Tensor, model, cs: int, ucs: int, ol: i
                 bands.append((band, y0, y1))
             else:
                 buf = torch.empty((3, y1 - y0, W), dtype=torch.float32, device=img.device)
-                dist.recv(buf, src=r, group=group)
+                ops.append(dist.P2POp(dist.irecv, buf, r, group))
                 bands.append((buf, y0, y1))
+        if ops:
+            for req in dist.batch_isend_irecv(ops):
+                req.wait()
         return assemble_bands(bands, H, W, device=img.device)
     if band is not None:
-        dist.send(band.contiguous(), dst=dst, group=group)
+        for req in dist.batch_isend_irecv([dist.P2POp(dist.isend, band.contiguous(), dst, group)]):
+            req.wait()
     return None
 
 
