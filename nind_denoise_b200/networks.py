@@ -51,7 +51,9 @@ class _NativeNet(nn.Module):
                 pass
 
     def _state_key(self):
-        return tuple((k, v.data_ptr(), v._version) for k, v in self.state_dict(keep_vars=True).items())
+        # storage identity + in-place version counter of every parameter and buffer: changes on
+        # load_state_dict (copy_ bumps the version), optimiser steps, .to(device) (new storage)
+        return tuple((t.data_ptr(), t._version) for t in list(self.parameters()) + list(self.buffers()))
 
     def set_option(self, key: str, value: int):
         """Tuning knob forwarded to nind_set_option (e.g. 'n_tile_deep', 'max_ctas')."""

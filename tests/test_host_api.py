@@ -125,3 +125,18 @@ def test_rows_needed_covers_mirror_padding():
                 r0, r1 = rows_needed(W, H, cs, ucs, ol, a, b)
                 used = np.concatenate([og._sym(np.arange(t[i, 1], t[i, 1] + cs), H) for i in range(a, b)])
                 assert used.min() >= r0 and used.max() < r1, (W, H, cs, world, a, b)
+
+
+def test_compute_entry_points_fail_loudly_without_a_gpu():
+    """No GPU in this container: creating a network must return an error, never fall back to the CPU."""
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    from oracle import nets as on_
+    sd = on_.init_state_dict("UtNet", seed=0)
+    arr, n, keep = _capi.make_tensor_array(sd)
+    h = ctypes.c_void_p()
+    rc = _capi.lib().nind_net_create(0, 64, 0, arr, n, ctypes.byref(h))
+    assert rc != 0 and not h.value
+    assert b"cuda" in _capi.lib().nind_last_error().lower() or b"CUDA" in _capi.lib().nind_last_error()
+    with pytest.raises(_capi.NindError):
+        _capi.device_info()
