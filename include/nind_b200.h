@@ -104,6 +104,13 @@ int nind_stitch_crops(const float* crops, int height, int width, int cs, int ucs
 int nind_tiled_denoise_host(nind_net* net, const float* img_chw_host, float* out_chw_host, int height,
                             int width, int cs, int ucs, int ol, int batch);
 
+/* Throughput mode (a stream of images on one GPU, BASELINE config "batch of 64 x 24 MP"): enqueue without
+ * waiting — image k+1's upload overlaps image k's compute and download (two device slots) — then
+ * nind_host_sync() once.  Host buffers must stay valid (and should be pinned) until the sync returns. */
+int nind_tiled_denoise_host_async(nind_net* net, const float* img_chw_host, float* out_chw_host, int height,
+                                  int width, int cs, int ucs, int ol, int batch);
+int nind_host_sync(nind_net* net);
+
 /* Number of CUDA kernels this library has launched on the calling process so far. */
 int64_t nind_kernel_launches(void);
 

@@ -114,9 +114,16 @@ struct nind_net {
   int2* origin_buf = nullptr;
   size_t origin_cap = 0;
   std::vector<int> origin_key;  // geometry + range the device table currently holds
-  float* img_dev = nullptr;
-  float* out_dev = nullptr;
-  size_t img_cap = 0, out_cap = 0;
+  // host-buffer pipeline: two (device image, device output) slots so that consecutive images overlap
+  struct HostSlot {
+    float* img = nullptr;
+    float* out = nullptr;
+    size_t img_cap = 0, out_cap = 0;
+    cudaEvent_t img_free = nullptr, out_free = nullptr;  // last compute read of img / last D2H read of out
+    bool used = false;
+  };
+  HostSlot slots[2];
+  unsigned host_seq = 0;
   cudaStream_t s_in = nullptr, s_comp = nullptr, s_out = nullptr;
   std::vector<cudaEvent_t> ev_in, ev_done;
   // options
@@ -147,8 +154,12 @@ struct nind_net {
     cudaFree(err_flag);
     cudaFree(crops_buf);
     cudaFree(origin_buf);
-    cudaFree(img_dev);
-    cudaFree(out_dev);
+    for (auto& sl : slots) {
+      cudaFree(sl.img);
+      cudaFree(sl.out);
+      if (sl.img_free) cudaEventDestroy(sl.img_free);
+      if (sl.out_free) cudaEventDestroy(sl.out_free);
+    }
     for (auto e : ev_in) cudaEventDestroy(e);
     for (auto e : ev_done) cudaEventDestroy(e);
     if (s_in) { cudaStreamDestroy(s_in); cudaStreamDestroy(s_comp); cudaStreamDestroy(s_out); }
@@ -968,11 +979,13 @@ int nind_tiled_denoise(nind_net* net, const float* img_chw, float* out_band, int
   return launch_stitch(g, net->crops_buf, crop_begin, crop_end, out_band, y0, y1, false, st);
 }
 
-int nind_tiled_denoise_host(nind_net* net, const float* img_chw_host, float* out_chw_host, int height,
-                            int width, int cs, int ucs, int ol, int batch) {
+// Enqueue one image on the three-stream host pipeline (no synchronisation).
+static int enqueue_host_image(nind_net* net, const float* img_chw_host, float* out_chw_host, int height, int width,
+                              int cs, int ucs, int ol, int batch) {
   // Pipelined over grid rows of crops: the H2D copy of the image rows a grid row needs, the forward
   // of its crops, the stitch of the output rows it completes and their D2H copy run on three
-  // streams, so PCIe traffic hides behind compute when the host buffers are pinned.
+  // streams, so PCIe traffic hides behind compute when the host buffers are pinned.  Two device
+  // (image, output) slots let image k+1's upload overlap image k's compute and download.
   if (!net || !img_chw_host || !out_chw_host) return fail(NIND_E_INVALID, "null argument");
   if (batch <= 0) return fail(NIND_E_INVALID, "batch must be positive");
   GridGeom g;
@@ -980,8 +993,9 @@ int nind_tiled_denoise_host(nind_net* net, const float* img_chw_host, float* out
   const size_t plane = (size_t)height * width;
   const size_t bytes = 3 * plane * sizeof(float);
   int rc;
-  if ((rc = ensure(reinterpret_cast<void**>(&net->img_dev), &net->img_cap, bytes))) return rc;
-  if ((rc = ensure(reinterpret_cast<void**>(&net->out_dev), &net->out_cap, bytes))) return rc;
+  nind_net::HostSlot& S = net->slots[net->host_seq++ & 1];
+  if ((rc = ensure(reinterpret_cast<void**>(&S.img), &S.img_cap, bytes))) return rc;
+  if ((rc = ensure(reinterpret_cast<void**>(&S.out), &S.out_cap, bytes))) return rc;
   const int n = g.size();
   if ((rc = ensure(reinterpret_cast<void**>(&net->crops_buf), &net->crops_cap, (size_t)n * 3 * cs * cs * sizeof(float))))
     return rc;
@@ -989,6 +1003,10 @@ int nind_tiled_denoise_host(nind_net* net, const float* img_chw_host, float* out
     CUDA_TRY(cudaStreamCreateWithFlags(&net->s_in, cudaStreamNonBlocking));
     CUDA_TRY(cudaStreamCreateWithFlags(&net->s_comp, cudaStreamNonBlocking));
     CUDA_TRY(cudaStreamCreateWithFlags(&net->s_out, cudaStreamNonBlocking));
+  }
+  if (!S.img_free) {
+    CUDA_TRY(cudaEventCreateWithFlags(&S.img_free, cudaEventDisableTiming));
+    CUDA_TRY(cudaEventCreateWithFlags(&S.out_free, cudaEventDisableTiming));
   }
   while ((int)net->ev_in.size() < g.ny) {
     cudaEvent_t a, b;
@@ -998,6 +1016,10 @@ int nind_tiled_denoise_host(nind_net* net, const float* img_chw_host, float* out
     net->ev_done.push_back(b);
   }
   if ((rc = upload_origins(net, g, 0, n, net->s_comp))) return rc;
+  if (S.used) {  // the image that used this slot two calls ago must be done with it
+    CUDA_TRY(cudaStreamWaitEvent(net->s_in, S.img_free, 0));
+    CUDA_TRY(cudaStreamWaitEvent(net->s_comp, S.out_free, 0));
+  }
   // H2D: rows each grid row newly needs (planar image -> one 2-D copy of 3 plane segments)
   int uploaded = 0;
   for (int yi = 0; yi < g.ny; ++yi) {
@@ -1005,7 +1027,7 @@ int nind_tiled_denoise_host(nind_net* net, const float* img_chw_host, float* out
     const int upto = yi == g.ny - 1 ? height : std::max(uploaded, need);
     if (upto > uploaded) {
       const size_t off = (size_t)uploaded * width;
-      CUDA_TRY(cudaMemcpy2DAsync(net->img_dev + off, plane * sizeof(float), img_chw_host + off, plane * sizeof(float),
+      CUDA_TRY(cudaMemcpy2DAsync(S.img + off, plane * sizeof(float), img_chw_host + off, plane * sizeof(float),
                                  (size_t)(upto - uploaded) * width * sizeof(float), 3, cudaMemcpyHostToDevice,
                                  net->s_in));
       uploaded = upto;
@@ -1022,25 +1044,48 @@ int nind_tiled_denoise_host(nind_net* net, const float* img_chw_host, float* out
       if ((rc = get_plan(net, b, cs, cs, &plan))) return rc;
       GatherParams gp;
       memset(&gp, 0, sizeof gp);
-      gp.src = net->img_dev; gp.src_img = 0; gp.src_plane = (long long)plane; gp.src_w = width; gp.src_h = height;
+      gp.src = S.img; gp.src_img = 0; gp.src_plane = (long long)plane; gp.src_w = width; gp.src_h = height;
       gp.origin = net->origin_buf + i0;
       if ((rc = run_plan(net, plan, gp, net->crops_buf + (size_t)i0 * 3 * cs * cs, net->s_comp))) return rc;
     }
+    if (yb == g.ny) CUDA_TRY(cudaEventRecord(S.img_free, net->s_comp));
     // output rows completed by these grid rows: every crop that touches them has index < yb*nx
     const int r0 = g.stride * ya;
     const int r1 = yb == g.ny ? height : std::min(height, g.stride * yb);
     if (r1 > r0) {
-      if ((rc = launch_stitch(g, net->crops_buf, 0, n, net->out_dev, r0, r1, true, net->s_comp))) return rc;
+      if ((rc = launch_stitch(g, net->crops_buf, 0, n, S.out, r0, r1, true, net->s_comp))) return rc;
       CUDA_TRY(cudaEventRecord(net->ev_done[ya], net->s_comp));
       CUDA_TRY(cudaStreamWaitEvent(net->s_out, net->ev_done[ya], 0));
       const size_t off = (size_t)r0 * width;
-      CUDA_TRY(cudaMemcpy2DAsync(out_chw_host + off, plane * sizeof(float), net->out_dev + off, plane * sizeof(float),
+      CUDA_TRY(cudaMemcpy2DAsync(out_chw_host + off, plane * sizeof(float), S.out + off, plane * sizeof(float),
                                  (size_t)(r1 - r0) * width * sizeof(float), 3, cudaMemcpyDeviceToHost, net->s_out));
     }
   }
-  CUDA_TRY(cudaStreamSynchronize(net->s_out));
-  CUDA_TRY(cudaStreamSynchronize(net->s_comp));
+  CUDA_TRY(cudaEventRecord(S.out_free, net->s_out));
+  S.used = true;
+  return 0;
+}
+
+int nind_host_sync(nind_net* net) {
+  if (!net) return fail(NIND_E_INVALID, "null handle");
+  if (net->s_in) {
+    CUDA_TRY(cudaStreamSynchronize(net->s_out));
+    CUDA_TRY(cudaStreamSynchronize(net->s_comp));
+    CUDA_TRY(cudaStreamSynchronize(net->s_in));
+  }
   return check_err_flag(net);
+}
+
+int nind_tiled_denoise_host_async(nind_net* net, const float* img_chw_host, float* out_chw_host, int height,
+                                  int width, int cs, int ucs, int ol, int batch) {
+  return enqueue_host_image(net, img_chw_host, out_chw_host, height, width, cs, ucs, ol, batch);
+}
+
+int nind_tiled_denoise_host(nind_net* net, const float* img_chw_host, float* out_chw_host, int height,
+                            int width, int cs, int ucs, int ol, int batch) {
+  int rc = enqueue_host_image(net, img_chw_host, out_chw_host, height, width, cs, ucs, ol, batch);
+  if (rc) return rc;
+  return nind_host_sync(net);
 }
 
 }  // extern "C"

@@ -109,6 +109,25 @@ def denoise_tiled_host(img_host: torch.Tensor, model, cs: int, ucs: int, ol: int
     return out
 
 
+def denoise_images_host(imgs_host: Sequence[torch.Tensor], model, cs: int, ucs: int, ol: int = DEFAULT_OVERLAP,
+                        batch: Optional[int] = None, outs: Optional[Sequence[torch.Tensor]] = None):
+    """Throughput mode on one GPU: a sequence of CPU images (pinned for full PCIe speed) is pushed through
+    ``nind_tiled_denoise_host_async`` back to back — image k+1's upload overlaps image k's compute and
+    download — and synchronised once.  Returns the list of CPU outputs."""
+    imgs = [im.detach().float().contiguous() for im in imgs_host]
+    if outs is None:
+        outs = [torch.empty_like(im).pin_memory() if im.is_pinned() else torch.empty_like(im) for im in imgs]
+    h = model.native_handle()
+    lib = _capi.lib()
+    with torch.cuda.device(model._device):
+        for im, out in zip(imgs, outs):
+            _, H, W = im.shape
+            b = batch or default_batch(n_crops(W, H, cs, ucs, ol), cs, _nx(W, ucs, ol))
+            _capi.check(lib.nind_tiled_denoise_host_async(h, im.data_ptr(), out.data_ptr(), H, W, cs, ucs, ol, b))
+        _capi.check(lib.nind_host_sync(h))
+    return list(outs)
+
+
 # ------------------------------------------------------------------------------ multi-GPU
 def assemble_bands(bands: Sequence[Tuple[Optional[torch.Tensor], int, int]], height: int, width: int,
                    device=None) -> torch.Tensor:

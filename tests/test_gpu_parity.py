@@ -360,3 +360,17 @@ def test_crop_overlap_sweep(utnet):
                 ref = og.denoise_tiled(img, fwd, cs, ucs, ol)
             err = np.abs(out - ref).max()
             assert err <= MAX_ABS and err <= MAX_REL_SIGMA * ref.std(), (cs, ucs, ol, err)
+
+
+def test_throughput_mode_matches_single_image_path(utnet):
+    """nind_tiled_denoise_host_async + nind_host_sync: a stream of images (two device slots, three streams)
+    gives exactly what the synchronous host entry gives image by image."""
+    rng = np.random.default_rng(14)
+    shapes = [(3, 260, 300), (3, 260, 300), (3, 333, 271), (3, 260, 300), (3, 200, 420)]
+    imgs = [torch.from_numpy(rng.random(s, dtype=np.float32)).pin_memory() for s in shapes]
+    cs, ucs, ol = 120, 96, 6
+    outs = nb.denoise_images_host(imgs, utnet, cs, ucs, ol, batch=5)
+    for im, out in zip(imgs, outs):
+        ref = nb.denoise_tiled_host(im, utnet, cs, ucs, ol, batch=4)
+        assert out.shape == im.shape
+        assert float((out - ref).abs().max()) <= 1e-6
