@@ -87,9 +87,9 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+            self.rows.append([time.time()] + [c.strip() for c in line.split(",")])
 
-    def stop(self):
+    def stop(self, t0=None, t1=None):
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.15)
@@ -98,10 +98,15 @@ class ClockSampler:
             self.proc.wait(timeout=2)
         except Exception:
             self.proc.kill()
-        sm = [float(r[0]) for r in self.rows if len(r) >= 6 and r[0].replace(".", "").isdigit()]
-        mx = [float(r[1]) for r in self.rows if len(r) >= 6 and r[1].replace(".", "").isdigit()]
+        # keep the samples taken inside the timed region (the sampler is started before the warm-up so that
+        # nvidia-smi's start-up / NVML initialisation cannot stall the timed launches)
+        rows = [r[1:] for r in self.rows if len(r) >= 7 and (t0 is None or t0 - 0.05 <= r[0] <= t1 + 0.15)]
+        if not rows:
+            rows = [r[1:] for r in self.rows[-3:] if len(r) >= 7]
+        sm = [float(r[0]) for r in rows if r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in rows if r[1].replace(".", "").isdigit()]
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = sorted({names[i] for r in self.rows if len(r) >= 6 for i in range(4) if r[2 + i].startswith("Active")})
+        reasons = sorted({names[i] for r in rows for i in range(4) if r[2 + i].startswith("Active")})
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
                 "reasons": reasons, "samples": len(sm)}
 
@@ -236,27 +241,29 @@ def main():
             dist.barrier()
             torch.cuda.synchronize()
 
-    for _ in range(args.warmup):
-        step()
-    sync_all()
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
+    for _ in range(args.warmup):
+        step()
+    sync_all()
     l0 = lib.nind_kernel_launches()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     sync_all()
+    t_start = time.time()
     e0.record()
     for _ in range(args.steps):
         out = step()
     e1.record()
     sync_all()
+    t_end = time.time()
     ms = e0.elapsed_time(e1)
     launches = lib.nind_kernel_launches() - l0
     t = torch.tensor([ms], device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms = float(t.item())
-    clocks = sampler.stop() if rank == 0 else None
+    clocks = sampler.stop(t_start, t_end) if rank == 0 else None
 
     # ---- end to end through the host-buffer entry point (N = 1) / host image in + out (N > 1)
     def e2e_step():

@@ -1034,9 +1034,19 @@ static int enqueue_host_image(nind_net* net, const float* img_chw_host, float* o
     }
     CUDA_TRY(cudaEventRecord(net->ev_in[yi], net->s_in));
   }
-  const int rg = std::max(1, batch / g.nx);  // grid rows per pipeline step (batches may span rows)
-  for (int ya = 0; ya < g.ny; ya += rg) {
-    const int yb = std::min(g.ny, ya + rg);
+  // Pipeline steps = runs of grid rows (batches may span rows).  The first and the last step are a single
+  // grid row, so that compute starts after ~1/ny of the upload and only ~1/ny of the download is exposed.
+  const int rg = std::max(1, batch / g.nx);
+  std::vector<std::pair<int, int>> steps;
+  if (g.ny >= 3 && rg > 1) {
+    steps.push_back({0, 1});
+    for (int ya = 1; ya < g.ny - 1; ya += rg) steps.push_back({ya, std::min(g.ny - 1, ya + rg)});
+    steps.push_back({g.ny - 1, g.ny});
+  } else {
+    for (int ya = 0; ya < g.ny; ya += rg) steps.push_back({ya, std::min(g.ny, ya + rg)});
+  }
+  for (const auto& stp : steps) {
+    const int ya = stp.first, yb = stp.second;
     CUDA_TRY(cudaStreamWaitEvent(net->s_comp, net->ev_in[yb - 1], 0));
     for (int i0 = ya * g.nx; i0 < yb * g.nx; i0 += batch) {
       const int b = std::min(batch, yb * g.nx - i0);
