@@ -1,9 +1,9 @@
 #!/bin/bash
-# same-box A/B of two probe builds (tools/probe = baseline, tools/probe_pre = candidate)
+# same-box A/B of two probe builds (tools/probe = baseline, tools/probe_dual = candidate)
 for rep in 1 2; do
-for bin in probe probe_pre; do
-  for cfg in "9 64 64 4 510 510 0 0 0" "9 64 64 4 510 510 0 0 2" "9 128 64 4 508 508 0 0 0" "9 128 128 8 252 252 0 0 0" "9 256 128 8 252 252 0 0 0" "9 512 256 8 124 124 0 0 0" "9 1024 512 16 60 60 0 0 0" "1 1024 2048 16 28 28 0 0 1"; do
-    echo "$bin $cfg: $(timeout 60 ./tools/$bin conv $cfg | grep -E 'TFLOP|FAIL' | tr '\n' ' ' | cut -c1-100)"
+for bin in probe probe_dual; do
+  for cfg in "9 64 64 4 510 510 0 0 0" "9 64 64 4 510 510 0 0 2" "9 128 64 4 508 508 0 0 0" "9 64 128 8 252 252 0 0 0" "9 128 128 8 252 252 0 0 0" "9 256 128 8 252 252 0 0 0" "9 512 256 8 124 124 0 0 0" "9 1024 512 16 60 60 0 0 0" "1 1024 2048 16 28 28 0 0 1" "1 128 256 4 252 252 0 0 1" "9 8 64 4 508 508 0 0 0"; do
+    echo "$bin $cfg: $(timeout 60 ./tools/$bin conv $cfg | grep -E 'TFLOP|FAIL|failed' | tr '\n' ' ' | cut -c1-100)"
   done
 done
 done
