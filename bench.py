@@ -266,11 +266,14 @@ def main():
     clocks = sampler.stop(t_start, t_end) if rank == 0 else None
 
     # ---- end to end through the host-buffer entry point (N = 1) / host image in + out (N > 1)
+    # N > 1: one shared, page-locked host image that every rank writes the rows it owns into (N PCIe links)
+    out_shared = nb.SharedHostImage((3, H_IMG, W_IMG)) if world > 1 else None
+
     def e2e_step():
         if world == 1:
             nb.denoise_tiled_host(img_host, model, cs, ucs, ol, batch=batch, out=out_host)
         else:
-            nb.denoise_tiled_distributed_host(img_host, model, cs, ucs, ol, batch=batch, out=out_host)
+            nb.denoise_tiled_distributed_host(img_host, model, cs, ucs, ol, batch=batch, out=out_shared)
 
     e2e_step()
     e2e_step()  # the host pipeline alternates between two device slots: warm both

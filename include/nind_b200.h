@@ -20,6 +20,7 @@
 #ifndef NIND_B200_H
 #define NIND_B200_H
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -110,6 +111,12 @@ int nind_tiled_denoise_host(nind_net* net, const float* img_chw_host, float* out
 int nind_tiled_denoise_host_async(nind_net* net, const float* img_chw_host, float* out_chw_host, int height,
                                   int width, int cs, int ucs, int ol, int batch);
 int nind_host_sync(nind_net* net);
+
+/* Page-lock an existing host range (e.g. a shared-memory mapping every rank of a multi-GPU job writes
+ * its output rows into) so that copies to/from it are true asynchronous DMA.  The reference has no
+ * counterpart: it moves each crop with a synchronous .cpu() (denoise_image.py:254). */
+int nind_host_register(void* ptr, size_t bytes);
+int nind_host_unregister(void* ptr);
 
 /* Number of CUDA kernels this library has launched on the calling process so far. */
 int64_t nind_kernel_launches(void);

@@ -1086,6 +1086,18 @@ int nind_host_sync(nind_net* net) {
   return check_err_flag(net);
 }
 
+int nind_host_register(void* ptr, size_t bytes) {
+  if (!ptr || !bytes) return fail(NIND_E_INVALID, "null argument");
+  CUDA_TRY(cudaHostRegister(ptr, bytes, cudaHostRegisterPortable));
+  return 0;
+}
+
+int nind_host_unregister(void* ptr) {
+  if (!ptr) return fail(NIND_E_INVALID, "null argument");
+  CUDA_TRY(cudaHostUnregister(ptr));
+  return 0;
+}
+
 int nind_tiled_denoise_host_async(nind_net* net, const float* img_chw_host, float* out_chw_host, int height,
                                   int width, int cs, int ucs, int ol, int batch) {
   return enqueue_host_image(net, img_chw_host, out_chw_host, height, width, cs, ucs, ol, batch);

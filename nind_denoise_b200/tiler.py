@@ -143,10 +143,17 @@ def assemble_bands(bands: Sequence[Tuple[Optional[torch.Tensor], int, int]], hei
 
 def denoise_tiled_distributed(img: torch.Tensor, model, cs: int, ucs: int, ol: int = DEFAULT_OVERLAP,
                               batch: Optional[int] = None, group=None, dst: int = 0,
-                              band_fn: Optional[Callable] = None) -> Optional[torch.Tensor]:
+                              band_fn: Optional[Callable] = None, mode: str = "rows") -> Optional[torch.Tensor]:
     """Every rank holds the same ``img`` (read-only) and a replica of ``model``; rank ``dst`` returns the
-    stitched image, the others return None.  ``band_fn(img, crop_begin, crop_end) -> (band, y0, y1)``
-    replaces the GPU band computation in CPU (gloo) tests of the sharding/gather logic."""
+    stitched image, the others return None.
+
+    ``mode="rows"`` (default): neighbours first exchange the seam rows they share (``exchange_seams``),
+    then every rank sends only the rows it owns and ``dst`` receives them straight into the output image —
+    each output byte crosses NVLink once and nothing is summed on ``dst``.
+    ``mode="bands"``: whole overlapping bands are gathered and summed on ``dst`` (kept for comparison).
+
+    ``band_fn(img, crop_begin, crop_end) -> (band, y0, y1)`` replaces the GPU band computation in CPU
+    (gloo) tests of the sharding/gather logic."""
     import torch.distributed as dist
 
     world = dist.get_world_size(group)
@@ -160,19 +167,34 @@ def denoise_tiled_distributed(img: torch.Tensor, model, cs: int, ucs: int, ol: i
             batch = default_batch(max(1, ce - cb), cs, _nx(W, ucs, ol))
         band_fn = lambda im, a, b: _band(model, im, cs, ucs, ol, a, b, batch)
     # band extents are pure geometry: every rank can compute everybody's (no metadata exchange)
-    extents = []
-    for a, b in ranges:
-        if b > a:
-            t = crop_table(W, H, cs, ucs, ol)
-            y0 = int(t[a, 7])
-            y1 = min(H, int(t[b - 1, 7]) + int(t[b - 1, 5] - t[b - 1, 3]))
-            extents.append((y0, y1))
-        else:
-            extents.append((0, 0))
+    extents = band_extents(W, H, cs, ucs, ol, ranges)
     band = None
     if ce > cb:
         band, y0, y1 = band_fn(img, cb, ce)
         assert (y0, y1) == extents[rank]
+    if mode == "rows":
+        own = owned_rows(extents, H)
+        exchange_seams(band, extents, own, rank, group)
+        o0, o1 = own[rank]
+        ops = []
+        if rank == dst:
+            out = torch.empty((3, H, W), dtype=torch.float32, device=img.device)
+            for r in range(world):
+                a, b = own[r]
+                if b <= a:
+                    continue
+                if r == rank:
+                    out[:, a:b, :].copy_(band[:, a - y0:b - y0, :])
+                else:  # one receive per colour plane: out[c, a:b] is contiguous
+                    ops += [dist.P2POp(dist.irecv, out[c, a:b, :], r, group) for c in range(3)]
+        elif o1 > o0:
+            ops = [dist.P2POp(dist.isend, band[c, o0 - y0:o1 - y0, :], dst, group) for c in range(3)]
+        if ops:
+            for req in dist.batch_isend_irecv(ops):
+                req.wait()
+        return out if rank == dst else None
+    if mode != "bands":
+        raise ValueError(f"unknown mode {mode!r}")
     if rank == dst:
         # post every receive at once (one batched NCCL group): the bands arrive concurrently through NVSwitch
         bands, ops = [], []
@@ -210,32 +232,165 @@ def rows_needed(width: int, height: int, cs: int, ucs: int, ol: int, crop_begin:
     return r0, r1
 
 
+def band_extents(width: int, height: int, cs: int, ucs: int, ol: int, ranges) -> List[Tuple[int, int]]:
+    """Output rows [y0, y1) each rank's crop range touches ((0, 0) for an empty range) — pure geometry,
+    every rank computes everybody's."""
+    t = crop_table(width, height, cs, ucs, ol)
+    ext = []
+    for a, b in ranges:
+        if b > a:
+            ext.append((int(t[a, 7]), min(height, int(t[b - 1, 7]) + int(t[b - 1, 5] - t[b - 1, 3]))))
+        else:
+            ext.append((0, 0))
+    return ext
+
+
+def owned_rows(extents: Sequence[Tuple[int, int]], height: int) -> List[Tuple[int, int]]:
+    """Disjoint row ownership for the scatter-free output: a non-empty rank owns the rows from its band's
+    first row up to the next non-empty band's first row (the last one up to ``height``).  Rows of band r
+    that lie in a later rank's range are that rank's to finish (see ``exchange_seams``)."""
+    own = [(0, 0)] * len(extents)
+    live = [r for r, (y0, y1) in enumerate(extents) if y1 > y0]
+    for i, r in enumerate(live):
+        end = extents[live[i + 1]][0] if i + 1 < len(live) else height
+        own[r] = (extents[r][0], max(extents[r][0], end))
+    return own
+
+
+def exchange_seams(band: Optional[torch.Tensor], extents, own, rank: int, group=None) -> None:
+    """Neighbour exchange that completes every rank's owned rows in place: rank r sends the rows of its
+    band that a later rank owns (the grid row the two ranges share, or just the ``ol`` seam rows) and adds
+    what earlier ranks send for its own rows, in rank (= raster) order.  One batched P2P group."""
+    import torch.distributed as dist
+
+    if band is None:
+        return
+    y0, y1 = extents[rank]
+    ops, recvs, keep = [], [], []
+    for s in range(rank + 1, len(extents)):
+        a, b = max(y0, own[s][0]), min(y1, own[s][1])
+        if b > a:
+            keep.append(band[:, a - y0:b - y0, :].contiguous())
+            ops.append(dist.P2POp(dist.isend, keep[-1], s, group))
+    for r in range(rank):
+        a, b = max(extents[r][0], own[rank][0]), min(extents[r][1], own[rank][1])
+        if b > a:
+            buf = torch.empty((3, b - a, band.shape[2]), dtype=band.dtype, device=band.device)
+            ops.append(dist.P2POp(dist.irecv, buf, r, group))
+            recvs.append((buf, a, b))
+    if ops:
+        for req in dist.batch_isend_irecv(ops):
+            req.wait()
+    for buf, a, b in recvs:
+        band[:, a - y0:b - y0, :] += buf
+
+
+class SharedHostImage:
+    """A [3,H,W] fp32 host image in ONE shared-memory segment mapped by every rank of ``group`` (ranks of a
+    node), page-locked on each rank: the multi-GPU host entry lets every GPU copy the rows it owns straight
+    into it over its own PCIe link instead of funnelling the whole image through rank ``src``'s.
+    Collective constructor.  ``tensor`` is the CPU view (all ranks see the same bytes)."""
+
+    def __init__(self, shape, group=None, src: int = 0, pin: bool = True):
+        import os
+
+        import torch.distributed as dist
+
+        self.shape = tuple(int(v) for v in shape)
+        numel = math.prod(self.shape)
+        self._fd = None
+        rank = dist.get_rank(group)
+        path = [None]
+        if rank == src:
+            # anonymous memory file, reachable by the other ranks through /proc (no /dev/shm size limit)
+            self._fd = os.memfd_create("nind_b200_out")
+            os.ftruncate(self._fd, numel * 4)
+            path[0] = f"/proc/{os.getpid()}/fd/{self._fd}"
+        dist.broadcast_object_list(path, src=dist.get_global_rank(group, src) if group is not None else src,
+                                   group=group)
+        self.tensor = torch.from_file(path[0], shared=True, size=numel, dtype=torch.float32).view(self.shape)
+        self.pinned = False
+        if pin and torch.cuda.is_available():
+            _capi.check(_capi.lib().nind_host_register(self.tensor.data_ptr(), numel * 4))
+            self.pinned = True
+        dist.barrier(group)  # everyone has mapped it; the creator can drop its descriptor
+        if self._fd is not None:
+            os.close(self._fd)
+            self._fd = None
+
+    def close(self):
+        if self.pinned:
+            _capi.check(_capi.lib().nind_host_unregister(self.tensor.data_ptr()))
+            self.pinned = False
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
 def denoise_tiled_distributed_host(img_host: torch.Tensor, model, cs: int, ucs: int, ol: int = DEFAULT_OVERLAP,
-                                   batch: Optional[int] = None, group=None, dst: int = 0,
-                                   out: Optional[torch.Tensor] = None) -> Optional[torch.Tensor]:
+                                   batch: Optional[int] = None, group=None, dst: int = 0, out=None,
+                                   band_fn: Optional[Callable] = None) -> Optional[torch.Tensor]:
     """Multi-GPU host-buffer entry: every rank holds the same CPU image (pinned for full PCIe speed),
-    uploads only the rows its crop range reads, stitches its band on its GPU; bands are gathered to
-    rank ``dst`` over NCCL and copied to ``out`` (CPU) there.  Other ranks return None."""
+    uploads only the rows its crop range reads and stitches its band on its GPU.
+
+    * ``out`` a ``SharedHostImage``: neighbours exchange the seam rows over NCCL, then every rank copies
+      the rows it owns straight into the shared host image — N PCIe links in parallel, no gather.
+    * ``out`` a plain CPU tensor or None: bands are gathered to rank ``dst`` over NCCL and copied to host
+      there (one PCIe link).
+
+    Rank ``dst`` returns the CPU image, the others None.  ``band_fn(img, crop_begin, crop_end)`` stands in
+    for the GPU band computation in the CPU (gloo) tests."""
     import torch.distributed as dist
 
     world, rank = dist.get_world_size(group), dist.get_rank(group)
     _, H, W = img_host.shape
     n = n_crops(W, H, cs, ucs, ol)
-    cb, ce = shard_ranges(n, world)[rank]
-    dev = model._device if getattr(model, "_handle", None) else next(model.parameters()).device
-    d_img = torch.empty((3, H, W), dtype=torch.float32, device=dev)
+    ranges = shard_ranges(n, world)
+    cb, ce = ranges[rank]
+    if band_fn is None:
+        dev = model._device if getattr(model, "_handle", None) else next(model.parameters()).device
+        d_img = torch.empty((3, H, W), dtype=torch.float32, device=dev)
+        if ce > cb:
+            r0, r1 = rows_needed(W, H, cs, ucs, ol, cb, ce)
+            for c in range(3):  # per plane: contiguous pinned source -> true async DMA (a strided CPU view is staged)
+                d_img[c, r0:r1].copy_(img_host[c, r0:r1], non_blocking=True)
+    else:
+        dev, d_img = img_host.device, img_host
+    if not isinstance(out, SharedHostImage):
+        res = denoise_tiled_distributed(d_img, model, cs, ucs, ol, batch=batch, group=group, dst=dst, band_fn=band_fn)
+        if rank != dst:
+            return None
+        if out is None:
+            out = torch.empty((3, H, W), dtype=torch.float32, pin_memory=dev.type == "cuda")
+        out.copy_(res, non_blocking=True)
+        if dev.type == "cuda":
+            torch.cuda.synchronize(dev)
+        return out
+    if out.shape != (3, H, W):
+        raise ValueError(f"shared output is {out.shape}, image is {(3, H, W)}")
+    extents = band_extents(W, H, cs, ucs, ol, ranges)
+    own = owned_rows(extents, H)
+    band = None
     if ce > cb:
-        r0, r1 = rows_needed(W, H, cs, ucs, ol, cb, ce)
-        for c in range(3):  # per plane: contiguous pinned source -> true async DMA (a strided CPU view is staged)
-            d_img[c, r0:r1].copy_(img_host[c, r0:r1], non_blocking=True)
-    res = denoise_tiled_distributed(d_img, model, cs, ucs, ol, batch=batch, group=group, dst=dst)
-    if rank != dst:
-        return None
-    if out is None:
-        out = torch.empty((3, H, W), dtype=torch.float32, pin_memory=True)
-    out.copy_(res, non_blocking=True)
-    torch.cuda.synchronize(dev)
-    return out
+        if band_fn is None:
+            if batch is None:
+                batch = default_batch(ce - cb, cs, _nx(W, ucs, ol))
+            band, y0, y1 = _band(model, d_img, cs, ucs, ol, cb, ce, batch)
+        else:
+            band, y0, y1 = band_fn(d_img, cb, ce)
+        assert (y0, y1) == extents[rank]
+    exchange_seams(band, extents, own, rank, group)
+    o0, o1 = own[rank]
+    if o1 > o0:
+        for c in range(3):
+            out.tensor[c, o0:o1].copy_(band[c, o0 - y0:o1 - y0], non_blocking=True)
+    if dev.type == "cuda":
+        torch.cuda.current_stream(dev).synchronize()
+    dist.barrier(group)  # every rank's rows have landed in the shared image
+    return out.tensor if rank == dst else None
 
 
 # ------------------------------------------------------------------------------ geometry ops

@@ -29,12 +29,22 @@ def oracle_band(img, a, b):
     return torch.from_numpy(full[:, y0:y1].copy()), y0, y1
 
 
-def _worker(rank, world, port, q):
+def _worker(rank, world, port, q, shared=False):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
     img = torch.from_numpy(np.random.default_rng(3).random((3, H, W), dtype=np.float32))
-    out = nb.denoise_tiled_distributed(img, None, CS, UCS, OL, band_fn=oracle_band)
+    if shared:  # seam exchange between neighbours + every rank writes its own rows into one shared host image
+        sh = nb.SharedHostImage((3, H, W))
+        sh.tensor.fill_(float("nan")) if rank == 0 else None
+        dist.barrier()
+        for _ in range(2):  # the buffer is reusable
+            out = nb.denoise_tiled_distributed_host(img, None, CS, UCS, OL, out=sh, band_fn=oracle_band)
+    else:
+        out = nb.denoise_tiled_distributed(img, None, CS, UCS, OL, band_fn=oracle_band)
+        out_b = nb.denoise_tiled_distributed(img, None, CS, UCS, OL, band_fn=oracle_band, mode="bands")
+        if rank == 0:
+            assert float((out - out_b).abs().max()) <= 1e-6
     if rank == 0:
         ref = og.denoise_tiled(img.numpy(), fake_model_np, CS, UCS, OL)
         q.put(float(np.abs(out.numpy() - ref).max()))
@@ -44,14 +54,14 @@ def _worker(rank, world, port, q):
     dist.destroy_process_group()
 
 
-def _run(world):
+def _run(world, shared=False):
     s = socket.socket()
     s.bind(("127.0.0.1", 0))
     port = s.getsockname()[1]
     s.close()
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
-    procs = [ctx.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
+    procs = [ctx.Process(target=_worker, args=(r, world, port, q, shared)) for r in range(world)]
     for p in procs:
         p.start()
     err = q.get(timeout=120)
@@ -69,3 +79,24 @@ def test_eight_ranks_with_an_empty_shard():
     # 20 crops over 8 ranks -> ceil = 3 per rank, rank 7 gets nothing
     assert nb.shard_ranges(nb.n_crops(W, H, CS, UCS, OL), 8)[-1] == (20, 20)
     _run(8)
+
+
+def test_two_ranks_shared_host_image():
+    _run(2, shared=True)
+
+
+def test_eight_ranks_shared_host_image_with_an_empty_shard():
+    _run(8, shared=True)
+
+
+def test_owned_rows_partition_the_image():
+    for world in (1, 2, 3, 5, 8, 19, 40):
+        for (w, h, cs, ucs, ol) in ((101, 83, 40, 28, 4), (600, 400, 56, 40, 6), (64, 300, 72, 40, 2)):
+            ranges = nb.shard_ranges(nb.n_crops(w, h, cs, ucs, ol), world)
+            ext = nb.band_extents(w, h, cs, ucs, ol, ranges)
+            own = nb.owned_rows(ext, h)
+            rows = np.zeros(h, dtype=np.int32)
+            for (o0, o1), (y0, y1) in zip(own, ext):
+                assert o0 >= y0 and (o1 <= y1 or o1 == o0)   # a rank only owns rows of its own band
+                rows[o0:o1] += 1
+            assert (rows == 1).all()

@@ -28,5 +28,13 @@ for cs, ucs, ol in ((248, 224, 6), (120, 96, 6)):
         errh = float((outh.to(dev) - ref).abs().max())
         print(f"world {dist.get_world_size()} cs {cs}: host entry max diff = {errh:.3e}")
         assert errh <= 1e-6
+    sh = nb.SharedHostImage(tuple(img.shape))
+    for _ in range(2):
+        outs = nb.denoise_tiled_distributed_host(img.cpu().pin_memory(), model, cs, ucs, ol, out=sh)
+    if dist.get_rank() == 0:
+        errs = float((outs.to(dev) - ref).abs().max())
+        print(f"world {dist.get_world_size()} cs {cs}: shared host image max diff = {errs:.3e} (pinned {sh.pinned})")
+        assert errs <= 1e-6
+    sh.close()
 dist.barrier()
 dist.destroy_process_group()
