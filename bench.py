@@ -189,6 +189,8 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--ref-sample", type=int, default=0, help="crops per step of the CPU reference arm")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--gather", default="rows", choices=["rows", "bands"],
+                    help="N>1: seam exchange + owned-row gather (default) or whole-band gather summed on rank 0")
     ap.add_argument("--layers", action="store_true", help="print the per-layer timing table to stderr")
     args = ap.parse_args()
     set_workload(args.network)
@@ -233,7 +235,7 @@ def main():
     def step():
         if world == 1:
             return nb.denoise_tiled(img, model, cs, ucs, ol, batch=batch)
-        return nb.denoise_tiled_distributed(img, model, cs, ucs, ol, batch=batch)
+        return nb.denoise_tiled_distributed(img, model, cs, ucs, ol, batch=batch, mode=args.gather)
 
     def sync_all():
         torch.cuda.synchronize()
@@ -374,7 +376,8 @@ def main():
             "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
             "config": {"workload": f"{NETWORK}(funit 64, random init) {W_IMG}x{H_IMG} synthetic image, cs {cs} ucs {ucs} overlap {ol} "
                                    f"-> {n} crops, batch {batch} crops/forward; crops sharded over {world} GPU(s)"
-                                   + (", NCCL send/recv gather of row bands to rank 0" if world > 1 else ""),
+                                   + (f", NCCL seam exchange between neighbours + send/recv gather of owned rows to rank 0 ({args.gather})"
+                                      if world > 1 else ""),
                        "l2": "inputs larger than L2 (288 MB image, >1 GB activation arena per batch)",
                        "algorithmic_tflop_per_step": flops_image / 1e12},
             "pct_of_bf16_peak": {"sustained": flops_image / (ms / args.steps * 1e-3) / 1e12 / (pk["sustained"] * world),

@@ -112,6 +112,17 @@ int nind_tiled_denoise_host_async(nind_net* net, const float* img_chw_host, floa
                                   int width, int cs, int ucs, int ol, int batch);
 int nind_host_sync(nind_net* net);
 
+/* One rank's share of an image on the same pipeline (multi-GPU host entry): crops [crop_begin, crop_end)
+ * only.  The image rows those crops read are uploaded step by step, the band they produce is stitched
+ * into a device image of full [3][H][W] layout (*d_out, valid until the second next call on this net), and
+ * band rows [d2h_y0, d2h_y1) are copied to out_chw_host (full layout too) as they complete.  No
+ * synchronisation: nind_host_join() orders another stream (NCCL seam exchange, further copies) after the
+ * pipeline's compute stream, nind_host_sync() waits for everything. */
+int nind_tiled_denoise_host_range(nind_net* net, const float* img_chw_host, float* out_chw_host, int height,
+                                  int width, int cs, int ucs, int ol, int batch, int crop_begin, int crop_end,
+                                  int d2h_y0, int d2h_y1, float** d_out);
+int nind_host_join(nind_net* net, void* stream);
+
 /* Page-lock an existing host range (e.g. a shared-memory mapping every rank of a multi-GPU job writes
  * its output rows into) so that copies to/from it are true asynchronous DMA.  The reference has no
  * counterpart: it moves each crop with a synchronous .cpu() (denoise_image.py:254). */

@@ -45,6 +45,9 @@ SIGNATURES = {
     "nind_tiled_denoise_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p] + [C.c_int] * 6),
     "nind_tiled_denoise_host_async": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p] + [C.c_int] * 6),
     "nind_host_sync": (C.c_int, [C.c_void_p]),
+    "nind_tiled_denoise_host_range": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p] + [C.c_int] * 10
+                                      + [C.POINTER(C.c_void_p)]),
+    "nind_host_join": (C.c_int, [C.c_void_p, C.c_void_p]),
     "nind_host_register": (C.c_int, [C.c_void_p, C.c_size_t]),
     "nind_host_unregister": (C.c_int, [C.c_void_p]),
     "nind_kernel_launches": (C.c_int64, []),

@@ -126,6 +126,7 @@ struct nind_net {
   unsigned host_seq = 0;
   cudaStream_t s_in = nullptr, s_comp = nullptr, s_out = nullptr;
   std::vector<cudaEvent_t> ev_in, ev_done;
+  cudaEvent_t ev_join = nullptr;
   // options
   int n_tile_deep = 256, max_ctas = 0, cg = 0, fuse_pool = 1;
   // First layer: 3x3 implicit GEMM over the 8-channel padded-crop tensor (1) or K=64 GEMM over an im2col (0).
@@ -979,24 +980,28 @@ int nind_tiled_denoise(nind_net* net, const float* img_chw, float* out_band, int
   return launch_stitch(g, net->crops_buf, crop_begin, crop_end, out_band, y0, y1, false, st);
 }
 
-// Enqueue one image on the three-stream host pipeline (no synchronisation).
-static int enqueue_host_image(nind_net* net, const float* img_chw_host, float* out_chw_host, int height, int width,
-                              int cs, int ucs, int ol, int batch) {
-  // Pipelined over grid rows of crops: the H2D copy of the image rows a grid row needs, the forward
-  // of its crops, the stitch of the output rows it completes and their D2H copy run on three
+// Enqueue crops [cb, ce) of one image on the three-stream host pipeline (no synchronisation).  Rows
+// [d2h_y0, d2h_y1) of the stitched band are downloaded to `out_chw_host` as they complete; `d_out`
+// (optional) receives the device image (full [3][H][W] layout) the band is stitched into.
+static int enqueue_host_range(nind_net* net, const float* img_chw_host, float* out_chw_host, int height, int width,
+                              int cs, int ucs, int ol, int batch, int cb, int ce, int d2h_y0, int d2h_y1,
+                              float** d_out) {
+  // Pipelined over steps of crops in raster order: the H2D copy of the image rows a step needs, the
+  // forward of its crops, the stitch of the output rows it completes and their D2H copy run on three
   // streams, so PCIe traffic hides behind compute when the host buffers are pinned.  Two device
   // (image, output) slots let image k+1's upload overlap image k's compute and download.
   if (!net || !img_chw_host || !out_chw_host) return fail(NIND_E_INVALID, "null argument");
   if (batch <= 0) return fail(NIND_E_INVALID, "batch must be positive");
   GridGeom g;
-  if (!make_grid(width, height, cs, ucs, ol, &g)) return fail(NIND_E_INVALID, "illegal crop geometry");
+  int rc;
+  if ((rc = check_range(width, height, cs, ucs, ol, cb, ce, &g))) return rc;
   const size_t plane = (size_t)height * width;
   const size_t bytes = 3 * plane * sizeof(float);
-  int rc;
   nind_net::HostSlot& S = net->slots[net->host_seq++ & 1];
   if ((rc = ensure(reinterpret_cast<void**>(&S.img), &S.img_cap, bytes))) return rc;
   if ((rc = ensure(reinterpret_cast<void**>(&S.out), &S.out_cap, bytes))) return rc;
-  const int n = g.size();
+  if (d_out) *d_out = S.out;
+  const int n = ce - cb;
   if ((rc = ensure(reinterpret_cast<void**>(&net->crops_buf), &net->crops_cap, (size_t)n * 3 * cs * cs * sizeof(float))))
     return rc;
   if (!net->s_in) {
@@ -1008,23 +1013,41 @@ static int enqueue_host_image(nind_net* net, const float* img_chw_host, float* o
     CUDA_TRY(cudaEventCreateWithFlags(&S.img_free, cudaEventDisableTiming));
     CUDA_TRY(cudaEventCreateWithFlags(&S.out_free, cudaEventDisableTiming));
   }
-  while ((int)net->ev_in.size() < g.ny) {
+  // Steps.  The first and the last are about one grid row of crops, so that compute starts after a small
+  // part of the upload and only a small part of the download is exposed; the rest are `batch` crops.
+  std::vector<std::pair<int, int>> steps;
+  if (n > 2 * g.nx && batch > g.nx) {
+    steps.push_back({cb, cb + g.nx});
+    for (int i = cb + g.nx; i < ce - g.nx; i += batch) steps.push_back({i, std::min(ce - g.nx, i + batch)});
+    steps.push_back({ce - g.nx, ce});
+  } else {
+    for (int i = cb; i < ce; i += batch) steps.push_back({i, std::min(ce, i + batch)});
+  }
+  while (net->ev_in.size() < steps.size()) {
     cudaEvent_t a, b;
     CUDA_TRY(cudaEventCreateWithFlags(&a, cudaEventDisableTiming));
     CUDA_TRY(cudaEventCreateWithFlags(&b, cudaEventDisableTiming));
     net->ev_in.push_back(a);
     net->ev_done.push_back(b);
   }
-  if ((rc = upload_origins(net, g, 0, n, net->s_comp))) return rc;
+  if ((rc = upload_origins(net, g, cb, n, net->s_comp))) return rc;
   if (S.used) {  // the image that used this slot two calls ago must be done with it
     CUDA_TRY(cudaStreamWaitEvent(net->s_in, S.img_free, 0));
     CUDA_TRY(cudaStreamWaitEvent(net->s_comp, S.out_free, 0));
   }
-  // H2D: rows each grid row newly needs (planar image -> one 2-D copy of 3 plane segments)
-  int uploaded = 0;
-  for (int yi = 0; yi < g.ny; ++yi) {
-    const int need = std::min(height, g.stride * yi - g.pad + cs);
-    const int upto = yi == g.ny - 1 ? height : std::max(uploaded, need);
+  // H2D: the image rows each step newly needs, in increasing order (planar image -> one 2-D copy of 3
+  // plane segments).  Rows the mirror padding reflects to lie inside the range: at the top they are the
+  // first rows; at the bottom edge (window overshoots the image) they can lie above the window's own
+  // first row, so the range starts there.
+  const int y_first = g.stride * (cb / g.nx) - g.pad, y_last_end = g.stride * ((ce - 1) / g.nx) - g.pad + cs;
+  int rows_lo = std::max(0, y_first), rows_hi = std::min(height, y_last_end);
+  if (y_last_end > height) rows_lo = std::min(rows_lo, std::max(0, 2 * height - y_last_end));
+  if (y_first < 0) rows_hi = std::max(rows_hi, std::min(height, -y_first));
+  int uploaded = rows_lo;
+  for (size_t k = 0; k < steps.size(); ++k) {
+    const int yi = (steps[k].second - 1) / g.nx;
+    const int need = std::min(rows_hi, std::max(g.stride * yi - g.pad + cs, y_first < 0 ? -y_first : 0));
+    const int upto = k + 1 == steps.size() ? rows_hi : std::max(uploaded, need);
     if (upto > uploaded) {
       const size_t off = (size_t)uploaded * width;
       CUDA_TRY(cudaMemcpy2DAsync(S.img + off, plane * sizeof(float), img_chw_host + off, plane * sizeof(float),
@@ -1032,48 +1055,52 @@ static int enqueue_host_image(nind_net* net, const float* img_chw_host, float* o
                                  net->s_in));
       uploaded = upto;
     }
-    CUDA_TRY(cudaEventRecord(net->ev_in[yi], net->s_in));
+    CUDA_TRY(cudaEventRecord(net->ev_in[k], net->s_in));
   }
-  // Pipeline steps = runs of grid rows (batches may span rows).  The first and the last step are a single
-  // grid row, so that compute starts after ~1/ny of the upload and only ~1/ny of the download is exposed.
-  const int rg = std::max(1, batch / g.nx);
-  std::vector<std::pair<int, int>> steps;
-  if (g.ny >= 3 && rg > 1) {
-    steps.push_back({0, 1});
-    for (int ya = 1; ya < g.ny - 1; ya += rg) steps.push_back({ya, std::min(g.ny - 1, ya + rg)});
-    steps.push_back({g.ny - 1, g.ny});
-  } else {
-    for (int ya = 0; ya < g.ny; ya += rg) steps.push_back({ya, std::min(g.ny, ya + rg)});
-  }
-  for (const auto& stp : steps) {
-    const int ya = stp.first, yb = stp.second;
-    CUDA_TRY(cudaStreamWaitEvent(net->s_comp, net->ev_in[yb - 1], 0));
-    for (int i0 = ya * g.nx; i0 < yb * g.nx; i0 += batch) {
-      const int b = std::min(batch, yb * g.nx - i0);
+  int y0, y1;
+  band_of(g, cb, ce, &y0, &y1);
+  int done = y0;  // band rows [y0, done) are final
+  for (size_t k = 0; k < steps.size(); ++k) {
+    const int ia = steps[k].first, ib = steps[k].second;
+    CUDA_TRY(cudaStreamWaitEvent(net->s_comp, net->ev_in[k], 0));
+    for (int i0 = ia; i0 < ib; i0 += batch) {
+      const int b = std::min(batch, ib - i0);
       Plan* plan = nullptr;
       if ((rc = get_plan(net, b, cs, cs, &plan))) return rc;
       GatherParams gp;
       memset(&gp, 0, sizeof gp);
       gp.src = S.img; gp.src_img = 0; gp.src_plane = (long long)plane; gp.src_w = width; gp.src_h = height;
-      gp.origin = net->origin_buf + i0;
-      if ((rc = run_plan(net, plan, gp, net->crops_buf + (size_t)i0 * 3 * cs * cs, net->s_comp))) return rc;
+      gp.origin = net->origin_buf + (i0 - cb);
+      if ((rc = run_plan(net, plan, gp, net->crops_buf + (size_t)(i0 - cb) * 3 * cs * cs, net->s_comp))) return rc;
     }
-    if (yb == g.ny) CUDA_TRY(cudaEventRecord(S.img_free, net->s_comp));
-    // output rows completed by these grid rows: every crop that touches them has index < yb*nx
-    const int r0 = g.stride * ya;
-    const int r1 = yb == g.ny ? height : std::min(height, g.stride * yb);
+    if (ib == ce) CUDA_TRY(cudaEventRecord(S.img_free, net->s_comp));
+    // output rows completed by this step: every crop of the range that touches them has index < ib
+    const int r0 = done;
+    const int r1 = ib == ce ? y1 : std::min(y1, std::max(done, g.stride * (ib / g.nx)));
     if (r1 > r0) {
-      if ((rc = launch_stitch(g, net->crops_buf, 0, n, S.out, r0, r1, true, net->s_comp))) return rc;
-      CUDA_TRY(cudaEventRecord(net->ev_done[ya], net->s_comp));
-      CUDA_TRY(cudaStreamWaitEvent(net->s_out, net->ev_done[ya], 0));
-      const size_t off = (size_t)r0 * width;
-      CUDA_TRY(cudaMemcpy2DAsync(out_chw_host + off, plane * sizeof(float), S.out + off, plane * sizeof(float),
-                                 (size_t)(r1 - r0) * width * sizeof(float), 3, cudaMemcpyDeviceToHost, net->s_out));
+      if ((rc = launch_stitch(g, net->crops_buf, cb, ce, S.out, r0, r1, true, net->s_comp))) return rc;
+      done = r1;
+      const int c0 = std::max(r0, d2h_y0), c1 = std::min(r1, d2h_y1);
+      if (c1 > c0) {
+        CUDA_TRY(cudaEventRecord(net->ev_done[k], net->s_comp));
+        CUDA_TRY(cudaStreamWaitEvent(net->s_out, net->ev_done[k], 0));
+        const size_t off = (size_t)c0 * width;
+        CUDA_TRY(cudaMemcpy2DAsync(out_chw_host + off, plane * sizeof(float), S.out + off, plane * sizeof(float),
+                                   (size_t)(c1 - c0) * width * sizeof(float), 3, cudaMemcpyDeviceToHost, net->s_out));
+      }
     }
   }
   CUDA_TRY(cudaEventRecord(S.out_free, net->s_out));
   S.used = true;
   return 0;
+}
+
+static int enqueue_host_image(nind_net* net, const float* img_chw_host, float* out_chw_host, int height, int width,
+                              int cs, int ucs, int ol, int batch) {
+  GridGeom g;
+  if (!make_grid(width, height, cs, ucs, ol, &g)) return fail(NIND_E_INVALID, "illegal crop geometry");
+  return enqueue_host_range(net, img_chw_host, out_chw_host, height, width, cs, ucs, ol, batch, 0, g.size(), 0,
+                            height, nullptr);
 }
 
 int nind_host_sync(nind_net* net) {
@@ -1084,6 +1111,22 @@ int nind_host_sync(nind_net* net) {
     CUDA_TRY(cudaStreamSynchronize(net->s_in));
   }
   return check_err_flag(net);
+}
+
+int nind_tiled_denoise_host_range(nind_net* net, const float* img_chw_host, float* out_chw_host, int height,
+                                  int width, int cs, int ucs, int ol, int batch, int crop_begin, int crop_end,
+                                  int d2h_y0, int d2h_y1, float** d_out) {
+  return enqueue_host_range(net, img_chw_host, out_chw_host, height, width, cs, ucs, ol, batch, crop_begin, crop_end,
+                            d2h_y0, d2h_y1, d_out);
+}
+
+int nind_host_join(nind_net* net, void* stream) {
+  if (!net) return fail(NIND_E_INVALID, "null handle");
+  if (!net->s_comp) return 0;
+  if (!net->ev_join) CUDA_TRY(cudaEventCreateWithFlags(&net->ev_join, cudaEventDisableTiming));
+  CUDA_TRY(cudaEventRecord(net->ev_join, net->s_comp));
+  CUDA_TRY(cudaStreamWaitEvent(static_cast<cudaStream_t>(stream), net->ev_join, 0));
+  return 0;
 }
 
 int nind_host_register(void* ptr, size_t bytes) {

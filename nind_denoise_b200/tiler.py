@@ -285,6 +285,32 @@ def exchange_seams(band: Optional[torch.Tensor], extents, own, rank: int, group=
         band[:, a - y0:b - y0, :] += buf
 
 
+class _DevicePtr:
+    """Zero-copy torch view of library-owned device memory (``__cuda_array_interface__``)."""
+
+    def __init__(self, ptr: int, shape):
+        self.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": "<f4", "data": (int(ptr), False),
+                                         "version": 2, "strides": None}
+
+
+def host_range(model, img_host: torch.Tensor, out_host: torch.Tensor, cs: int, ucs: int, ol: int, batch: int,
+               crop_begin: int, crop_end: int, d2h_y0: int, d2h_y1: int) -> torch.Tensor:
+    """``nind_tiled_denoise_host_range`` + ``nind_host_join``: enqueue one rank's crops on the library's
+    H2D | compute | D2H pipeline (rows [d2h_y0, d2h_y1) go to ``out_host`` as they complete) and return the
+    device image [3,H,W] its band is stitched into, ordered on the current torch stream."""
+    if img_host.is_cuda or out_host.is_cuda or img_host.dtype != torch.float32 or not img_host.is_contiguous():
+        raise ValueError("host_range expects contiguous fp32 CPU tensors")
+    _, H, W = img_host.shape
+    h = model.native_handle()
+    lib = _capi.lib()
+    d_out = C.c_void_p()
+    with torch.cuda.device(model._device):
+        _capi.check(lib.nind_tiled_denoise_host_range(h, img_host.data_ptr(), out_host.data_ptr(), H, W, cs, ucs, ol,
+                                                      batch, crop_begin, crop_end, d2h_y0, d2h_y1, C.byref(d_out)))
+        _capi.check(lib.nind_host_join(h, C.c_void_p(torch.cuda.current_stream().cuda_stream)))
+        return torch.as_tensor(_DevicePtr(d_out.value, (3, H, W)), device=model._device)
+
+
 class SharedHostImage:
     """A [3,H,W] fp32 host image in ONE shared-memory segment mapped by every rank of ``group`` (ranks of a
     node), page-locked on each rank: the multi-GPU host entry lets every GPU copy the rows it owns straight
@@ -350,6 +376,37 @@ def denoise_tiled_distributed_host(img_host: torch.Tensor, model, cs: int, ucs: 
     n = n_crops(W, H, cs, ucs, ol)
     ranges = shard_ranges(n, world)
     cb, ce = ranges[rank]
+    if isinstance(out, SharedHostImage):
+        if out.shape != (3, H, W):
+            raise ValueError(f"shared output is {out.shape}, image is {(3, H, W)}")
+        extents = band_extents(W, H, cs, ucs, ol, ranges)
+        own = owned_rows(extents, H)
+        y0, y1 = extents[rank]
+        o0, o1 = own[rank]
+        # own rows that earlier ranks' bands also touch are only final after the seam exchange
+        lo = min(o1, max([o0] + [extents[r][1] for r in range(rank) if extents[r][1] > extents[r][0]]))
+        band = full = None
+        if ce > cb:
+            if band_fn is None:
+                if batch is None:
+                    batch = default_batch(ce - cb, cs, _nx(W, ucs, ol))
+                # H2D | forward | stitch | D2H of rows [lo, o1) pipelined inside the library; the stream we
+                # continue on is ordered after its compute stream
+                full = host_range(model, img_host, out.tensor, cs, ucs, ol, batch, cb, ce, lo, o1)
+                band = full[:, y0:y1, :]
+            else:
+                band, by0, by1 = band_fn(img_host, cb, ce)
+                assert (by0, by1) == (y0, y1)
+                out.tensor[:, lo:o1, :].copy_(band[:, lo - y0:o1 - y0, :])
+        exchange_seams(band, extents, own, rank, group)
+        if lo > o0:
+            for c in range(3):
+                out.tensor[c, o0:lo].copy_(band[c, o0 - y0:lo - y0], non_blocking=True)
+        if band_fn is None and ce > cb:
+            _capi.check(_capi.lib().nind_host_sync(model.native_handle()))
+            torch.cuda.current_stream(model._device).synchronize()
+        dist.barrier(group)  # every rank's rows have landed in the shared image
+        return out.tensor if rank == dst else None
     if band_fn is None:
         dev = model._device if getattr(model, "_handle", None) else next(model.parameters()).device
         d_img = torch.empty((3, H, W), dtype=torch.float32, device=dev)
@@ -359,38 +416,15 @@ def denoise_tiled_distributed_host(img_host: torch.Tensor, model, cs: int, ucs: 
                 d_img[c, r0:r1].copy_(img_host[c, r0:r1], non_blocking=True)
     else:
         dev, d_img = img_host.device, img_host
-    if not isinstance(out, SharedHostImage):
-        res = denoise_tiled_distributed(d_img, model, cs, ucs, ol, batch=batch, group=group, dst=dst, band_fn=band_fn)
-        if rank != dst:
-            return None
-        if out is None:
-            out = torch.empty((3, H, W), dtype=torch.float32, pin_memory=dev.type == "cuda")
-        out.copy_(res, non_blocking=True)
-        if dev.type == "cuda":
-            torch.cuda.synchronize(dev)
-        return out
-    if out.shape != (3, H, W):
-        raise ValueError(f"shared output is {out.shape}, image is {(3, H, W)}")
-    extents = band_extents(W, H, cs, ucs, ol, ranges)
-    own = owned_rows(extents, H)
-    band = None
-    if ce > cb:
-        if band_fn is None:
-            if batch is None:
-                batch = default_batch(ce - cb, cs, _nx(W, ucs, ol))
-            band, y0, y1 = _band(model, d_img, cs, ucs, ol, cb, ce, batch)
-        else:
-            band, y0, y1 = band_fn(d_img, cb, ce)
-        assert (y0, y1) == extents[rank]
-    exchange_seams(band, extents, own, rank, group)
-    o0, o1 = own[rank]
-    if o1 > o0:
-        for c in range(3):
-            out.tensor[c, o0:o1].copy_(band[c, o0 - y0:o1 - y0], non_blocking=True)
+    res = denoise_tiled_distributed(d_img, model, cs, ucs, ol, batch=batch, group=group, dst=dst, band_fn=band_fn)
+    if rank != dst:
+        return None
+    if out is None:
+        out = torch.empty((3, H, W), dtype=torch.float32, pin_memory=dev.type == "cuda")
+    out.copy_(res, non_blocking=True)
     if dev.type == "cuda":
-        torch.cuda.current_stream(dev).synchronize()
-    dist.barrier(group)  # every rank's rows have landed in the shared image
-    return out.tensor if rank == dst else None
+        torch.cuda.synchronize(dev)
+    return out
 
 
 # ------------------------------------------------------------------------------ geometry ops

@@ -374,3 +374,44 @@ def test_throughput_mode_matches_single_image_path(utnet):
         ref = nb.denoise_tiled_host(im, utnet, cs, ucs, ol, batch=4)
         assert out.shape == im.shape
         assert float((out - ref).abs().max()) <= 1e-6
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("world", [2, 3, 5])
+def test_host_range_pipeline_composes_to_the_whole_image(utnet, world):
+    """nind_tiled_denoise_host_range: the per-rank share of the multi-GPU host entry, run here rank after
+    rank on one GPU with the seam exchange done locally, gives the single-GPU image; rows [lo, o1) arrive
+    in the host image straight from the pipeline."""
+    from nind_denoise_b200.tiler import host_range
+    rng = np.random.default_rng(21)
+    H, W, cs, ucs, ol = 610, 455, 120, 96, 6
+    img = torch.from_numpy(rng.random((3, H, W), dtype=np.float32)).pin_memory()
+    ref = nb.denoise_tiled_host(img, utnet, cs, ucs, ol, batch=7)
+    ranges = nb.shard_ranges(nb.n_crops(W, H, cs, ucs, ol), world)
+    ext = nb.band_extents(W, H, cs, ucs, ol, ranges)
+    own = nb.owned_rows(ext, H)
+    out = torch.full((3, H, W), float("nan")).pin_memory()
+    bands = []
+    for r, (cb, ce) in enumerate(ranges):
+        if ce <= cb:
+            bands.append(None)
+            continue
+        o0, o1 = own[r]
+        lo = min(o1, max([o0] + [ext[q][1] for q in range(r) if ext[q][1] > ext[q][0]]))
+        full = host_range(utnet, img, out, cs, ucs, ol, 6, cb, ce, lo, o1)
+        _capi.check(_capi.lib().nind_host_sync(utnet.native_handle()))
+        torch.cuda.synchronize()
+        bands.append(full[:, ext[r][0]:ext[r][1], :].clone())
+        assert not torch.isnan(out[:, lo:o1]).any()
+        # seam rows [o0, lo): what exchange_seams does between ranks
+        if lo > o0:
+            acc = torch.zeros((3, lo - o0, W), device="cuda")
+            for q in range(r + 1):
+                if bands[q] is None:
+                    continue
+                a, b = max(ext[q][0], o0), min(ext[q][1], lo)
+                if b > a:
+                    acc[:, a - o0:b - o0] += bands[q][:, a - ext[q][0]:b - ext[q][0]]
+            out[:, o0:lo] = acc.cpu()
+    assert not torch.isnan(out).any()
+    assert float((out - ref).abs().max()) <= 1e-6
