@@ -55,6 +55,8 @@ struct Step {
 
 struct Plan {
   int b = 0, h = 0, w = 0;
+  size_t bytes = 0;          // activation arena owned by this plan
+  unsigned long long last_use = 0;
   std::vector<void*> bufs;
   std::vector<Step> steps;
   int gather_step = -1, head_step = -1;
@@ -108,6 +110,7 @@ struct nind_net {
   float* head_b = nullptr;
   int* err_flag = nullptr;
   std::map<std::vector<int>, std::unique_ptr<Plan>> plans;
+  unsigned long long plan_tick = 0;
   // tiled driver scratch
   float* crops_buf = nullptr;
   size_t crops_cap = 0;
@@ -127,6 +130,7 @@ struct nind_net {
   cudaStream_t s_in = nullptr, s_comp = nullptr, s_out = nullptr;
   std::vector<cudaEvent_t> ev_in, ev_done;
   cudaEvent_t ev_join = nullptr;
+  int host_first = -1, host_last = -1;  // crops in the first / last pipeline step (-1: one grid row)
   // options
   int n_tile_deep = 256, max_ctas = 0, cg = 0, fuse_pool = 1;
   // First layer: 3x3 implicit GEMM over the 8-channel padded-crop tensor (1) or K=64 GEMM over an im2col (0).
@@ -437,6 +441,7 @@ struct PlanBuilder {
       return a;
     }
     plan->bufs.push_back(p);
+    plan->bytes += a.elems() * sizeof(__nv_bfloat16);
     a.ptr = static_cast<__nv_bfloat16*>(p);
     return a;
   }
@@ -655,14 +660,30 @@ int build_unet_plan(nind_net* net, Plan* plan, int B, int H, int W) {
 int get_plan(nind_net* net, int B, int H, int W, Plan** out) {
   std::vector<int> key{B, H, W};
   auto it = net->plans.find(key);
-  if (it != net->plans.end()) { *out = it->second.get(); return 0; }
+  if (it != net->plans.end()) {
+    it->second->last_use = ++net->plan_tick;
+    *out = it->second.get();
+    return 0;
+  }
   std::unique_ptr<Plan> plan(new Plan);
   plan->b = B; plan->h = H; plan->w = W;
   int rc = net->arch == NIND_ARCH_UTNET ? build_utnet_plan(net, plan.get(), B, H, W)
                                          : build_unet_plan(net, plan.get(), B, H, W);
   if (rc) return rc;
-  // keep at most a few plans alive (each owns an activation arena)
-  if (net->plans.size() >= 4) net->plans.erase(net->plans.begin());
+  // Keep a few plans alive (each owns an activation arena): least recently used go first once there are
+  // more than 8 or they hold more than 48 GB.  (cudaFree waits for the device, so work still queued on an
+  // evicted plan's buffers has finished.)
+  plan->last_use = ++net->plan_tick;
+  for (;;) {
+    size_t total = plan->bytes;
+    auto lru = net->plans.end();
+    for (auto i = net->plans.begin(); i != net->plans.end(); ++i) {
+      total += i->second->bytes;
+      if (lru == net->plans.end() || i->second->last_use < lru->second->last_use) lru = i;
+    }
+    if (lru == net->plans.end() || (net->plans.size() < 8 && total <= (48ull << 30))) break;
+    net->plans.erase(lru);
+  }
   *out = plan.get();
   net->plans[key] = std::move(plan);
   return 0;
@@ -832,6 +853,12 @@ int nind_set_option(nind_net* net, const char* key, int value) {
     net->fuse_pool = value ? 1 : 0;
   } else if (k == "first_c8") {
     net->first_c8 = value ? 1 : 0;
+  } else if (k == "host_first") {  // crops in the first step of the host pipeline (-1: one grid row)
+    net->host_first = value;
+    return 0;
+  } else if (k == "host_last") {
+    net->host_last = value;
+    return 0;
   } else {
     return fail(NIND_E_INVALID, "unknown option " + k);
   }
@@ -1016,13 +1043,12 @@ static int enqueue_host_range(nind_net* net, const float* img_chw_host, float* o
   // Steps.  The first and the last are about one grid row of crops, so that compute starts after a small
   // part of the upload and only a small part of the download is exposed; the rest are `batch` crops.
   std::vector<std::pair<int, int>> steps;
-  if (n > 2 * g.nx && batch > g.nx) {
-    steps.push_back({cb, cb + g.nx});
-    for (int i = cb + g.nx; i < ce - g.nx; i += batch) steps.push_back({i, std::min(ce - g.nx, i + batch)});
-    steps.push_back({ce - g.nx, ce});
-  } else {
-    for (int i = cb; i < ce; i += batch) steps.push_back({i, std::min(ce, i + batch)});
-  }
+  int first = net->host_first >= 0 ? net->host_first : (n > 2 * g.nx && batch > g.nx ? g.nx : 0);
+  int last = net->host_last >= 0 ? net->host_last : (n > 2 * g.nx && batch > g.nx ? g.nx : 0);
+  if (first + last >= n) first = last = 0;
+  if (first) steps.push_back({cb, cb + first});
+  for (int i = cb + first; i < ce - last; i += batch) steps.push_back({i, std::min(ce - last, i + batch)});
+  if (last) steps.push_back({ce - last, ce});
   while (net->ev_in.size() < steps.size()) {
     cudaEvent_t a, b;
     CUDA_TRY(cudaEventCreateWithFlags(&a, cudaEventDisableTiming));
