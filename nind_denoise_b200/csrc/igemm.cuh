@@ -25,6 +25,7 @@
 //              global stores (8 pixels x 64 B per warp instruction); the epilogue of a tile overlaps
 //              the MMAs of the next two tiles.
 #pragma once
+#include <type_traits>
 #include "ptx.cuh"
 
 namespace nind {
@@ -351,172 +352,231 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     if (p.epi_mode == EPI_HEAD) {
       for (int i = etid; i < 195; i += 128) head_s[i] = i < 192 ? __ldg(p.head_w + i) : __ldg(p.head_b + i - 192);
     }
-    const int n_groups = N_TILE / 64;
+    constexpr int n_groups = N_TILE / 64;
     const uint32_t acc = eset;
-    int prev_nt = -1, bsel = 1;
-    uint32_t aph = 0;
-    int tl = eset;
     const uint32_t t_empty_addr = CG == 2 ? mapa_shared(t_empty + 8 * acc, 0) : (t_empty + 8 * acc);
-    for (int tile = tile0 + eset * tstep; tile < p.total_tiles; tile += ES * tstep, tl += ES, aph ^= 1) {
-      const int nt = tile / tiles_xy;
-      const int r = tile % tiles_xy;
-      int yt = r / p.tiles_x, xt = r - yt * p.tiles_x;
-      if (CG == 2) { if (p.pair_y) yt = yt * 2 + (int)cg_rank; else xt = xt * 2 + (int)cg_rank; }
+    // Lane roles.  TMEM side: thread = accumulator row (pixel quarter*32 + lane), registers = channels.
+    // Store side: 4 lanes cover one pixel's 32 channels (64 B); lane (sub, ch) writes pixel column `sub` of
+    // the warp's four tile rows, so its four destinations are plain per-tile integer math (no shuffles).
+    const int sub = lane >> 2, ch = lane & 3;
+    uint8_t* const stg_w = stg + lane * 64;               // this thread's staging row (16-byte chunks swizzled)
+    const int sw_w = (lane >> 1) & 3;
+    const uint8_t* const stg_r = stg + sub * 64 + ((ch ^ ((sub >> 1) & 3)) << 4);  // + it * 512
+    // fused 2x2 max-pool: lane -> (pooled pixel sub, 16-byte chunk ch); source rows r00, +1, +8, +9
+    const int r00 = (sub >> 2) * 16 + (sub & 3) * 2;
+    const uint8_t* const stg_p = stg + r00 * 64 + ((ch ^ ((r00 >> 1) & 3)) << 4);
 
-      if (nt != prev_nt) {  // (re)stage this N-tile's bias; uniform over the four warps of the set
-        prev_nt = nt;
-        bsel ^= 1;
-        for (int i = etid; i < N_TILE; i += 128) {
-          const int n = nt * N_TILE + i;
-          float bv = 0.f;
-          if (n < p.n_total) bv = __ldg(p.bias + (p.epi_mode == EPI_D2S ? n % p.d2s_cout : n));
-          bias_s[bsel * 256 + i] = bv;
+    // The tile loop is instantiated per (store mode, activation) so that nothing is decided per element:
+    // MODE 0 store, 1 store + fused max-pool, 2 depth-to-space, 3 fused 1x1 head;
+    // ACT 0 none, 1 PReLU/ReLU with 0 <= slope <= 1 (max(x, a*x)), 2 anything else.
+    auto run = [&](auto mode_c, auto act_c) {
+      constexpr int MODE = decltype(mode_c)::value;
+      constexpr int ACT = decltype(act_c)::value;
+      int prev_nt = -1, bsel = 1;
+      uint32_t aph = 0;
+      int tl = eset;
+      for (int tile = tile0 + eset * tstep; tile < p.total_tiles; tile += ES * tstep, tl += ES, aph ^= 1) {
+        const int nt = tile / tiles_xy;
+        const int r = tile % tiles_xy;
+        int yt = r / p.tiles_x, xt = r - yt * p.tiles_x;
+        if (CG == 2) { if (p.pair_y) yt = yt * 2 + (int)cg_rank; else xt = xt * 2 + (int)cg_rank; }
+
+        if (nt != prev_nt) {  // (re)stage this N-tile's bias; uniform over the four warps of the set
+          prev_nt = nt;
+          bsel ^= 1;
+          for (int i = etid; i < N_TILE; i += 128) {
+            const int n = nt * N_TILE + i;
+            float bv = 0.f;
+            if (n < p.n_total) bv = __ldg(p.bias + (MODE == 2 ? n % p.d2s_cout : n));
+            bias_s[bsel * 256 + i] = bv;
+          }
+          asm volatile("bar.sync %0, 128;" ::"r"(eset + 1) : "memory");
         }
-        asm volatile("bar.sync %0, 128;" ::"r"(eset + 1) : "memory");
-      }
 
-      const int row = quarter * 32 + lane;
-      const int yflat = yt * IG_TILE_H + (row >> 3);
-      const int x = xt * IG_TILE_W + (row & 7);
-      const int b = yflat / p.hs_in;
-      const int y = yflat - b * p.hs_in;
-      const bool valid = (yflat < p.rows_total) && (y < p.h_valid) && (x < p.w_valid);
-      // element offset of this thread's pixel in the destination (channel 0 of the layer's range)
-      const long long pix_off = p.epi_mode == EPI_D2S
-                                    ? b * p.o_img + (long long)(2 * y) * p.o_row + (long long)(2 * x) * p.o_pix
-                                    : b * p.o_img + (long long)y * p.o_row + (long long)x * p.o_pix;
-      const long long pool_off = b * p.pl_img + (long long)(y >> 1) * p.pl_row + (long long)(x >> 1) * p.pl_pix;
-      // number of 64-column groups of this tile that hold real output columns
-      int live = (p.n_total - nt * N_TILE + 63) / 64;
-      live = live > n_groups ? n_groups : live;
-
-      mbar_wait(t_full + 8 * acc, aph, p.err, 6);
-      tc_fence_after();
-      if (quarter == 0) NIND_TRACE(tl, TR_EPI_TFULL);
-      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * N_TILE;
-
-      float h0 = 0.f, h1 = 0.f, h2 = 0.f;
-#pragma unroll 1
-      for (int c64 = 0; c64 < live; ++c64) {
-        const int n = nt * N_TILE + c64 * 64;
-        long long off = pix_off;
-        if (p.epi_mode == EPI_D2S) {
-          const int q = n / p.d2s_cout;
-          off += (long long)(q >> 1) * p.o_row + (long long)(q & 1) * p.o_pix + (n - q * p.d2s_cout);
+        // ---- per-tile destination geometry
+        // (element offsets fit 32 bits: build_igemm rejects larger destination buffers)
+        uint32_t dst[4];            // MODE 0..2: channel 0 of the layer's range at this lane's four pixels
+        uint32_t vmask = 0;         //            which of them exist
+        uint32_t pdst = 0;
+        bool pvalid = false;        // MODE 1: pooled pixel
+        float* hdst = nullptr;      // MODE 3: this thread's output pixel (nullptr: none)
+        if (MODE == 3) {
+          const int row = quarter * 32 + lane;
+          const int yflat = yt * IG_TILE_H + (row >> 3);
+          const int x = xt * IG_TILE_W + (row & 7);
+          const int b = yflat / p.hs_in;
+          const int y = yflat - b * p.hs_in;
+          const int oy = y - p.h_unpad, ox = x - p.h_unpad;
+          if ((yflat < p.rows_total) && (y < p.h_valid) && (x < p.w_valid) && oy >= 0 && ox >= 0 && oy < p.h_size_y &&
+              ox < p.h_size_x)
+            hdst = p.head_out + b * p.h_img + (long long)oy * p.h_row + ox;
         } else {
-          off += n;
+          const int x = xt * IG_TILE_W + sub;
+          const int yf0 = yt * IG_TILE_H + quarter * 4;
+          int b = yf0 / p.hs_in;
+          int y = yf0 - b * p.hs_in;
+          const int xp = xt * IG_TILE_W + (sub & 3) * 2, pit = (sub >> 2) * 2;
+#pragma unroll
+          for (int it = 0; it < 4; ++it) {
+            const bool row_ok = (yf0 + it < p.rows_total) && (y < p.h_valid);
+            vmask |= (uint32_t)(row_ok && (x < p.w_valid)) << it;
+            const long long o = MODE == 2 ? b * p.o_img + (long long)(2 * y) * p.o_row + (long long)(2 * x) * p.o_pix
+                                          : b * p.o_img + (long long)y * p.o_row + (long long)x * p.o_pix;
+            dst[it] = (uint32_t)o + ch * 8;
+            if (MODE == 1 && it == pit) {
+              pdst = (uint32_t)(b * p.pl_img + (long long)(y >> 1) * p.pl_row + (long long)(xp >> 1) * p.pl_pix) + ch * 8;
+              pvalid = row_ok && (xp < p.w_valid);
+            }
+            if (++y == p.hs_in) { y = 0; ++b; }
+          }
         }
+        // number of 64-column groups of this tile that hold real output columns
+        int live = (p.n_total - nt * N_TILE + 63) / 64;
+        live = live > n_groups ? n_groups : live;
+
+        mbar_wait(t_full + 8 * acc, aph, p.err, 6);
+        tc_fence_after();
+        if (quarter == 0) NIND_TRACE(tl, TR_EPI_TFULL);
+        const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * N_TILE;
+
+        float h0 = 0.f, h1 = 0.f, h2 = 0.f;
 #pragma unroll 1
-        for (int half = 0; half < 2; ++half) {
-          uint32_t v[32];
-          tmem_ld_32x32(taddr + c64 * 64 + half * 32, v);
-          tmem_wait_ld();
-          if (half == 1 && c64 == live - 1) {  // accumulator fully read: hand it back to the MMA warp
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) {
-              if (CG == 2) mbar_arrive_cluster(t_empty_addr);
-              else mbar_arrive(t_empty_addr);
-            }
-            if (quarter == 0) NIND_TRACE(tl, TR_EPI_TMEM);
+        for (int c64 = 0; c64 < live; ++c64) {
+          const int n = nt * N_TILE + c64 * 64;
+          uint32_t extra = n;  // element offset of this group's first channel from dst[]
+          if (MODE == 2) {
+            const int q = n / p.d2s_cout;
+            extra = (uint32_t)((long long)(q >> 1) * p.o_row + (long long)(q & 1) * p.o_pix + (n - q * p.d2s_cout));
           }
-          float f[32];
-          const float4* bp = reinterpret_cast<const float4*>(bias_s + bsel * 256 + c64 * 64 + half * 32);
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const float4 bb = bp[j];
-            f[4 * j + 0] = __uint_as_float(v[4 * j + 0]) + bb.x;
-            f[4 * j + 1] = __uint_as_float(v[4 * j + 1]) + bb.y;
-            f[4 * j + 2] = __uint_as_float(v[4 * j + 2]) + bb.z;
-            f[4 * j + 3] = __uint_as_float(v[4 * j + 3]) + bb.w;
-          }
-          if (p.act == ACT_PRELU) {  // also ReLU (slope 0)
-            const float sl = p.slope;
-            if (sl >= 0.f && sl <= 1.f) {  // max(x, a*x) == PReLU for 0 <= a <= 1: FMUL + FMNMX
-#pragma unroll
-              for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], f[j] * sl);
-            } else {
-#pragma unroll
-              for (int j = 0; j < 32; ++j) f[j] = f[j] > 0.f ? f[j] : f[j] * sl;
-            }
-          } else if (p.act == ACT_ELU) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) f[j] = f[j] > 0.f ? f[j] : (__expf(f[j]) - 1.f);
-          } else if (p.act == ACT_HARDSWISH) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) f[j] = f[j] * fminf(fmaxf(f[j] + 3.f, 0.f), 6.f) * (1.f / 6.f);
-          }
-          if (p.epi_mode == EPI_HEAD) {
-            const float* w0 = head_s + half * 32;
-#pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              h0 = fmaf(f[j], w0[j], h0);
-              h1 = fmaf(f[j], w0[64 + j], h1);
-              h2 = fmaf(f[j], w0[128 + j], h2);
-            }
-          } else {
-            // this thread's 32 channels (64 B) -> staging row; 16-byte chunks XOR-swizzled so that both
-            // the row-wise writes and the pixel-wise reads below are bank-conflict free
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              uint4 o;
-              o.x = pack_bf16x2(f[8 * j + 0], f[8 * j + 1]);
-              o.y = pack_bf16x2(f[8 * j + 2], f[8 * j + 3]);
-              o.z = pack_bf16x2(f[8 * j + 4], f[8 * j + 5]);
-              o.w = pack_bf16x2(f[8 * j + 6], f[8 * j + 7]);
-              *reinterpret_cast<uint4*>(stg + lane * 64 + ((j ^ ((lane >> 1) & 3)) << 4)) = o;
-            }
-            __syncwarp();
-            // coalesced write-out: 4 lanes cover one pixel's 32 channels (64 B), 8 pixels per instruction
-            const int sub = lane >> 2, ch = lane & 3;
-#pragma unroll
-            for (int it = 0; it < 4; ++it) {
-              const int rr = it * 8 + sub;
-              const long long roff = __shfl_sync(0xffffffffu, off, rr);
-              const int rvalid = __shfl_sync(0xffffffffu, (int)valid, rr);
-              const uint4 o = *reinterpret_cast<const uint4*>(stg + rr * 64 + ((ch ^ ((rr >> 1) & 3)) << 4));
-              if (rvalid) *reinterpret_cast<uint4*>(p.out + roff + half * 32 + ch * 8) = o;
-            }
-            if (p.pool_out) {
-              // fused 2x2 max-pool: this warp's 32 rows are 4 tile rows x 8 pixels = 2 x 4 pooled pixels;
-              // lane -> (pooled pixel, 16-byte chunk); tile origins and map sizes are even, so the
-              // validity of the top-left source pixel covers all four
-              const int pp = lane >> 2;
-              const int r00 = (pp >> 2) * 16 + (pp & 3) * 2;
-              const long long poff = __shfl_sync(0xffffffffu, pool_off, r00);
-              const int pvalid = __shfl_sync(0xffffffffu, (int)valid, r00);
-              uint4 m = *reinterpret_cast<const uint4*>(stg + r00 * 64 + ((ch ^ ((r00 >> 1) & 3)) << 4));
-              const int rs[3] = {r00 + 1, r00 + 8, r00 + 9};
-#pragma unroll
-              for (int k = 0; k < 3; ++k) {
-                const uint4 t = *reinterpret_cast<const uint4*>(stg + rs[k] * 64 + ((ch ^ ((rs[k] >> 1) & 3)) << 4));
-                __nv_bfloat162* pm = reinterpret_cast<__nv_bfloat162*>(&m);
-                const __nv_bfloat162* pt = reinterpret_cast<const __nv_bfloat162*>(&t);
-#pragma unroll
-                for (int e = 0; e < 4; ++e) pm[e] = __hmax2(pm[e], pt[e]);
+          for (int half = 0; half < 2; ++half) {
+            uint32_t v[32];
+            tmem_ld_32x32(taddr + c64 * 64 + half * 32, v);
+            tmem_wait_ld();
+            if (half == 1 && c64 == live - 1) {  // accumulator fully read: hand it back to the MMA warp
+              tc_fence_before();
+              __syncwarp();
+              if (lane == 0) {
+                if (CG == 2) mbar_arrive_cluster(t_empty_addr);
+                else mbar_arrive(t_empty_addr);
               }
-              if (pvalid) *reinterpret_cast<uint4*>(p.pool_out + poff + n + half * 32 + ch * 8) = m;
+              if (quarter == 0) NIND_TRACE(tl, TR_EPI_TMEM);
             }
-            __syncwarp();
+            float f[32];
+            const float4* bp = reinterpret_cast<const float4*>(bias_s + bsel * 256 + c64 * 64 + half * 32);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const float4 bb = bp[j];
+              f[4 * j + 0] = __uint_as_float(v[4 * j + 0]);
+              f[4 * j + 1] = __uint_as_float(v[4 * j + 1]);
+              f[4 * j + 2] = __uint_as_float(v[4 * j + 2]);
+              f[4 * j + 3] = __uint_as_float(v[4 * j + 3]);
+              f32x2_add(f[4 * j + 0], f[4 * j + 1], bb.x, bb.y);
+              f32x2_add(f[4 * j + 2], f[4 * j + 3], bb.z, bb.w);
+            }
+            if (ACT == 1) {  // max(x, a*x) == PReLU for 0 <= a <= 1 (ReLU: a = 0): FMUL2 + 2 FMNMX per pair
+              const float sl = p.slope;
+#pragma unroll
+              for (int j = 0; j < 16; ++j) {
+                float t0, t1;
+                f32x2_scale(t0, t1, f[2 * j], f[2 * j + 1], sl);
+                f[2 * j] = fmaxf(f[2 * j], t0);
+                f[2 * j + 1] = fmaxf(f[2 * j + 1], t1);
+              }
+            } else if (ACT == 2) {
+              if (p.act == ACT_PRELU) {
+                const float sl = p.slope;
+#pragma unroll
+                for (int j = 0; j < 32; ++j) f[j] = f[j] > 0.f ? f[j] : f[j] * sl;
+              } else if (p.act == ACT_ELU) {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) f[j] = f[j] > 0.f ? f[j] : (__expf(f[j]) - 1.f);
+              } else if (p.act == ACT_HARDSWISH) {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) f[j] = f[j] * fminf(fmaxf(f[j] + 3.f, 0.f), 6.f) * (1.f / 6.f);
+              }
+            }
+            if (MODE == 3) {
+              const float* w0 = head_s + half * 32;
+#pragma unroll
+              for (int j = 0; j < 32; ++j) {
+                h0 = fmaf(f[j], w0[j], h0);
+                h1 = fmaf(f[j], w0[64 + j], h1);
+                h2 = fmaf(f[j], w0[128 + j], h2);
+              }
+            } else {
+              // this thread's 32 channels (64 B) -> staging row; 16-byte chunks XOR-swizzled so that both
+              // the row-wise writes and the pixel-wise reads below are bank-conflict free
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                uint4 o;
+                o.x = pack_bf16x2(f[8 * j + 0], f[8 * j + 1]);
+                o.y = pack_bf16x2(f[8 * j + 2], f[8 * j + 3]);
+                o.z = pack_bf16x2(f[8 * j + 4], f[8 * j + 5]);
+                o.w = pack_bf16x2(f[8 * j + 6], f[8 * j + 7]);
+                *reinterpret_cast<uint4*>(stg_w + ((j ^ sw_w) << 4)) = o;
+              }
+              __syncwarp();
+              // coalesced write-out: 8 pixels x 64 B per warp instruction
+              const uint32_t e = extra + half * 32;
+#pragma unroll
+              for (int it = 0; it < 4; ++it) {
+                const uint4 o = *reinterpret_cast<const uint4*>(stg_r + it * 512);
+                if (vmask & (1u << it)) *reinterpret_cast<uint4*>(p.out + (dst[it] + e)) = o;
+              }
+              if (MODE == 1) {
+                // fused 2x2 max-pool: this warp's 32 rows are 4 tile rows x 8 pixels = 2 x 4 pooled pixels;
+                // tile origins and map sizes are even, so the validity of the top-left source pixel covers
+                // all four
+                uint4 m = *reinterpret_cast<const uint4*>(stg_p);
+                const int rs[3] = {64, 512, 576};
+#pragma unroll
+                for (int k = 0; k < 3; ++k) {
+                  const uint4 t = *reinterpret_cast<const uint4*>(stg_p + rs[k]);
+                  __nv_bfloat162* pm = reinterpret_cast<__nv_bfloat162*>(&m);
+                  const __nv_bfloat162* pt = reinterpret_cast<const __nv_bfloat162*>(&t);
+#pragma unroll
+                  for (int q = 0; q < 4; ++q) pm[q] = __hmax2(pm[q], pt[q]);
+                }
+                if (pvalid) *reinterpret_cast<uint4*>(p.pool_out + (pdst + n + half * 32)) = m;
+              }
+              __syncwarp();
+            }
           }
         }
-      }
-      if (quarter == 0) NIND_TRACE(tl, TR_EPI_DONE);
-      if (p.epi_mode == EPI_HEAD) {
-        const int oy = y - p.h_unpad, ox = x - p.h_unpad;
-        if (valid && oy >= 0 && ox >= 0 && oy < p.h_size_y && ox < p.h_size_x) {
+        if (quarter == 0) NIND_TRACE(tl, TR_EPI_DONE);
+        if (MODE == 3 && hdst) {
           float o0 = h0 + head_s[192], o1 = h1 + head_s[193], o2 = h2 + head_s[194];
           if (p.head_sigmoid) {
             o0 = 1.f / (1.f + __expf(-o0));
             o1 = 1.f / (1.f + __expf(-o1));
             o2 = 1.f / (1.f + __expf(-o2));
           }
-          float* ho = p.head_out + b * p.h_img + (long long)oy * p.h_row + ox;
-          ho[0] = o0;
-          ho[p.h_plane] = o1;
-          ho[2 * p.h_plane] = o2;
+          hdst[0] = o0;
+          hdst[p.h_plane] = o1;
+          hdst[2 * p.h_plane] = o2;
         }
       }
+    };
+    const int mode = p.epi_mode == EPI_HEAD ? 3 : (p.epi_mode == EPI_D2S ? 2 : (p.pool_out ? 1 : 0));
+    const int actk = p.act == ACT_NONE ? 0 : ((p.act == ACT_PRELU && p.slope >= 0.f && p.slope <= 1.f) ? 1 : 2);
+    using I0 = std::integral_constant<int, 0>;
+    using I1 = std::integral_constant<int, 1>;
+    using I2 = std::integral_constant<int, 2>;
+    using I3 = std::integral_constant<int, 3>;
+    switch (mode * 3 + actk) {
+      case 0: run(I0{}, I0{}); break;
+      case 1: run(I0{}, I1{}); break;
+      case 2: run(I0{}, I2{}); break;
+      case 3: run(I1{}, I0{}); break;
+      case 4: run(I1{}, I1{}); break;
+      case 5: run(I1{}, I2{}); break;
+      case 6: run(I2{}, I0{}); break;
+      case 7: run(I2{}, I1{}); break;
+      case 8: run(I2{}, I2{}); break;
+      case 9: run(I3{}, I0{}); break;
+      case 10: run(I3{}, I1{}); break;
+      default: run(I3{}, I2{}); break;
     }
   }
 

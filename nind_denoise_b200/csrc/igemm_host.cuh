@@ -130,6 +130,9 @@ inline bool build_igemm(const ConvSpec& s, IgemmLaunch* L, std::string* why) {
   if (s.n_total % 64 != 0) return fail("output columns must be a multiple of 64");
   if (s.epi_mode == EPI_D2S && (s.d2s_cout % 64 != 0)) return fail("depth-to-space needs C_out multiple of 64");
   if (s.in.c % 8 != 0) return fail("buffer channel count must be a multiple of 8");
+  // the epilogue addresses its destinations with 32-bit element offsets
+  if (s.epi_mode != EPI_HEAD && s.out.elems() >= (1ull << 32)) return fail("destination buffer too large (>= 2^32 elements): use a smaller batch");
+  if (s.pool.ptr && s.pool.elems() >= (1ull << 32)) return fail("pool buffer too large (>= 2^32 elements)");
   const int shrink = s.taps == 9 ? 2 : 0;
   IgemmParams& p = L->p;
   memset(&p, 0, sizeof p);

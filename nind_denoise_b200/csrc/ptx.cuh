@@ -24,6 +24,20 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   return *reinterpret_cast<uint32_t*>(&t);
 }
 
+// Packed fp32 pairs (sm_100 FADD2 / FMUL2): two lanes of fp32 math per issued instruction.
+__device__ __forceinline__ void f32x2_add(float& a0, float& a1, float b0, float b1) {
+  asm("{\n\t.reg .b64 x, y;\n\tmov.b64 x, {%0, %1};\n\tmov.b64 y, {%2, %3};\n\tadd.rn.f32x2 x, x, y;\n\t"
+      "mov.b64 {%0, %1}, x;\n\t}"
+      : "+f"(a0), "+f"(a1)
+      : "f"(b0), "f"(b1));
+}
+__device__ __forceinline__ void f32x2_scale(float& r0, float& r1, float a0, float a1, float s) {
+  asm("{\n\t.reg .b64 x, y;\n\tmov.b64 x, {%2, %3};\n\tmov.b64 y, {%4, %4};\n\tmul.rn.f32x2 x, x, y;\n\t"
+      "mov.b64 {%0, %1}, x;\n\t}"
+      : "=f"(r0), "=f"(r1)
+      : "f"(a0), "f"(a1), "f"(s));
+}
+
 // ---------------------------------------------------------------- mbarrier
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
