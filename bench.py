@@ -45,10 +45,10 @@ def set_workload(network):
 
 
 # dram__bytes_read.sum + dram__bytes_write.sum of the heaviest igemm launch, from the committed
-# `ncu --set full` capture of this command (profiles/r01_ncu_summary.md)
-NCU_TRAFFIC = {(248, 168): 4.10e9}
-NCU_TRAFFIC_NOTE = ("tconvs4.0 launch (168 crops, 128->64 ch @250^2): 4.10 GB measured vs 4.07 GB algorithmic "
-                    "(bf16 in + out once); all four captured launches are within 3 % of algorithmic")
+# `ncu --set full` capture of this command (profiles/r01_v12_ncu_summary.md)
+NCU_TRAFFIC = {(248, 168): 4.05e9}
+NCU_TRAFFIC_NOTE = ("tconvs4.0 launch (168 crops, 128->64 ch @250^2): 4.05 GB measured vs 4.07 GB algorithmic "
+                    "(bf16 in + out once); all five captured launches are within 4 % of algorithmic")
 
 
 def workload(cs):
@@ -301,18 +301,22 @@ def main():
     d2h = out_host.numel() * 4
 
     # ---- throughput mode (BASELINE configs[4] in miniature): a stream of images through the async host entry
-    thr = None
-    if world == 1:
-        n_img = 6
-        outs2 = [out_host, torch.empty_like(img_host).pin_memory()]
-        nb.denoise_images_host([img_host] * 2, model, cs, ucs, ol, batch=batch, outs=outs2)
-        torch.cuda.synchronize()
-        t0 = time.perf_counter()
-        nb.denoise_images_host([img_host] * n_img, model, cs, ucs, ol, batch=batch,
-                               outs=[outs2[i & 1] for i in range(n_img)])
-        dt = time.perf_counter() - t0
-        thr = {"value": MP * n_img / dt, "unit": "MP/s", "images": n_img,
-               "note": "stream of images, host buffers in/out, H2D/D2H of neighbouring images overlapped"}
+    # N > 1: every rank streams whole images on its own GPU (replicas, no collective); aggregate over ranks.
+    n_img = 6
+    full_batch = args.batch or default_batch(n, cs, -(-(W_IMG - ucs) // (ucs - ol)) + 1)
+    outs2 = [out_host, torch.empty_like(img_host).pin_memory()]
+    nb.denoise_images_host([img_host] * 2, model, cs, ucs, ol, batch=full_batch, outs=outs2)
+    sync_all()
+    t0 = time.perf_counter()
+    nb.denoise_images_host([img_host] * n_img, model, cs, ucs, ol, batch=full_batch,
+                           outs=[outs2[i & 1] for i in range(n_img)])
+    torch.cuda.synchronize()
+    t3 = torch.tensor([time.perf_counter() - t0], device=dev)
+    if world > 1:
+        dist.all_reduce(t3, op=dist.ReduceOp.MAX)
+    thr = {"value": MP * n_img * world / float(t3.item()), "unit": "MP/s", "images": n_img * world,
+           "note": "stream of images, host buffers in/out, H2D/D2H of neighbouring images overlapped"
+                   + (f"; {n_img} whole images per GPU, {world} independent replicas" if world > 1 else "")}
 
     # ---- roofline of the dominant kernel (igemm conv): per-layer CUDA-event times over one image
     flops_image = (utnet_flops(cs) if NETWORK == "UtNet" else unet_flops(cs)) * n

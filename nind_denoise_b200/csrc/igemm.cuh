@@ -439,7 +439,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         if (quarter == 0) NIND_TRACE(tl, TR_EPI_TFULL);
         const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * N_TILE;
 
-        float h0 = 0.f, h1 = 0.f, h2 = 0.f;
+        float h0 = 0.f, h1 = 0.f, h2 = 0.f, g0 = 0.f, g1 = 0.f, g2 = 0.f;  // head: even / odd channel partial sums
 #pragma unroll 1
         for (int c64 = 0; c64 < live; ++c64) {
           const int n = nt * N_TILE + c64 * 64;
@@ -497,12 +497,14 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
               }
             }
             if (MODE == 3) {
-              const float* w0 = head_s + half * 32;
+              // 1x1 head: three dot products over this pixel's 64 channels, two channels per FFMA2
+              const float2* w0 = reinterpret_cast<const float2*>(head_s + half * 32);
 #pragma unroll
-              for (int j = 0; j < 32; ++j) {
-                h0 = fmaf(f[j], w0[j], h0);
-                h1 = fmaf(f[j], w0[64 + j], h1);
-                h2 = fmaf(f[j], w0[128 + j], h2);
+              for (int j = 0; j < 16; ++j) {
+                const float2 wa = w0[j], wb = w0[32 + j], wc = w0[64 + j];
+                f32x2_fma(h0, g0, f[2 * j], f[2 * j + 1], wa.x, wa.y);
+                f32x2_fma(h1, g1, f[2 * j], f[2 * j + 1], wb.x, wb.y);
+                f32x2_fma(h2, g2, f[2 * j], f[2 * j + 1], wc.x, wc.y);
               }
             } else {
               // this thread's 32 channels (64 B) -> staging row; 16-byte chunks XOR-swizzled so that both
@@ -546,7 +548,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         }
         if (quarter == 0) NIND_TRACE(tl, TR_EPI_DONE);
         if (MODE == 3 && hdst) {
-          float o0 = h0 + head_s[192], o1 = h1 + head_s[193], o2 = h2 + head_s[194];
+          float o0 = (h0 + g0) + head_s[192], o1 = (h1 + g1) + head_s[193], o2 = (h2 + g2) + head_s[194];
           if (p.head_sigmoid) {
             o0 = 1.f / (1.f + __expf(-o0));
             o1 = 1.f / (1.f + __expf(-o1));

@@ -31,6 +31,12 @@ __device__ __forceinline__ void f32x2_add(float& a0, float& a1, float b0, float 
       : "+f"(a0), "+f"(a1)
       : "f"(b0), "f"(b1));
 }
+__device__ __forceinline__ void f32x2_fma(float& c0, float& c1, float a0, float a1, float b0, float b1) {
+  asm("{\n\t.reg .b64 x, y, z;\n\tmov.b64 x, {%2, %3};\n\tmov.b64 y, {%4, %5};\n\tmov.b64 z, {%0, %1};\n\t"
+      "fma.rn.f32x2 z, x, y, z;\n\tmov.b64 {%0, %1}, z;\n\t}"
+      : "+f"(c0), "+f"(c1)
+      : "f"(a0), "f"(a1), "f"(b0), "f"(b1));
+}
 __device__ __forceinline__ void f32x2_scale(float& r0, float& r1, float a0, float a1, float s) {
   asm("{\n\t.reg .b64 x, y;\n\tmov.b64 x, {%2, %3};\n\tmov.b64 y, {%4, %4};\n\tmul.rn.f32x2 x, x, y;\n\t"
       "mov.b64 {%0, %1}, x;\n\t}"
