@@ -38,6 +38,9 @@ constexpr int IG_BAR_BYTES = 2048;     // mbarriers + TMEM base slot
 #ifndef NIND_SETS64
 #define NIND_SETS64 4
 #endif
+#ifndef NIND_EPI_X16
+#define NIND_EPI_X16 1
+#endif
 constexpr int IG_MAX_SETS = 4;         // epilogue warp sets (= TMEM accumulator stages)
 constexpr int IG_EPI_BYTES = IG_MAX_SETS * 3072;  // per set: staged bias [2][256] fp32 + head weights [3][64]+[3]
 constexpr int IG_SET_STAGE_BYTES = 8192;          // per set: 4 warps x 32 rows x 64 B of store staging
@@ -76,8 +79,7 @@ struct IgemmParams {
   long long pl_img, pl_row;
   int pl_pix;
   // EPI_HEAD: 1x1 conv to 3 channels (+ optional sigmoid), fp32 planar output
-  const float* head_w;     // [3][64]
-  const float* head_b;     // [3]
+  float head_c[196];       // [3][64] weights + [3] bias (copied from the device arrays when the launch is built)
   float* head_out;
   long long h_img, h_plane;
   int h_row;
@@ -347,12 +349,9 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     const int etid = threadIdx.x - 128 - eset * 128;  // 0..127 inside the set
     uint8_t* smem_gen = smem_raw + (sbase - smem_u32(smem_raw));
     float* bias_s = reinterpret_cast<float*>(smem_gen + (epi_base - sbase) + eset * 3072);  // [2][256] per set
-    float* head_s = bias_s + 512;                                                            // [3][64]+[3]
     uint8_t* stg = smem_gen + (stg_base - sbase) + (eset * 4 + quarter) * 2048;  // 32 rows x 64 B
-    if (p.epi_mode == EPI_HEAD) {
-      for (int i = etid; i < 195; i += 128) head_s[i] = i < 192 ? __ldg(p.head_w + i) : __ldg(p.head_b + i - 192);
-    }
     constexpr int n_groups = N_TILE / 64;
+    constexpr int CW = (N_TILE == 64 && NIND_EPI_X16) ? 16 : 32;  // accumulator columns per TMEM load
     const uint32_t acc = eset;
     const uint32_t t_empty_addr = CG == 2 ? mapa_shared(t_empty + 8 * acc, 0) : (t_empty + 8 * acc);
     // Lane roles.  TMEM side: thread = accumulator row (pixel quarter*32 + lane), registers = channels.
@@ -439,7 +438,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         if (quarter == 0) NIND_TRACE(tl, TR_EPI_TFULL);
         const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * N_TILE;
 
-        float h0 = 0.f, h1 = 0.f, h2 = 0.f, g0 = 0.f, g1 = 0.f, g2 = 0.f;  // head: even / odd channel partial sums
+        float h0 = 0.f, h1 = 0.f, h2 = 0.f;
 #pragma unroll 1
         for (int c64 = 0; c64 < live; ++c64) {
           const int n = nt * N_TILE + c64 * 64;
@@ -450,74 +449,81 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
           }
 #pragma unroll
           for (int half = 0; half < 2; ++half) {
-            uint32_t v[32];
-            tmem_ld_32x32(taddr + c64 * 64 + half * 32, v);
-            tmem_wait_ld();
-            if (half == 1 && c64 == live - 1) {  // accumulator fully read: hand it back to the MMA warp
-              tc_fence_before();
-              __syncwarp();
-              if (lane == 0) {
-                if (CG == 2) mbar_arrive_cluster(t_empty_addr);
-                else mbar_arrive(t_empty_addr);
-              }
-              if (quarter == 0) NIND_TRACE(tl, TR_EPI_TMEM);
-            }
-            float f[32];
-            const float4* bp = reinterpret_cast<const float4*>(bias_s + bsel * 256 + c64 * 64 + half * 32);
+            // CW accumulator columns at a time (16 for the 640-thread N_TILE = 64 kernels, whose 96-register
+            // budget a 32-wide chunk overflows)
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              const float4 bb = bp[j];
-              f[4 * j + 0] = __uint_as_float(v[4 * j + 0]);
-              f[4 * j + 1] = __uint_as_float(v[4 * j + 1]);
-              f[4 * j + 2] = __uint_as_float(v[4 * j + 2]);
-              f[4 * j + 3] = __uint_as_float(v[4 * j + 3]);
-              f32x2_add(f[4 * j + 0], f[4 * j + 1], bb.x, bb.y);
-              f32x2_add(f[4 * j + 2], f[4 * j + 3], bb.z, bb.w);
-            }
-            if (ACT == 1) {  // max(x, a*x) == PReLU for 0 <= a <= 1 (ReLU: a = 0): FMUL2 + 2 FMNMX per pair
-              const float sl = p.slope;
-#pragma unroll
-              for (int j = 0; j < 16; ++j) {
-                float t0, t1;
-                f32x2_scale(t0, t1, f[2 * j], f[2 * j + 1], sl);
-                f[2 * j] = fmaxf(f[2 * j], t0);
-                f[2 * j + 1] = fmaxf(f[2 * j + 1], t1);
+            for (int q = 0; q < 32 / CW; ++q) {
+              uint32_t v[CW];
+              tmem_ld_32x32(taddr + c64 * 64 + half * 32 + q * CW, v);
+              tmem_wait_ld();
+              if (half == 1 && q == 32 / CW - 1 && c64 == live - 1) {  // accumulator fully read: back to the MMA warp
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) {
+                  if (CG == 2) mbar_arrive_cluster(t_empty_addr);
+                  else mbar_arrive(t_empty_addr);
+                }
+                if (quarter == 0) NIND_TRACE(tl, TR_EPI_TMEM);
               }
-            } else if (ACT == 2) {
-              if (p.act == ACT_PRELU) {
+              float f[CW];
+              const float4* bp = reinterpret_cast<const float4*>(bias_s + bsel * 256 + c64 * 64 + half * 32 + q * CW);
+#pragma unroll
+              for (int j = 0; j < CW / 4; ++j) {
+                const float4 bb = bp[j];
+                f[4 * j + 0] = __uint_as_float(v[4 * j + 0]);
+                f[4 * j + 1] = __uint_as_float(v[4 * j + 1]);
+                f[4 * j + 2] = __uint_as_float(v[4 * j + 2]);
+                f[4 * j + 3] = __uint_as_float(v[4 * j + 3]);
+                f32x2_add(f[4 * j + 0], f[4 * j + 1], bb.x, bb.y);
+                f32x2_add(f[4 * j + 2], f[4 * j + 3], bb.z, bb.w);
+              }
+              if (ACT == 1) {  // max(x, a*x) == PReLU for 0 <= a <= 1 (ReLU: a = 0): FMUL2 + 2 FMNMX per pair
                 const float sl = p.slope;
 #pragma unroll
-                for (int j = 0; j < 32; ++j) f[j] = f[j] > 0.f ? f[j] : f[j] * sl;
-              } else if (p.act == ACT_ELU) {
+                for (int j = 0; j < CW / 2; ++j) {
+                  float t0, t1;
+                  f32x2_scale(t0, t1, f[2 * j], f[2 * j + 1], sl);
+                  f[2 * j] = fmaxf(f[2 * j], t0);
+                  f[2 * j + 1] = fmaxf(f[2 * j + 1], t1);
+                }
+              } else if (ACT == 2) {
+                if (p.act == ACT_PRELU) {
+                  const float sl = p.slope;
 #pragma unroll
-                for (int j = 0; j < 32; ++j) f[j] = f[j] > 0.f ? f[j] : (__expf(f[j]) - 1.f);
-              } else if (p.act == ACT_HARDSWISH) {
+                  for (int j = 0; j < CW; ++j) f[j] = f[j] > 0.f ? f[j] : f[j] * sl;
+                } else if (p.act == ACT_ELU) {
 #pragma unroll
-                for (int j = 0; j < 32; ++j) f[j] = f[j] * fminf(fmaxf(f[j] + 3.f, 0.f), 6.f) * (1.f / 6.f);
+                  for (int j = 0; j < CW; ++j) f[j] = f[j] > 0.f ? f[j] : (__expf(f[j]) - 1.f);
+                } else if (p.act == ACT_HARDSWISH) {
+#pragma unroll
+                  for (int j = 0; j < CW; ++j) f[j] = f[j] * fminf(fmaxf(f[j] + 3.f, 0.f), 6.f) * (1.f / 6.f);
+                }
+              }
+              if (MODE == 3) {
+                // 1x1 head: three dot products over this pixel's 64 channels.  The weights are kernel
+                // parameters, i.e. constant-bank operands of the FFMAs: no shared-memory reads in a kernel
+                // whose shared-memory pipe is the bottleneck.
+#pragma unroll
+                for (int j = 0; j < CW; ++j) {
+                  h0 = fmaf(f[j], p.head_c[half * 32 + q * CW + j], h0);
+                  h1 = fmaf(f[j], p.head_c[64 + half * 32 + q * CW + j], h1);
+                  h2 = fmaf(f[j], p.head_c[128 + half * 32 + q * CW + j], h2);
+                }
+              } else {
+                // this thread's channels -> staging row (64 B per half); 16-byte chunks XOR-swizzled so that
+                // both the row-wise writes and the pixel-wise reads below are bank-conflict free
+#pragma unroll
+                for (int j = 0; j < CW / 8; ++j) {
+                  uint4 o;
+                  o.x = pack_bf16x2(f[8 * j + 0], f[8 * j + 1]);
+                  o.y = pack_bf16x2(f[8 * j + 2], f[8 * j + 3]);
+                  o.z = pack_bf16x2(f[8 * j + 4], f[8 * j + 5]);
+                  o.w = pack_bf16x2(f[8 * j + 6], f[8 * j + 7]);
+                  *reinterpret_cast<uint4*>(stg_w + (((q * (CW / 8) + j) ^ sw_w) << 4)) = o;
+                }
               }
             }
-            if (MODE == 3) {
-              // 1x1 head: three dot products over this pixel's 64 channels, two channels per FFMA2
-              const float2* w0 = reinterpret_cast<const float2*>(head_s + half * 32);
-#pragma unroll
-              for (int j = 0; j < 16; ++j) {
-                const float2 wa = w0[j], wb = w0[32 + j], wc = w0[64 + j];
-                f32x2_fma(h0, g0, f[2 * j], f[2 * j + 1], wa.x, wa.y);
-                f32x2_fma(h1, g1, f[2 * j], f[2 * j + 1], wb.x, wb.y);
-                f32x2_fma(h2, g2, f[2 * j], f[2 * j + 1], wc.x, wc.y);
-              }
-            } else {
-              // this thread's 32 channels (64 B) -> staging row; 16-byte chunks XOR-swizzled so that both
-              // the row-wise writes and the pixel-wise reads below are bank-conflict free
-#pragma unroll
-              for (int j = 0; j < 4; ++j) {
-                uint4 o;
-                o.x = pack_bf16x2(f[8 * j + 0], f[8 * j + 1]);
-                o.y = pack_bf16x2(f[8 * j + 2], f[8 * j + 3]);
-                o.z = pack_bf16x2(f[8 * j + 4], f[8 * j + 5]);
-                o.w = pack_bf16x2(f[8 * j + 6], f[8 * j + 7]);
-                *reinterpret_cast<uint4*>(stg_w + ((j ^ sw_w) << 4)) = o;
-              }
+            if (MODE != 3) {
               __syncwarp();
               // coalesced write-out: 8 pixels x 64 B per warp instruction
               const uint32_t e = extra + half * 32;
@@ -548,7 +554,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         }
         if (quarter == 0) NIND_TRACE(tl, TR_EPI_DONE);
         if (MODE == 3 && hdst) {
-          float o0 = (h0 + g0) + head_s[192], o1 = (h1 + g1) + head_s[193], o2 = (h2 + g2) + head_s[194];
+          float o0 = h0 + p.head_c[192], o1 = h1 + p.head_c[193], o2 = h2 + p.head_c[194];
           if (p.head_sigmoid) {
             o0 = 1.f / (1.f + __expf(-o0));
             o1 = 1.f / (1.f + __expf(-o1));

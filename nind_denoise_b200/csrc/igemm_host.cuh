@@ -246,7 +246,12 @@ inline bool build_igemm(const ConvSpec& s, IgemmLaunch* L, std::string* why) {
   p.slope = s.slope;
   p.bias = s.bias;
   if (s.epi_mode == EPI_HEAD) {
-    p.head_w = s.head_w; p.head_b = s.head_b; p.head_out = s.head_out;
+    p.head_out = s.head_out;
+    if (!s.head_w || !s.head_b) return fail("head needs weights and bias");
+    if (cudaMemcpy(p.head_c, s.head_w, 192 * sizeof(float), cudaMemcpyDeviceToHost) != cudaSuccess ||
+        cudaMemcpy(p.head_c + 192, s.head_b, 3 * sizeof(float), cudaMemcpyDeviceToHost) != cudaSuccess)
+      return fail("cannot read the head weights");
+    p.head_c[195] = 0.f;
     p.h_unpad = s.head_unpad; p.h_size_y = s.head_hy; p.h_size_x = s.head_hx;
     p.h_row = s.head_hx; p.h_plane = (long long)s.head_hy * s.head_hx; p.h_img = 3 * p.h_plane;
     p.head_sigmoid = s.head_sigmoid;
