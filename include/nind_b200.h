@@ -141,7 +141,8 @@ int nind_get_layer_times(nind_net* net, int max_layers, const char** names, floa
 int nind_get_layer_bytes(nind_net* net, int max_layers, double* bytes, int* n_layers);
 
 /* Tuning knobs (affect plans built afterwards): "n_tile_deep" (128|256), "max_ctas",
- * "cta_group" (0 auto | 1 | 2), "fuse_pool" (0|1), "first_c8" (0|1); host pipeline: "host_first" /
+ * "cta_group" (0 auto | 1 | 2), "fuse_pool" (0|1), "first_c8" (0|1), "flat" (-1 auto | 0 off: 1-D tiles on
+ * narrow maps); host pipeline: "host_first" /
  * "host_last" = crops in its first / last step (-1: one grid row). */
 int nind_set_option(nind_net* net, const char* key, int value);
 

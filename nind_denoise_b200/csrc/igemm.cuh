@@ -74,6 +74,12 @@ struct IgemmParams {
   long long o_img, o_row;  // element strides
   int o_pix;
   int d2s_cout;            // EPI_D2S: channels per sub-pixel
+  // Flat mode (narrow maps): tiles are 128 consecutive pixels of the row-major (b, y, x) index space of the
+  // INPUT buffer (pitch = its width), the A box is a 2-D slab of 128 + 2*pitch + 2 pixel rows, and tap
+  // (ky, kx) starts (ky*pitch + kx) rows into it.  No 8-pixel column quantisation; the only waste is the
+  // (taps-1) garbage columns per map row.
+  int flat, flat_pitch;
+  uint32_t tap_pitch16;    // descriptor start-address step per ky, in 16-byte units
   // EPI_STORE only: fused nn.MaxPool2d(2) of the stored tensor (UtNet.py:34,100-103) into a second buffer
   __nv_bfloat16* pool_out; // already offset by halo; null = no pooling
   long long pl_img, pl_row;
@@ -195,7 +201,15 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         for (int kc = 0; kc < p.kchunks; ++kc) {
           mbar_wait(a_empty + 8 * s, ph ^ 1, p.err, 1);
           if (kc == 0) NIND_TRACE(tl, TR_A_ISSUE);
-          if (CG == 2) {
+          if (p.flat) {  // yt is the flat tile index (tiles_x == 1, pairs along "y")
+            if (CG == 2) {
+              if (cg_rank == 0) mbar_arrive_expect_tx(a_full + 8 * s, 2 * p.a_tx_bytes);
+              tma_load_2d_cg2(a_base + s * p.a_stage_bytes, &tmA, mapa_shared(a_full + 8 * s, 0), kc * 64, yt * 128);
+            } else {
+              mbar_arrive_expect_tx(a_full + 8 * s, p.a_tx_bytes);
+              tma_load_2d(a_base + s * p.a_stage_bytes, &tmA, a_full + 8 * s, kc * 64, yt * 128);
+            }
+          } else if (CG == 2) {
             // both CTAs' patches complete on the leader's barrier; only the leader arms it
             if (cg_rank == 0) mbar_arrive_expect_tx(a_full + 8 * s, 2 * p.a_tx_bytes);
             tma_load_3d_cg2(a_base + s * p.a_stage_bytes, &tmA, mapa_shared(a_full + 8 * s, 0), kc * 64,
@@ -253,7 +267,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     // in uniform registers); one elected lane issues tcgen05.mma / tcgen05.commit.
     constexpr uint32_t DESC_HI_B = (1024u >> 4) | (1u << 14) | (2u << 29);
     const uint32_t desc_hi_a = (p.a_sbo >> 4) | (1u << 14) | (2u << 29);
-    const uint32_t pitch16 = (p.a_sbo >> 4);  // one patch row, in 16-byte units
+    const uint32_t pitch16 = p.tap_pitch16;  // one patch row, in 16-byte units
     uint32_t sa_i = 0, pha = 0, sb_i = 0, phb = 0, acc = 0, aph = 0;
     int tl = 0;
     for (int tile = tile0; tile < p.total_tiles; tile += tstep, ++tl) {
@@ -410,23 +424,40 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
               ox < p.h_size_x)
             hdst = p.head_out + b * p.h_img + (long long)oy * p.h_row + ox;
         } else {
-          const int x = xt * IG_TILE_W + sub;
-          const int yf0 = yt * IG_TILE_H + quarter * 4;
-          int b = yf0 / p.hs_in;
-          int y = yf0 - b * p.hs_in;
-          const int xp = xt * IG_TILE_W + (sub & 3) * 2, pit = (sub >> 2) * 2;
+          if (p.flat) {
+            // flat tile: this lane's four pixels are 8 apart in the row-major (b, y, x) index space
+            const int i0 = yt * 128 + quarter * 32 + sub;
 #pragma unroll
-          for (int it = 0; it < 4; ++it) {
-            const bool row_ok = (yf0 + it < p.rows_total) && (y < p.h_valid);
-            vmask |= (uint32_t)(row_ok && (x < p.w_valid)) << it;
-            const long long o = MODE == 2 ? b * p.o_img + (long long)(2 * y) * p.o_row + (long long)(2 * x) * p.o_pix
-                                          : b * p.o_img + (long long)y * p.o_row + (long long)x * p.o_pix;
-            dst[it] = (uint32_t)o + ch * 8;
-            if (MODE == 1 && it == pit) {
-              pdst = (uint32_t)(b * p.pl_img + (long long)(y >> 1) * p.pl_row + (long long)(xp >> 1) * p.pl_pix) + ch * 8;
-              pvalid = row_ok && (xp < p.w_valid);
+            for (int it = 0; it < 4; ++it) {
+              const int i = i0 + it * 8;
+              const int yf = i / p.flat_pitch;
+              const int x = i - yf * p.flat_pitch;
+              const int b = yf / p.hs_in;
+              const int y = yf - b * p.hs_in;
+              vmask |= (uint32_t)((yf < p.rows_total) && (y < p.h_valid) && (x < p.w_valid)) << it;
+              const long long o = MODE == 2 ? b * p.o_img + (long long)(2 * y) * p.o_row + (long long)(2 * x) * p.o_pix
+                                            : b * p.o_img + (long long)y * p.o_row + (long long)x * p.o_pix;
+              dst[it] = (uint32_t)o + ch * 8;
             }
-            if (++y == p.hs_in) { y = 0; ++b; }
+          } else {
+            const int x = xt * IG_TILE_W + sub;
+            const int yf0 = yt * IG_TILE_H + quarter * 4;
+            int b = yf0 / p.hs_in;
+            int y = yf0 - b * p.hs_in;
+            const int xp = xt * IG_TILE_W + (sub & 3) * 2, pit = (sub >> 2) * 2;
+#pragma unroll
+            for (int it = 0; it < 4; ++it) {
+              const bool row_ok = (yf0 + it < p.rows_total) && (y < p.h_valid);
+              vmask |= (uint32_t)(row_ok && (x < p.w_valid)) << it;
+              const long long o = MODE == 2 ? b * p.o_img + (long long)(2 * y) * p.o_row + (long long)(2 * x) * p.o_pix
+                                            : b * p.o_img + (long long)y * p.o_row + (long long)x * p.o_pix;
+              dst[it] = (uint32_t)o + ch * 8;
+              if (MODE == 1 && it == pit) {
+                pdst = (uint32_t)(b * p.pl_img + (long long)(y >> 1) * p.pl_row + (long long)(xp >> 1) * p.pl_pix) + ch * 8;
+                pvalid = row_ok && (xp < p.w_valid);
+              }
+              if (++y == p.hs_in) { y = 0; ++b; }
+            }
           }
         }
         // number of 64-column groups of this tile that hold real output columns

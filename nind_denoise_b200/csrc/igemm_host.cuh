@@ -36,6 +36,7 @@ struct ConvSpec {
   float* head_out = nullptr;  // [B][3][hy][hx] fp32
   int head_unpad = 0, head_hy = 0, head_hx = 0, head_sigmoid = 0;
   // tuning
+  int flat = -1;  // flat (1-D) tiles for narrow maps: -1 auto, 0 off, 1 force (error if illegal), 2 wherever legal
   int n_tile = 0;     // 0 = auto
   int cg = 0;         // CTAs per tile group: 0 = auto, 1, or 2 (cta_group::2 pair)
   bool c8 = false;    // first layer over the 8-channel padded-crop tensor (C_in = 3 as hi/lo bf16)
@@ -159,12 +160,32 @@ inline bool build_igemm(const ConvSpec& s, IgemmLaunch* L, std::string* why) {
   }
   if (cg != 1 && cg != 2) return fail("cg must be 1 or 2");
   L->cg = cg;
+  // Flat tiles (128 consecutive pixels of the input's row-major index space) when the 8-pixel tile columns
+  // would waste more than the (taps-1) garbage columns per row do; the 2-D box is limited to 256 rows.
+  bool flat = false;
+  {
+    const int box_rows = s.taps == 9 ? 130 + 2 * s.in.ws : 128;
+    const double eff_tile = (double)p.w_valid / (IG_TILE_W * tiles_x_real), eff_flat = (double)p.w_valid / s.in.ws;
+    const bool can = !s.c8 && s.epi_mode != EPI_HEAD && !s.pool.ptr && box_rows <= 256;
+    if (s.flat == 1 && !can) return fail("flat tiles need a narrow map (<= 63 px), no fused pool / head, not the first layer");
+    flat = can && (s.flat >= 1 || (s.flat == -1 && eff_flat > eff_tile + 0.02));
+  }
   // Pair the two tiles of a CTA pair along x when that wastes nothing (even tile count), else along y:
   // rows are batch-flattened (hundreds of tile rows), so a padded odd row count costs < 1 %.
   const int tiles_y_real = (p.rows_total - shrink + IG_TILE_H - 1) / IG_TILE_H;
-  p.pair_y = (cg == 2 && (tiles_x_real & 1)) ? 1 : 0;
-  p.tiles_x = p.pair_y ? tiles_x_real : (tiles_x_real + cg - 1) / cg;
-  p.tiles_y = p.pair_y ? (tiles_y_real + 1) / 2 : tiles_y_real;
+  if (flat) {
+    const long long n_flat = (long long)p.rows_total * s.in.ws;
+    const int tiles = (int)((n_flat + 127) / 128);
+    p.flat = 1;
+    p.flat_pitch = s.in.ws;
+    p.pair_y = cg == 2 ? 1 : 0;
+    p.tiles_x = 1;
+    p.tiles_y = (tiles + cg - 1) / cg;
+  } else {
+    p.pair_y = (cg == 2 && (tiles_x_real & 1)) ? 1 : 0;
+    p.tiles_x = p.pair_y ? tiles_x_real : (tiles_x_real + cg - 1) / cg;
+    p.tiles_y = p.pair_y ? (tiles_y_real + 1) / 2 : tiles_y_real;
+  }
   p.tiles_n = (s.n_total + n_tile - 1) / n_tile;
   p.total_tiles = p.tiles_x * p.tiles_y * p.tiles_n;
   p.kchunks = s.c8 ? 1 : s.cin / 64;
@@ -174,7 +195,11 @@ inline bool build_igemm(const ConvSpec& s, IgemmLaunch* L, std::string* why) {
   // nine tap views are descriptor offsets (verified on B200: the UMMA 128B-swizzle XOR is applied to
   // absolute shared-memory address bits, so a start address moved by whole 128-byte rows is legal).
   uint32_t boxA[3];
-  if (s.taps == 1) {
+  if (flat) {
+    boxA[0] = 64; boxA[1] = s.taps == 9 ? 130 + 2 * s.in.ws : 128; boxA[2] = 1;
+    p.a_tx_bytes = boxA[1] * 128; p.a_stage_bytes = (p.a_tx_bytes + 1023) & ~1023; p.a_sbo = 1024;
+    p.tap_pitch16 = (uint32_t)s.in.ws * 8;
+  } else if (s.taps == 1) {
     boxA[0] = 64; boxA[1] = 8; boxA[2] = 16;
     p.a_tx_bytes = 16384; p.a_stage_bytes = 16384; p.a_sbo = 1024;
   } else if (s.c8) {
@@ -184,6 +209,8 @@ inline bool build_igemm(const ConvSpec& s, IgemmLaunch* L, std::string* why) {
     boxA[0] = 64; boxA[1] = 10; boxA[2] = 18;
     p.a_tx_bytes = 10 * 18 * 128; p.a_stage_bytes = 23552; p.a_sbo = 1280;
   }
+
+  if (!flat) p.tap_pitch16 = p.a_sbo >> 4;
 
   // pipeline depth / weights-stationary decision
   const int tps = s.c8 ? 1 : ((s.taps == 9 && n_tile <= 128) ? 3 : 1);  // taps per weight stage
@@ -223,6 +250,10 @@ inline bool build_igemm(const ConvSpec& s, IgemmLaunch* L, std::string* why) {
       const uint64_t stridesA[1] = {(uint64_t)s.in.ws * 16};
       const uint32_t boxA2[2] = {80, 18};
       if (!encode_tmap_bf16(&L->tmA, s.in.ptr, 2, dimsA, stridesA, boxA2, why, false)) return false;
+    } else if (flat) {  // [all pixels of the buffer][channels]
+      const uint64_t dimsA[2] = {(uint64_t)s.cin, (uint64_t)p.rows_total * s.in.ws};
+      const uint64_t stridesA[1] = {(uint64_t)s.in.c * 2};
+      if (!encode_tmap_bf16(&L->tmA, s.in.ptr + s.in_coff, 2, dimsA, stridesA, boxA, why)) return false;
     } else if (!encode_tmap_bf16(&L->tmA, s.in.ptr + s.in_coff, 3, dims, strides, boxA, why)) {
       return false;
     }

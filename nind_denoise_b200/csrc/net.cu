@@ -130,6 +130,7 @@ struct nind_net {
   cudaStream_t s_in = nullptr, s_comp = nullptr, s_out = nullptr;
   std::vector<cudaEvent_t> ev_in, ev_done;
   cudaEvent_t ev_join = nullptr;
+  int flat = -1;
   int host_first = -1, host_last = -1;  // crops in the first / last pipeline step (-1: one grid row)
   // options
   int n_tile_deep = 256, max_ctas = 0, cg = 0, fuse_pool = 1;
@@ -467,6 +468,7 @@ struct PlanBuilder {
     s.c8 = c8;
     s.max_ctas = net->max_ctas;
     s.cg = net->cg;
+    s.flat = net->flat == 1 ? 2 : net->flat;  // 1 = on every layer where it is legal
     if (L.n_total >= 256) s.n_tile = net->n_tile_deep;
     Step st;
     st.kind = STEP_IGEMM; st.name = name;
@@ -853,6 +855,8 @@ int nind_set_option(nind_net* net, const char* key, int value) {
     net->fuse_pool = value ? 1 : 0;
   } else if (k == "first_c8") {
     net->first_c8 = value ? 1 : 0;
+  } else if (k == "flat") {  // flat (1-D) tiles on narrow maps: -1 auto, 0 off, 1 wherever legal
+    net->flat = value;
   } else if (k == "host_first") {  // crops in the first step of the host pipeline (-1: one grid row)
     net->host_first = value;
     return 0;

@@ -291,6 +291,7 @@ static int run_conv(int argc, char** argv) {
   const int ws = argc > 12 ? atoi(argv[12]) : -1;
   const int ctas = argc > 13 ? atoi(argv[13]) : 0;
   const int cg = argc > 14 ? atoi(argv[14]) : 0;
+  const int flat = argc > 15 ? atoi(argv[15]) : -1;
   const int tw = taps == 9 ? 3 : 1;
   const int Hv = Hs - (tw - 1), Wv = Ws - (tw - 1);
   const bool c8 = cin == 8;              // first-layer mode: 8-channel input, no-swizzle descriptors
@@ -342,7 +343,7 @@ static int run_conv(int argc, char** argv) {
   }
   s.in_coff = coff; s.cin = cin; s.taps = taps; s.w = c8 ? dw8 : dw; s.n_total = n_total; s.bias = dbias;
   s.act = act; s.slope = slope; s.epi_mode = epi; (void)a_mode; (void)bo_mode;
-  s.n_tile = n_tile; s.force_ws = ws; s.max_ctas = ctas; s.cg = cg;
+  s.n_tile = n_tile; s.force_ws = ws; s.max_ctas = ctas; s.cg = cg; s.flat = flat;
   const int halo = 2, ocoff = 32;
   int Ho = 0, Wo = 0, Co = 0;
   const int unpad = 1;
@@ -376,7 +377,7 @@ static int run_conv(int argc, char** argv) {
   if (!build_igemm(s, &L, &why)) { printf("build_igemm failed: %s\n", why.c_str()); return 2; }
   printf("CONV taps=%d cin=%d N=%d B=%d %dx%d a_mode=%d bo=%d epi=%d | n_tile=%d tiles=%d (x%d y%d n%d) grid=%d sa=%d sb=%d ws=%d smem=%zu\n",
          taps, cin, n_total, B, Hs, Ws, a_mode, bo_mode, epi, L.n_tile, L.p.total_tiles, L.p.tiles_x,
-         L.p.tiles_y, L.p.tiles_n, L.grid, L.p.sa, L.p.sb, L.p.ws, L.smem); printf("  tps=%d cg=%d\n", L.tps, L.cg);
+         L.p.tiles_y, L.p.tiles_n, L.grid, L.p.sa, L.p.sb, L.p.ws, L.smem); printf("  tps=%d cg=%d flat=%d\n", L.tps, L.cg, L.p.flat);
 
   naive_conv_kernel<<<1024, 256>>>(din, B, Hs, Ws, Cbuf, coff, cin, dw, taps, n_total, dbias, act, slope, dref);
   CK(cudaGetLastError());
