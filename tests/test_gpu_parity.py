@@ -246,15 +246,16 @@ def test_kernel_launch_counter(utnet):
 
 
 def test_kernel_variants_agree():
-    """Fused vs separate max-pool and CTA-pair (cta_group::2) vs single-CTA tiles compute the same
-    function: identical bf16 pooling, and fp32 accumulation orders that differ only inside the MMA."""
+    """Fused vs separate max-pool, CTA-pair (cta_group::2) vs single-CTA tiles and flat vs 16x8 tiles compute
+    the same function: identical bf16 pooling, and fp32 accumulation orders that differ only inside the MMA."""
     sd = on.init_state_dict("UtNet", seed=0)
     torch.manual_seed(6)
     x = torch.rand(2, 3, 120, 136, device=dev())
     outs = {}
     for name, opts in (("default", {}), ("unfused_pool", {"fuse_pool": 0}), ("im2col_first", {"first_c8": 0}),
                        ("cta1", {"cta_group": 1}),
-                       ("cta2", {"cta_group": 2}), ("n128", {"n_tile_deep": 128})):
+                       ("cta2", {"cta_group": 2}), ("n128", {"n_tile_deep": 128}),
+                       ("flat_off", {"flat": 0}), ("flat_all", {"flat": 1})):
         m = nb.UtNet().to(dev()).eval()
         m.load_state_dict(sd)
         for k, v in opts.items():
@@ -268,6 +269,9 @@ def test_kernel_variants_agree():
     assert d <= 3e-4
     for k in ("cta1", "cta2", "n128"):
         assert np.abs(outs[k] - outs["default"]).max() <= 2e-5, k
+    # flat (1-D) tiles only change which pixels share a tile, not any pixel's summation order
+    assert np.array_equal(outs["flat_off"], outs["default"])
+    assert np.array_equal(outs["flat_all"], outs["default"])
 
 
 def test_cli_shim_roundtrip(tmp_path, golden_networks):
