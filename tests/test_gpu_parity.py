@@ -5,6 +5,7 @@ max abs error <= 2e-2 and PSNR difference <= 0.05 dB versus the fp32 reference o
 default-initialised weights give a tiny output range (sigma_out ~ 0.007) every pixel test
 also bounds the error RELATIVE to the output's standard deviation."""
 import math
+import os
 
 import numpy as np
 import pytest
@@ -419,3 +420,36 @@ def test_host_range_pipeline_composes_to_the_whole_image(utnet, world):
             out[:, o0:lo] = acc.cpu()
     assert not torch.isnan(out).any()
     assert float((out - ref).abs().max()) <= 1e-6
+
+
+@pytest.mark.gpu
+def test_dir_cli_matches_single_image_path(tmp_path):
+    """nind_denoise_b200.dir_cli (denoise_dir.py:76-103 without the per-image subprocess): a
+    directory streamed through the async host entry gives, file by file, what the single-image CLI writes."""
+    import cv2
+    from nind_denoise_b200 import cli, dir_cli
+
+    rng = np.random.default_rng(31)
+    noisy = tmp_path / "noisy"
+    noisy.mkdir()
+    shapes = {"a.tif": (150, 170), "b.png": (131, 200), "c.tif": (150, 170)}
+    for name, (h, w) in shapes.items():
+        img16 = (rng.random((h, w, 3)) * 65535).astype(np.uint16)
+        cv2.imwrite(str(noisy / name), img16)
+    clean = str(noisy / "clean.tif")
+    cv2.imwrite(clean, (rng.random((150, 170, 3)) * 65535).astype(np.uint16))
+    model_path = str(tmp_path / "generator_1.pt")
+    torch.save(on.init_state_dict("UtNet", seed=0), model_path)
+    out_dir = tmp_path / "out"
+    rc = dir_cli.main(["--noisy_dir", str(noisy), "--result_dir", str(out_dir), "--network", "UtNet",
+                       "--model_path", model_path, "--cs", "120", "--ucs", "96", "--baseline", clean])
+    assert rc == 0
+    assert sorted(os.listdir(out_dir)) == sorted(shapes)
+    for name in shapes:
+        single = str(tmp_path / ("single_" + name))
+        cli.main(["--network", "UtNet", "--model_path", model_path, "--input", str(noisy / name), "--output", single,
+                  "--cs", "120", "--ucs", "96"])
+        a = cv2.imread(str(out_dir / name), cv2.IMREAD_UNCHANGED)
+        b = cv2.imread(single, cv2.IMREAD_UNCHANGED)
+        assert a.dtype == np.uint16 and a.shape == b.shape, name
+        assert np.abs(a.astype(np.int64) - b.astype(np.int64)).max() <= 1, name   # same kernels, same batches

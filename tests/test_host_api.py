@@ -140,3 +140,18 @@ def test_compute_entry_points_fail_loudly_without_a_gpu():
     assert b"cuda" in _capi.lib().nind_last_error().lower() or b"CUDA" in _capi.lib().nind_last_error()
     with pytest.raises(_capi.NindError):
         _capi.device_info()
+
+
+def test_dir_cli_file_conventions(tmp_path):
+    """dir_cli: listing, output naming (denoise_dir.py:84-85) and scoring helpers need no GPU."""
+    from nind_denoise_b200 import dir_cli
+    for n in ("b.png", "a.tif", "c.jpg", "notes.txt", "clean.tif"):
+        (tmp_path / n).write_bytes(b"")
+    ins = dir_cli.list_images(str(tmp_path), skip=[str(tmp_path / "clean.tif")])
+    assert [os.path.basename(p) for p in ins] == ["a.tif", "b.png", "c.jpg"]
+    assert dir_cli.out_path_for(ins[2], "/out") == "/out/c.jpg.tif"
+    assert dir_cli.out_path_for(ins[0], "/out") == "/out/a.tif"
+    a = torch.rand(3, 8, 9)
+    assert dir_cli.losses(a, a)["mse"] == 0.0
+    l = dir_cli.losses(a, (a + 0.1))
+    assert abs(l["psnr"] - (-10 * np.log10(l["mse"]))) < 1e-4
