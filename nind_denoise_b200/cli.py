@@ -130,8 +130,6 @@ def main(argv=None) -> int:
     ap.add_argument("--models_dpath")
     args, _ = ap.parse_known_args(argv)
     autodetect_network_cs_ucs(args)
-    if args.whole_image:
-        sys.exit("--whole_image is not part of the tiled hot path of nind_denoise_b200")
     if args.max_subpixels is not None and 3 * args.cs * args.cs > args.max_subpixels:
         sys.exit(f"denoise_image.py: crop of 3x{args.cs}x{args.cs} > {args.max_subpixels=} for {args.input=}; aborting")
     if not torch.cuda.is_available():
@@ -148,8 +146,13 @@ def main(argv=None) -> int:
         args.output = os.path.join(root, "test", "denoised_images", f"{os.path.basename(args.input)}_{leaf}.tif")
     img = torch.from_numpy(img_path_to_np_flt(args.input))
     start = time.time()
-    out = nb.denoise_tiled_host(img.pin_memory(), model, args.cs, args.ucs, args.overlap,
-                                batch=args.batch_size or None)
+    if args.whole_image:  # one forward over the mirror-padded image (denoise_image.py:91-97,110-128)
+        if not args.pad:
+            print("OneImageDS: Warning: you should really consider (pad>0)")
+        out = nb.denoise_whole_image(img.to(device), model, args.pad or 0).cpu()
+    else:
+        out = nb.denoise_tiled_host(img.pin_memory(), model, args.cs, args.ucs, args.overlap,
+                                    batch=args.batch_size or None)
     tensor_to_imgfile(out, args.output)
     print(f"Wrote denoised image to {args.output}")
     print("Elapsed time: " + str(time.time() - start) + " seconds")

@@ -90,6 +90,39 @@ def denoise_tiled(img: torch.Tensor, model, cs: Optional[int] = None, ucs: Optio
     return out
 
 
+def pad_whole_image(img: torch.Tensor, pad: int) -> torch.Tensor:
+    """The reference's whole-image input (denoise_image.py:110-126): the image centred in a zero canvas
+    ``pad`` larger on every side, the four sides filled with the edge-inclusive mirror of the image, the
+    corners left at zero.  (The reference allocates the canvas with width and height swapped, :113, so it
+    only runs on square images; this is the layout it builds for those.)"""
+    _, H, W = img.shape
+    if pad < 0 or pad > min(H, W):
+        raise ValueError(f"pad must be in [0, {min(H, W)}], got {pad}")
+    ret = torch.zeros((3, H + 2 * pad, W + 2 * pad), dtype=img.dtype, device=img.device)
+    ret[:, pad:H + pad, pad:W + pad] = img
+    if pad:
+        ret[:, pad:H + pad, :pad] = img[:, :, :pad].flip(2)
+        ret[:, pad:H + pad, W + pad:] = img[:, :, W - pad:].flip(2)
+        ret[:, :pad, pad:W + pad] = img[:, :pad, :].flip(1)
+        ret[:, H + pad:, pad:W + pad] = img[:, H - pad:, :].flip(1)
+    return ret
+
+
+def denoise_whole_image(img: torch.Tensor, model, pad: int = 0) -> torch.Tensor:
+    """``--whole_image`` mode of the reference script (denoise_image.py:91-97,110-128,255-256): ONE forward
+    over the mirror-padded image, trimmed back to [3,H,W].  For small images; the padded size must be one
+    the network accepts (UtNet: 16a+56 — the reference fails inside torch.cat otherwise, this raises)."""
+    if img.dim() != 3 or img.shape[0] != 3:
+        raise ValueError(f"expected a [3,H,W] image, got {tuple(img.shape)}")
+    if not img.is_cuda:
+        raise RuntimeError("denoise_whole_image (nind_denoise_b200): image must be a CUDA tensor; there is no CPU path")
+    _, H, W = img.shape
+    x = pad_whole_image(img.detach().float(), int(pad or 0))
+    y = model(x.unsqueeze(0))[0]
+    pad = int(pad or 0)
+    return y[:, pad:H + pad, pad:W + pad].contiguous()
+
+
 def denoise_tiled_host(img_host: torch.Tensor, model, cs: int, ucs: int, ol: int = DEFAULT_OVERLAP,
                        batch: Optional[int] = None, out: Optional[torch.Tensor] = None) -> torch.Tensor:
     """Host-buffer variant (the call the reference's script would make): H2D + all crops + D2H inside

@@ -146,3 +146,18 @@ def denoise_tiled(img: np.ndarray, model_fn, cs: int, ucs: int, ol: int, crop_ra
     network: CHW float32 crop [3,cs,cs] -> [3,cs,cs]."""
     g = crop_grid(img.shape[2], img.shape[1], cs, ucs, ol)
     return stitch(lambda i: model_fn(gather_crop(img, g, i)), g, crop_range)
+
+
+def whole_image_input(img: np.ndarray, pad: int) -> np.ndarray:
+    """The whole-image branch of OneImageDS.__getitem__ (denoise_image.py:110-126): image centred in a zero
+    canvas, four sides mirrored (edge pixel included), corners left zero.  The reference allocates the canvas
+    as (3, W+2p, H+2p) (:113), which only works for square images; this is the (3, H+2p, W+2p) layout."""
+    _, H, W = img.shape
+    ret = np.zeros((3, H + 2 * pad, W + 2 * pad), dtype=np.float32)
+    ret[:, pad:H + pad, pad:W + pad] = img
+    if pad:
+        ret[:, pad:-pad, :pad] = np.flip(img[:, :, :pad], axis=2)
+        ret[:, pad:-pad, W + pad:] = np.flip(img[:, :, W - pad:], axis=2)
+        ret[:, :pad, pad:-pad] = np.flip(img[:, :pad, :], axis=1)
+        ret[:, H + pad:, pad:-pad] = np.flip(img[:, H - pad:, :], axis=1)
+    return ret

@@ -117,8 +117,38 @@ TABLE_ONLY = [(6000, 4000, 504, 480, 6), (6000, 4000, 248, 224, 6), (6000, 4000,
               (4000, 6000, 248, 224, 32)]
 
 
+def whole_image_golden() -> int:
+    """tests/golden/whole_image.npz: the reference's --whole_image input for a square image (its canvas has
+    width and height swapped, so square is all it can do) next to oracle.geometry.whole_image_input."""
+    cwd = os.getcwd()
+    os.chdir(REF)
+    try:
+        import denoise_image as di
+    finally:
+        os.chdir(cwd)
+    rng = np.random.default_rng(5)
+    out, bad = {}, 0
+    for k, (n, pad) in enumerate(((40, 8), (33, 0), (24, 24))):
+        img = rng.random((3, n, n), dtype=np.float32)
+        ds = di.OneImageDS.__new__(di.OneImageDS)
+        ds.inimg, ds.width, ds.height = img, n, n
+        ds.whole_image, ds.pad, ds.size = True, pad, 1
+        crop, ud, us = ds[0]
+        crop = crop.numpy() if hasattr(crop, "numpy") else np.asarray(crop)
+        mine = og.whole_image_input(img, pad)
+        if not np.array_equal(mine, crop) or tuple(int(v) for v in ud) != (pad, pad, n + pad, n + pad):
+            print(f"MISMATCH whole-image input n={n} pad={pad}")
+            bad += 1
+        out[f"w{k}_img"], out[f"w{k}_pad"], out[f"w{k}_input"] = img, np.array([pad], dtype=np.int32), crop
+    np.savez_compressed(os.path.join(OUT, "whole_image.npz"), **out)
+    print("whole_image.npz written,", "OK" if not bad else f"{bad} MISMATCHES")
+    return bad
+
+
 def main() -> int:
-    bad = 0
+    if "--whole-image-only" in sys.argv:
+        return whole_image_golden()
+    bad = whole_image_golden()
     rng = np.random.default_rng(0)
     # ------------------------------------------------------------------ geometry
     geo = {}

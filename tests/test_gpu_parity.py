@@ -453,3 +453,20 @@ def test_dir_cli_matches_single_image_path(tmp_path):
         b = cv2.imread(single, cv2.IMREAD_UNCHANGED)
         assert a.dtype == np.uint16 and a.shape == b.shape, name
         assert np.abs(a.astype(np.int64) - b.astype(np.int64)).max() <= 1, name   # same kernels, same batches
+
+
+@pytest.mark.gpu
+def test_whole_image_mode(utnet):
+    """--whole_image (denoise_image.py:91-97,110-128,255-256): one forward over the mirror-padded image."""
+    sd = on.init_state_dict("UtNet", seed=0)
+    rng = np.random.default_rng(8)
+    for (h, w, pad) in ((104, 136, 8), (120, 120, 0)):
+        img = rng.random((3, h, w), dtype=np.float32)
+        got = nb.denoise_whole_image(torch.from_numpy(img).to(dev()), utnet, pad).cpu().numpy()
+        x = torch.from_numpy(og.whole_image_input(img, pad)).unsqueeze(0)
+        with torch.no_grad():
+            ref = on.utnet_forward(sd, x)[0].numpy()[:, pad:h + pad, pad:w + pad]
+        assert got.shape == (3, h, w)
+        check_pixels(got, ref, f"whole image {h}x{w} pad {pad}")
+    with pytest.raises(Exception):   # padded size 100+16 is not a legal UtNet size
+        nb.denoise_whole_image(torch.zeros(3, 100, 100, device=dev()), utnet, 8)

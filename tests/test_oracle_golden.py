@@ -1,5 +1,7 @@
 """CPU: the oracle restatement against the golden vectors produced by the reference itself
 (oracle/make_golden.py).  These pin the oracle; the GPU parity tests then compare against the oracle."""
+import os
+
 import numpy as np
 import torch
 
@@ -106,3 +108,19 @@ def test_tiled_utnet_golden(golden_networks):
 def test_flops_closed_form():
     for cs, g in [(120, 14.22357248), (248, 73.974119936), (504, 338.00254208), (1016, 1444.168695296)]:
         assert abs(on.utnet_flops(cs) / 1e9 - g) < 1e-6
+
+
+def test_whole_image_input_matches_reference_golden():
+    """oracle.geometry.whole_image_input == the reference's OneImageDS whole-image branch (vectors generated
+    by oracle/make_golden.py from the reference itself), and the host layer's torch version == the oracle on
+    non-square images too."""
+    import nind_denoise_b200 as nb
+    G = np.load(os.path.join(os.path.dirname(__file__), "golden", "whole_image.npz"))
+    for k in range(3):
+        img, pad = G[f"w{k}_img"], int(G[f"w{k}_pad"][0])
+        assert np.array_equal(og.whole_image_input(img, pad), G[f"w{k}_input"])
+        assert np.array_equal(nb.pad_whole_image(torch.from_numpy(img), pad).numpy(), G[f"w{k}_input"])
+    rng = np.random.default_rng(2)
+    for (h, w, pad) in ((20, 31, 5), (17, 9, 9), (12, 40, 0)):
+        img = rng.random((3, h, w), dtype=np.float32)
+        assert np.array_equal(nb.pad_whole_image(torch.from_numpy(img), pad).numpy(), og.whole_image_input(img, pad))
