@@ -1026,6 +1026,7 @@ static int enqueue_host_range(nind_net* net, const float* img_chw_host, float* o
   GridGeom g;
   int rc;
   if ((rc = check_range(width, height, cs, ucs, ol, cb, ce, &g))) return rc;
+  if (d2h_y0 < 0 || d2h_y1 > height || d2h_y0 > d2h_y1) return fail(NIND_E_INVALID, "illegal download row range");
   const size_t plane = (size_t)height * width;
   const size_t bytes = 3 * plane * sizeof(float);
   nind_net::HostSlot& S = net->slots[net->host_seq++ & 1];
