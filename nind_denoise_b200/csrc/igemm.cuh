@@ -38,6 +38,11 @@ constexpr int IG_BAR_BYTES = 2048;     // mbarriers + TMEM base slot
 #ifndef NIND_SETS64
 #define NIND_SETS64 4
 #endif
+// EXPERIMENTAL pixel-pair mode for the C_out = 64 3x3 layers (see the comment above igemm_kernel): compiled only
+// with -DNIND_PAIR_MODE=1.  With the default 0 every line it touches is the round-1 code that was measured.
+#ifndef NIND_PAIR_MODE
+#define NIND_PAIR_MODE 0
+#endif
 #ifndef NIND_EPI_X16
 #define NIND_EPI_X16 1
 #endif
@@ -121,10 +126,25 @@ __host__ __device__ inline size_t igemm_smem_bytes(int n_tile, int tps, int cg, 
 // WITHOUT swizzle, and one K=16 MMA covers two taps x 8 channels through the no-swizzle descriptor's
 // leading-dimension offset (LBO = distance between the two taps' pixels, SBO = one patch row); five MMAs
 // per tile (the tenth half-K has zero weights).  Descriptor semantics verified by `tools/probe desc0`.
+#if NIND_PAIR_MODE
+// PM ("pixel pair", EXPERIMENTAL, off by default, not yet validated on hardware): a C_out = 64 3x3 layer as an
+// N = 128 GEMM over the NHWC input viewed as [rows, W/2, 2C]: GEMM row = a pair of x-adjacent pixels, GEMM
+// columns = (pixel of the pair a, c_out).  Output pixel 2P+a reads input pixels 2P+a .. 2P+a+2 = pair P+j,
+// pixel e with kx = 2j + e - a.  Per 64-channel chunk of input pixel e and kernel row ky this is one N = 128
+// MMA (pair tap j = 1-e: both output pixels) and one N = 64 MMA (j = e: only output pixel a = e, written to
+// its half of the accumulator) — the same FLOPs as the 3x3 form, but 12 instead of 18 A-operand fetches per
+// 256 output pixels, which is what bounds the N_TILE = 64 kernels (tests/test_pair_reformulation.py has
+// the algebra).  Weights are resident; tools/probe `pair` checks it against the naive convolution.
+template <int N_TILE, int TPS, int CG, bool C8 = false, bool PM = false>
+#else
 template <int N_TILE, int TPS, int CG, bool C8 = false>
+#endif
 __global__ void __launch_bounds__(ig_threads(N_TILE), 1)
 igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
              const IgemmParams p) {
+#if NIND_PAIR_MODE
+  static_assert(!PM || (N_TILE == 128 && CG == 2 && TPS == 1 && !C8), "pair mode is N_TILE 128 on CTA pairs");
+#endif
   extern __shared__ uint8_t smem_raw[];
   constexpr uint32_t B_ROWS = N_TILE / CG;           // weight rows held by this CTA
   constexpr uint32_t B_TAP_BYTES = B_ROWS * 128;
@@ -236,7 +256,18 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         mbar_arrive_expect_tx(b_full, 10240);
         tma_load_3d(b_base, &tmB, b_full, 0, 0, 0);
       }
+#if NIND_PAIR_MODE
+      if (PM) {  // resident weights: per (chunk, ky) one block of 64 (N=128 MMA) + 32 (N=64 MMA) rows per CTA
+        const int blocks = p.kchunks * 3;
+        if (cg_rank == 0) mbar_arrive_expect_tx(b_full, 2u * blocks * 12288u);
+        const uint32_t bar = mapa_shared(b_full, 0);
+        for (int g = 0; g < blocks; ++g)
+          tma_load_2d_cg2(b_base + g * 12288, &tmB, bar, 0, ((int)cg_rank * blocks + g) * 96);
+      }
+      for (int tile = tile0; tile < p.total_tiles && !C8 && !PM; tile += tstep, ++tl) {
+#else
       for (int tile = tile0; tile < p.total_tiles && !C8; tile += tstep, ++tl) {
+#endif
         if (p.ws && tl > 0) break;
         const int nt = tile / tiles_xy;
         for (int kc = 0; kc < p.kchunks; ++kc) {
@@ -300,7 +331,44 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         __syncwarp();
         if (++sa_i == (uint32_t)p.sa) { sa_i = 0; pha ^= 1; }
       }
+#if NIND_PAIR_MODE
+      if (PM) {
+        constexpr uint32_t IDESC64 = umma_idesc_bf16(256, 64);
+        const int half_chunks = p.kchunks >> 1;
+        for (int kc = 0; kc < p.kchunks; ++kc) {
+          mbar_wait(a_full + 8 * sa_i, pha, p.err, 4);
+          if (kc == 0) NIND_TRACE(tl, TR_MMA_AFULL);
+          if (tl == 0 && kc == 0) mbar_wait(b_full, 0, p.err, 5);
+          tc_fence_after();
+          const uint32_t e = kc >= half_chunks ? 1u : 0u;  // which pixel of the input pair this chunk holds
+          const uint32_t a_lo0 = (((a_base + sa_i * p.a_stage_bytes) >> 4) & 0x3FFF) | (1u << 16);
+          if (elect_one_sync()) {
+#pragma unroll
+            for (uint32_t ky = 0; ky < 3; ++ky) {
+              const uint32_t b_blk = (((b_base + (uint32_t)(kc * 3 + ky) * 12288u) >> 4) & 0x3FFF) | (1u << 16);
+              const uint32_t a128 = a_lo0 + (ky * 9 + (1 - e)) * 8;  // pair tap j = 1-e: both output pixels
+              const uint32_t a64 = a_lo0 + (ky * 9 + e) * 8;         // pair tap j = e: output pixel a = e only
+#pragma unroll
+              for (uint32_t k = 0; k < 4; ++k) {
+                umma_bf16_lohi_cg2(d, a128 + 2 * k, desc_hi_a, b_blk + 2 * k, DESC_HI_B, IDESC, accum);
+                accum = 1;
+              }
+#pragma unroll
+              for (uint32_t k = 0; k < 4; ++k)
+                umma_bf16_lohi_cg2(d + e * 64, a64 + 2 * k, desc_hi_a, b_blk + (8192u >> 4) + 2 * k, DESC_HI_B, IDESC64,
+                                   1u);
+            }
+            umma_commit_cg2(a_empty + 8 * sa_i);
+          }
+          __syncwarp();
+          accum = 1;
+          if (++sa_i == (uint32_t)p.sa) { sa_i = 0; pha ^= 1; }
+        }
+      }
+      for (int kc = 0; kc < p.kchunks && !C8 && !PM; ++kc) {
+#else
       for (int kc = 0; kc < p.kchunks && !C8; ++kc) {
+#endif
         mbar_wait(a_full + 8 * sa_i, pha, p.err, 4);
         if (kc == 0) NIND_TRACE(tl, TR_MMA_AFULL);
         const uint32_t a_lo0 = (((a_base + sa_i * p.a_stage_bytes) >> 4) & 0x3FFF) | (1u << 16);
@@ -400,7 +468,12 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
           for (int i = etid; i < N_TILE; i += 128) {
             const int n = nt * N_TILE + i;
             float bv = 0.f;
+#if NIND_PAIR_MODE
+            if (PM) bv = __ldg(p.bias + (i & 63));  // columns = (pixel of the pair, c_out)
+            else if (n < p.n_total) bv = __ldg(p.bias + (MODE == 2 ? n % p.d2s_cout : n));
+#else
             if (n < p.n_total) bv = __ldg(p.bias + (MODE == 2 ? n % p.d2s_cout : n));
+#endif
             bias_s[bsel * 256 + i] = bv;
           }
           asm volatile("bar.sync %0, 128;" ::"r"(eset + 1) : "memory");
@@ -412,17 +485,37 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         uint32_t vmask = 0;         //            which of them exist
         uint32_t pdst = 0;
         bool pvalid = false;        // MODE 1: pooled pixel
+#if NIND_PAIR_MODE
+        uint32_t pdst1 = 0, pvmask = 0;  // MODE 1, pair mode: second pooled row of this lane; validity bits
+        uint4 pkeep[2][2];          // MODE 1, pair mode: vertical maxima of the pair's first pixel [half][row pair]
+#endif
         float* hdst = nullptr;      // MODE 3: this thread's output pixel (nullptr: none)
+#if NIND_PAIR_MODE
+        float* hdst1 = nullptr;     //         pair mode: the second pixel of this thread's pair
+#endif
         if (MODE == 3) {
           const int row = quarter * 32 + lane;
           const int yflat = yt * IG_TILE_H + (row >> 3);
+#if NIND_PAIR_MODE
+          const int x = (xt * IG_TILE_W + (row & 7)) * (PM ? 2 : 1);
+#else
           const int x = xt * IG_TILE_W + (row & 7);
+#endif
           const int b = yflat / p.hs_in;
           const int y = yflat - b * p.hs_in;
           const int oy = y - p.h_unpad, ox = x - p.h_unpad;
+#if NIND_PAIR_MODE
+          const bool row_ok = (yflat < p.rows_total) && (y < p.h_valid) && oy >= 0 && oy < p.h_size_y;
+          if (row_ok && (x < p.w_valid) && ox >= 0 && ox < p.h_size_x)
+#else
           if ((yflat < p.rows_total) && (y < p.h_valid) && (x < p.w_valid) && oy >= 0 && ox >= 0 && oy < p.h_size_y &&
               ox < p.h_size_x)
+#endif
             hdst = p.head_out + b * p.h_img + (long long)oy * p.h_row + ox;
+#if NIND_PAIR_MODE
+          if (PM && row_ok && (x + 1 < p.w_valid) && ox + 1 >= 0 && ox + 1 < p.h_size_x)
+            hdst1 = p.head_out + b * p.h_img + (long long)oy * p.h_row + ox + 1;
+#endif
         } else {
           if (p.flat) {
             // flat tile: this lane's four pixels are 8 apart in the row-major (b, y, x) index space
@@ -440,7 +533,13 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
               dst[it] = (uint32_t)o + ch * 8;
             }
           } else {
+#if NIND_PAIR_MODE
+            // pair mode: lane column `sub` is a pixel PAIR; dst[] addresses its first pixel (the second one is
+            // the next 64-column group, one pixel further)
+            const int x = (xt * IG_TILE_W + sub) * (PM ? 2 : 1);
+#else
             const int x = xt * IG_TILE_W + sub;
+#endif
             const int yf0 = yt * IG_TILE_H + quarter * 4;
             int b = yf0 / p.hs_in;
             int y = yf0 - b * p.hs_in;
@@ -452,9 +551,21 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
               const long long o = MODE == 2 ? b * p.o_img + (long long)(2 * y) * p.o_row + (long long)(2 * x) * p.o_pix
                                             : b * p.o_img + (long long)y * p.o_row + (long long)x * p.o_pix;
               dst[it] = (uint32_t)o + ch * 8;
+#if NIND_PAIR_MODE
+              if (MODE == 1 && !PM && it == pit) {
+#else
               if (MODE == 1 && it == pit) {
+#endif
                 pdst = (uint32_t)(b * p.pl_img + (long long)(y >> 1) * p.pl_row + (long long)(xp >> 1) * p.pl_pix) + ch * 8;
                 pvalid = row_ok && (xp < p.w_valid);
+#if NIND_PAIR_MODE
+              }
+              if (MODE == 1 && PM && !(it & 1)) {  // pooled pixel (pair index, row pair it/2); even map sizes
+                const uint32_t po = (uint32_t)(b * p.pl_img + (long long)(y >> 1) * p.pl_row +
+                                               (long long)(x >> 1) * p.pl_pix) + ch * 8;
+                if (it == 0) pdst = po; else pdst1 = po;
+                pvmask |= (uint32_t)(row_ok && (x < p.w_valid)) << (it >> 1);
+#endif
               }
               if (++y == p.hs_in) { y = 0; ++b; }
             }
@@ -473,7 +584,11 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
 #pragma unroll 1
         for (int c64 = 0; c64 < live; ++c64) {
           const int n = nt * N_TILE + c64 * 64;
+#if NIND_PAIR_MODE
+          uint32_t extra = PM ? (uint32_t)(c64 * p.o_pix) : (uint32_t)n;  // offset of this group's first channel from dst[]
+#else
           uint32_t extra = n;  // element offset of this group's first channel from dst[]
+#endif
           if (MODE == 2) {
             const int q = n / p.d2s_cout;
             extra = (uint32_t)((long long)(q >> 1) * p.o_row + (long long)(q & 1) * p.o_pix + (n - q * p.d2s_cout));
@@ -558,12 +673,42 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
               __syncwarp();
               // coalesced write-out: 8 pixels x 64 B per warp instruction
               const uint32_t e = extra + half * 32;
+#if NIND_PAIR_MODE
+              uint4 ov[4];
+#endif
 #pragma unroll
               for (int it = 0; it < 4; ++it) {
                 const uint4 o = *reinterpret_cast<const uint4*>(stg_r + it * 512);
                 if (vmask & (1u << it)) *reinterpret_cast<uint4*>(p.out + (dst[it] + e)) = o;
+#if NIND_PAIR_MODE
+                if (MODE == 1 && PM) ov[it] = o;
+#endif
               }
+#if NIND_PAIR_MODE
+              if (MODE == 1 && PM) {
+                // fused 2x2 max-pool across the two column groups: rows (0,1) and (2,3) of this lane's pair
+                // column reduce in registers; group 0 (first pixel) is kept until group 1 arrives
+#pragma unroll
+                for (int m = 0; m < 2; ++m) {
+                  uint4 v = ov[2 * m];
+                  __nv_bfloat162* pv = reinterpret_cast<__nv_bfloat162*>(&v);
+                  const __nv_bfloat162* pw = reinterpret_cast<const __nv_bfloat162*>(&ov[2 * m + 1]);
+#pragma unroll
+                  for (int q4 = 0; q4 < 4; ++q4) pv[q4] = __hmax2(pv[q4], pw[q4]);
+                  if (c64 == 0) {
+                    pkeep[half][m] = v;
+                  } else {
+                    const __nv_bfloat162* pk = reinterpret_cast<const __nv_bfloat162*>(&pkeep[half][m]);
+#pragma unroll
+                    for (int q4 = 0; q4 < 4; ++q4) pv[q4] = __hmax2(pv[q4], pk[q4]);
+                    if (pvmask & (1u << m))
+                      *reinterpret_cast<uint4*>(p.pool_out + ((m ? pdst1 : pdst) + nt * 64 + half * 32)) = v;
+                  }
+                }
+              } else if (MODE == 1) {
+#else
               if (MODE == 1) {
+#endif
                 // fused 2x2 max-pool: this warp's 32 rows are 4 tile rows x 8 pixels = 2 x 4 pooled pixels;
                 // tile origins and map sizes are even, so the validity of the top-left source pixel covers
                 // all four
@@ -582,9 +727,30 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
               __syncwarp();
             }
           }
+#if NIND_PAIR_MODE
+          if (MODE == 3 && PM) {  // this column group was one pixel of the pair: write it, start the next
+            float* hd = c64 ? hdst1 : hdst;
+            if (hd) {
+              float o0 = h0 + p.head_c[192], o1 = h1 + p.head_c[193], o2 = h2 + p.head_c[194];
+              if (p.head_sigmoid) {
+                o0 = 1.f / (1.f + __expf(-o0));
+                o1 = 1.f / (1.f + __expf(-o1));
+                o2 = 1.f / (1.f + __expf(-o2));
+              }
+              hd[0] = o0;
+              hd[p.h_plane] = o1;
+              hd[2 * p.h_plane] = o2;
+            }
+            h0 = h1 = h2 = 0.f;
+          }
+#endif
         }
         if (quarter == 0) NIND_TRACE(tl, TR_EPI_DONE);
+#if NIND_PAIR_MODE
+        if (MODE == 3 && !PM && hdst) {
+#else
         if (MODE == 3 && hdst) {
+#endif
           float o0 = h0 + p.head_c[192], o1 = h1 + p.head_c[193], o2 = h2 + p.head_c[194];
           if (p.head_sigmoid) {
             o0 = 1.f / (1.f + __expf(-o0));

@@ -36,6 +36,10 @@ struct ConvSpec {
   float* head_out = nullptr;  // [B][3][hy][hx] fp32
   int head_unpad = 0, head_hy = 0, head_hx = 0, head_sigmoid = 0;
   // tuning
+#if NIND_PAIR_MODE
+  bool pair = false;  // EXPERIMENTAL pixel-pair mode (C_out = 64 3x3 layers as N = 128 GEMMs); `w` must then point to
+                      // the weights re-packed by pack_pair_weights()
+#endif
   int flat = -1;  // flat (1-D) tiles for narrow maps: -1 auto, 0 off, 1 force (error if illegal), 2 wherever legal
   int n_tile = 0;     // 0 = auto
   int cg = 0;         // CTAs per tile group: 0 = auto, 1, or 2 (cta_group::2 pair)
@@ -49,6 +53,9 @@ struct IgemmLaunch {
   IgemmParams p;
   int n_tile = 0, tps = 1, cg = 1;
   bool c8 = false;  // first layer: 3x3 conv over an 8-channel (16 B/pixel) tensor, no-swizzle descriptors
+#if NIND_PAIR_MODE
+  bool pm = false;  // pixel-pair mode
+#endif
   size_t smem = 0;
   int grid = 0;
   double flops = 0;  // algorithmic 2*MAC actually useful (valid outputs only)
@@ -119,6 +126,31 @@ inline int device_sm_count() {
   return n;
 }
 
+#if NIND_PAIR_MODE
+// Pixel-pair mode weights.  `w9` = the tap-major packing every 3x3 layer uses, [9][64][C] (host copy);
+// result = [CTA rank 0..1][block g = chunk*3 + ky][96 rows][64 k]: rows 0..63 = this CTA's half of the
+// N = 128 MMA's weight tile (pair tap j = 1-e; CTA rank a = output pixel a: kx = 2 - a for e = 0, 1 - a for
+// e = 1), rows 64..95 = its half (c_out = 32*rank ..) of the N = 64 MMA's tile (pair tap j = e, kx = 2e).
+// Chunks are ordered (input pixel e, 64-channel block).
+inline void pack_pair_weights(const __nv_bfloat16* w9, int C, std::vector<__nv_bfloat16>* out) {
+  const int sub_chunks = C / 64, kchunks = 2 * sub_chunks, blocks = kchunks * 3;
+  out->assign((size_t)2 * blocks * 96 * 64, __float2bfloat16(0.f));
+  auto W = [&](int ky, int kx, int co, int c) { return w9[((size_t)(ky * 3 + kx) * 64 + co) * C + c]; };
+  for (int r = 0; r < 2; ++r)
+    for (int kc = 0; kc < kchunks; ++kc) {
+      const int e = kc / sub_chunks, cb = (kc % sub_chunks) * 64;
+      for (int ky = 0; ky < 3; ++ky) {
+        __nv_bfloat16* blk = out->data() + ((size_t)(r * blocks + kc * 3 + ky) * 96) * 64;
+        const int kx128 = e == 0 ? 2 - r : 1 - r, kx64 = 2 * e;
+        for (int co = 0; co < 64; ++co)
+          for (int c = 0; c < 64; ++c) blk[(size_t)co * 64 + c] = W(ky, kx128, co, cb + c);
+        for (int i = 0; i < 32; ++i)
+          for (int c = 0; c < 64; ++c) blk[(size_t)(64 + i) * 64 + c] = W(ky, kx64, r * 32 + i, cb + c);
+      }
+    }
+}
+
+#endif
 inline bool build_igemm(const ConvSpec& s, IgemmLaunch* L, std::string* why) {
   auto fail = [&](const char* m) {
     if (why) *why = m;
@@ -138,18 +170,39 @@ inline bool build_igemm(const ConvSpec& s, IgemmLaunch* L, std::string* why) {
   IgemmParams& p = L->p;
   memset(&p, 0, sizeof p);
 
+#if NIND_PAIR_MODE
+  if (s.pair && (s.taps != 9 || s.c8 || s.n_total != 64 || s.in_coff != 0 || s.cin != s.in.c ||
+                 (s.cin != 64 && s.cin != 128) || (s.in.ws & 1) || s.epi_mode == EPI_D2S))
+    return fail("pixel-pair mode needs a 3x3 layer with C_out = 64, C_in = 64|128 filling its buffer, even width");
+  L->pm = s.pair;
+#endif
   int n_tile = s.n_tile;
+#if NIND_PAIR_MODE
+  if (s.pair) n_tile = 128;  // GEMM N = (pixel of the pair, c_out)
+#endif
   if (n_tile == 0) n_tile = s.n_total >= 256 ? 256 : (s.n_total >= 128 ? 128 : 64);
   if (n_tile != 64 && n_tile != 128 && n_tile != 256) return fail("n_tile must be 64/128/256");
+#if NIND_PAIR_MODE
+  if (s.epi_mode == EPI_HEAD && ((n_tile != 64 && !s.pair) || s.n_total != 64)) return fail("head needs N=64");
+#else
   if (s.epi_mode == EPI_HEAD && (n_tile != 64 || s.n_total != 64)) return fail("head needs N=64");
+#endif
   L->n_tile = n_tile;
 
   p.w_valid = s.in.ws - shrink;
   p.h_valid = s.in.hs - shrink;
   p.hs_in = s.in.hs;
   p.rows_total = s.in.b * s.in.hs;
+#if NIND_PAIR_MODE
+  // pair mode tiles 8 pixel PAIRS across
+  const int tiles_x_real = s.pair ? (p.w_valid / 2 + IG_TILE_W - 1) / IG_TILE_W : (p.w_valid + IG_TILE_W - 1) / IG_TILE_W;
+#else
   const int tiles_x_real = (p.w_valid + IG_TILE_W - 1) / IG_TILE_W;
+#endif
   int cg = s.cg;
+#if NIND_PAIR_MODE
+  if (s.pair) cg = 2;
+#endif
   // measured on B200 (profiles/r01_probe_cta_pair.log): the CTA pair wins on every 3x3 layer except
   // 64->128 (-3 %), and on the 1x1 / 2x2-s2 GEMMs only when K is large (C_in >= 512)
   if (s.c8) cg = 1;
@@ -166,7 +219,11 @@ inline bool build_igemm(const ConvSpec& s, IgemmLaunch* L, std::string* why) {
   {
     const int box_rows = s.taps == 9 ? 130 + 2 * s.in.ws : 128;
     const double eff_tile = (double)p.w_valid / (IG_TILE_W * tiles_x_real), eff_flat = (double)p.w_valid / s.in.ws;
+#if NIND_PAIR_MODE
+    const bool can = !s.c8 && !s.pair && s.epi_mode != EPI_HEAD && !s.pool.ptr && box_rows <= 256;
+#else
     const bool can = !s.c8 && s.epi_mode != EPI_HEAD && !s.pool.ptr && box_rows <= 256;
+#endif
     if (s.flat == 1 && !can) return fail("flat tiles need a narrow map (<= 63 px), no fused pool / head, not the first layer");
     flat = can && (s.flat >= 1 || (s.flat == -1 && eff_flat > eff_tile + 0.02));
   }
@@ -186,9 +243,17 @@ inline bool build_igemm(const ConvSpec& s, IgemmLaunch* L, std::string* why) {
     p.tiles_x = p.pair_y ? tiles_x_real : (tiles_x_real + cg - 1) / cg;
     p.tiles_y = p.pair_y ? (tiles_y_real + 1) / 2 : tiles_y_real;
   }
+#if NIND_PAIR_MODE
+  p.tiles_n = s.pair ? 1 : (s.n_total + n_tile - 1) / n_tile;
+#else
   p.tiles_n = (s.n_total + n_tile - 1) / n_tile;
+#endif
   p.total_tiles = p.tiles_x * p.tiles_y * p.tiles_n;
+#if NIND_PAIR_MODE
+  p.kchunks = s.c8 ? 1 : (s.pair ? 2 * s.cin / 64 : s.cin / 64);
+#else
   p.kchunks = s.c8 ? 1 : s.cin / 64;
+#endif
   p.taps = s.taps;
 
   // A operand: one TMA box per (tile, 64-channel chunk).  3x3: the (16+2) x (8+2) pixel patch, whose
@@ -199,6 +264,11 @@ inline bool build_igemm(const ConvSpec& s, IgemmLaunch* L, std::string* why) {
     boxA[0] = 64; boxA[1] = s.taps == 9 ? 130 + 2 * s.in.ws : 128; boxA[2] = 1;
     p.a_tx_bytes = boxA[1] * 128; p.a_stage_bytes = (p.a_tx_bytes + 1023) & ~1023; p.a_sbo = 1024;
     p.tap_pitch16 = (uint32_t)s.in.ws * 8;
+#if NIND_PAIR_MODE
+  } else if (s.pair) {  // 8 + 1 pixel pairs x 16 + 2 rows of the [rows, W/2, 2C] view
+    boxA[0] = 64; boxA[1] = 9; boxA[2] = 18;
+    p.a_tx_bytes = 9 * 18 * 128; p.a_stage_bytes = 21504; p.a_sbo = 1152;
+#endif
   } else if (s.taps == 1) {
     boxA[0] = 64; boxA[1] = 8; boxA[2] = 16;
     p.a_tx_bytes = 16384; p.a_stage_bytes = 16384; p.a_sbo = 1024;
@@ -213,7 +283,11 @@ inline bool build_igemm(const ConvSpec& s, IgemmLaunch* L, std::string* why) {
   if (!flat) p.tap_pitch16 = p.a_sbo >> 4;
 
   // pipeline depth / weights-stationary decision
+#if NIND_PAIR_MODE
+  const int tps = (s.c8 || s.pair) ? 1 : ((s.taps == 9 && n_tile <= 128) ? 3 : 1);  // taps per weight stage
+#else
   const int tps = s.c8 ? 1 : ((s.taps == 9 && n_tile <= 128) ? 3 : 1);  // taps per weight stage
+#endif
   L->tps = tps;
   const int kt = s.c8 ? 2 : p.kchunks * (p.taps / tps);  // c8: 10 KB of weights in two 8 KB "stages"
   bool ws = false;
@@ -224,7 +298,17 @@ inline bool build_igemm(const ConvSpec& s, IgemmLaunch* L, std::string* why) {
   auto fits = [&](int sa, int sb) {
     return igemm_smem_bytes(n_tile, tps, cg, sa, p.a_stage_bytes, sb) <= IG_SMEM_LIMIT;
   };
+#if NIND_PAIR_MODE
+  if (s.pair) {  // resident weights: 36 KB per (e, 64-channel block) per CTA, counted in 8 KB "stages"
+    ws = true;
+    p.sb = p.kchunks * 9 / 2;
+    p.sa = 2;
+    if (!fits(p.sa, p.sb)) return fail("pixel-pair weights do not fit in shared memory");
+    while (p.sa < 4 && fits(p.sa + 1, p.sb)) ++p.sa;
+  } else if (ws) {
+#else
   if (ws) {
+#endif
     p.sb = kt;
     p.sa = 2;
     while (p.sa < 6 && fits(p.sa + 1, p.sb)) ++p.sa;
@@ -250,6 +334,12 @@ inline bool build_igemm(const ConvSpec& s, IgemmLaunch* L, std::string* why) {
       const uint64_t stridesA[1] = {(uint64_t)s.in.ws * 16};
       const uint32_t boxA2[2] = {80, 18};
       if (!encode_tmap_bf16(&L->tmA, s.in.ptr, 2, dimsA, stridesA, boxA2, why, false)) return false;
+#if NIND_PAIR_MODE
+    } else if (s.pair) {  // [rows][W/2 pairs][2C channels]
+      const uint64_t dimsA[3] = {(uint64_t)2 * s.cin, (uint64_t)s.in.ws / 2, (uint64_t)p.rows_total};
+      const uint64_t stridesA[2] = {(uint64_t)s.in.c * 4, (uint64_t)s.in.ws * s.in.c * 2};
+      if (!encode_tmap_bf16(&L->tmA, s.in.ptr, 3, dimsA, stridesA, boxA, why)) return false;
+#endif
     } else if (flat) {  // [all pixels of the buffer][channels]
       const uint64_t dimsA[2] = {(uint64_t)s.cin, (uint64_t)p.rows_total * s.in.ws};
       const uint64_t stridesA[1] = {(uint64_t)s.in.c * 2};
@@ -262,6 +352,13 @@ inline bool build_igemm(const ConvSpec& s, IgemmLaunch* L, std::string* why) {
       const uint64_t stridesB[2] = {16, 1024};
       const uint32_t boxB[3] = {8, 64, 10};
       if (!encode_tmap_bf16(&L->tmB, s.w, 3, dimsB, stridesB, boxB, why, false)) return false;
+#if NIND_PAIR_MODE
+    } else if (s.pair) {  // pack_pair_weights(): [2 ranks x blocks x 96 rows][64]
+      const uint64_t dimsB[2] = {64, (uint64_t)2 * p.kchunks * 3 * 96};
+      const uint64_t stridesB[1] = {128};
+      const uint32_t boxB[2] = {64, 96};
+      if (!encode_tmap_bf16(&L->tmB, s.w, 2, dimsB, stridesB, boxB, why)) return false;
+#endif
     } else {
       const uint64_t dimsB[2] = {(uint64_t)s.cin, (uint64_t)s.taps * s.n_total};
       const uint64_t stridesB[1] = {(uint64_t)s.cin * 2};
@@ -271,7 +368,11 @@ inline bool build_igemm(const ConvSpec& s, IgemmLaunch* L, std::string* why) {
   }
 
   // epilogue
+#if NIND_PAIR_MODE
+  p.n_total = s.pair ? 128 : s.n_total;
+#else
   p.n_total = s.n_total;
+#endif
   p.epi_mode = s.epi_mode;
   p.act = s.act;
   p.slope = s.slope;
@@ -319,11 +420,19 @@ inline bool build_igemm(const ConvSpec& s, IgemmLaunch* L, std::string* why) {
   return true;
 }
 
+#if NIND_PAIR_MODE
+template <int N, int T, int CG, bool G = false, bool PM = false>
+#else
 template <int N, int T, int CG, bool G = false>
+#endif
 inline cudaError_t igemm_launch_t(const IgemmLaunch& L, const IgemmParams& p, cudaStream_t st) {
   static bool attr_done = false;
   if (!attr_done) {
+#if NIND_PAIR_MODE
+    cudaError_t e = cudaFuncSetAttribute(igemm_kernel<N, T, CG, G, PM>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+#else
     cudaError_t e = cudaFuncSetAttribute(igemm_kernel<N, T, CG, G>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+#endif
                                          (int)IG_SMEM_LIMIT);
     if (e != cudaSuccess) return e;
     attr_done = true;
@@ -341,7 +450,11 @@ inline cudaError_t igemm_launch_t(const IgemmLaunch& L, const IgemmParams& p, cu
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
+#if NIND_PAIR_MODE
+  return cudaLaunchKernelEx(&cfg, igemm_kernel<N, T, CG, G, PM>, L.tmA, L.tmB, p);
+#else
   return cudaLaunchKernelEx(&cfg, igemm_kernel<N, T, CG, G>, L.tmA, L.tmB, p);
+#endif
 }
 
 inline cudaError_t launch_igemm(const IgemmLaunch& L, int* err_flag, cudaStream_t st,
@@ -350,6 +463,9 @@ inline cudaError_t launch_igemm(const IgemmLaunch& L, int* err_flag, cudaStream_
   p.err = err_flag;
   p.trace = trace;
   if (L.c8) return igemm_launch_t<64, 1, 1, true>(L, p, st);
+#if NIND_PAIR_MODE
+  if (L.pm) return igemm_launch_t<128, 1, 2, false, true>(L, p, st);
+#endif
   const int key = L.n_tile * 100 + L.tps * 10 + L.cg;
   switch (key) {
     case 6411: return igemm_launch_t<64, 1, 1>(L, p, st);

@@ -131,6 +131,9 @@ struct nind_net {
   std::vector<cudaEvent_t> ev_in, ev_done;
   cudaEvent_t ev_join = nullptr;
   int flat = -1;
+#if NIND_PAIR_MODE
+  int pair64 = 0;  // EXPERIMENTAL, not validated on hardware yet
+#endif
   int host_first = -1, host_last = -1;  // crops in the first / last pipeline step (-1: one grid row)
   // options
   int n_tile_deep = 256, max_ctas = 0, cg = 0, fuse_pool = 1;
@@ -470,6 +473,10 @@ struct PlanBuilder {
     s.cg = net->cg;
     s.flat = net->flat == 1 ? 2 : net->flat;  // 1 = on every layer where it is legal
     if (L.n_total >= 256) s.n_tile = net->n_tile_deep;
+#if NIND_PAIR_MODE
+    maybe_pair(s, L, in, in_coff);
+    if (rc) return;
+#endif
     Step st;
     st.kind = STEP_IGEMM; st.name = name;
     std::string why;
@@ -484,6 +491,33 @@ struct PlanBuilder {
     plan->steps.push_back(st);
   }
 
+#if NIND_PAIR_MODE
+  // EXPERIMENTAL (option "pair64", off by default): run an eligible C_out = 64 3x3 layer in pixel-pair mode;
+  // its re-packed weights live in a plan-owned buffer.
+  void maybe_pair(ConvSpec& s, const PackedLayer& L, const ActBuf& in, int in_coff) {
+    if (rc || !net->pair64 || L.taps != 9 || L.n_total != 64 || in_coff != 0 || L.cin != in.c ||
+        (L.cin != 64 && L.cin != 128) || (in.ws & 1) || s.epi_mode == EPI_D2S || s.c8)
+      return;
+    std::vector<__nv_bfloat16> w9((size_t)9 * 64 * L.cin), wp;
+    if (cudaMemcpy(w9.data(), L.w, w9.size() * sizeof(__nv_bfloat16), cudaMemcpyDeviceToHost) != cudaSuccess) {
+      rc = fail(NIND_E_CUDA, "pair64: cannot read the packed weights");
+      return;
+    }
+    pack_pair_weights(w9.data(), L.cin, &wp);
+    void* d = nullptr;
+    if (cudaMalloc(&d, wp.size() * sizeof(__nv_bfloat16)) != cudaSuccess ||
+        cudaMemcpy(d, wp.data(), wp.size() * sizeof(__nv_bfloat16), cudaMemcpyHostToDevice) != cudaSuccess) {
+      if (d) cudaFree(d);
+      rc = fail(NIND_E_CUDA, "pair64: cannot upload the re-packed weights");
+      return;
+    }
+    plan->bufs.push_back(d);
+    s.w = static_cast<const __nv_bfloat16*>(d);
+    s.pair = true;
+    s.flat = 0;
+  }
+
+#endif
   void head(const std::string& name, const ActBuf& in, int unpad, int hy, int hx, int sigmoid) {
     if (rc) return;
     auto it = net->layers.find(name);
@@ -496,6 +530,10 @@ struct PlanBuilder {
     s.head_unpad = unpad; s.head_hy = hy; s.head_hx = hx; s.head_sigmoid = sigmoid;
     s.max_ctas = net->max_ctas;
     s.cg = net->cg;
+#if NIND_PAIR_MODE
+    maybe_pair(s, L, in, 0);
+    if (rc) return;
+#endif
     Step st;
     st.kind = STEP_IGEMM; st.name = name + "+head";
     std::string why;
@@ -855,6 +893,10 @@ int nind_set_option(nind_net* net, const char* key, int value) {
     net->fuse_pool = value ? 1 : 0;
   } else if (k == "first_c8") {
     net->first_c8 = value ? 1 : 0;
+#if NIND_PAIR_MODE
+  } else if (k == "pair64") {  // EXPERIMENTAL pixel-pair mode for the C_out = 64 3x3 layers (0 | 1)
+    net->pair64 = value ? 1 : 0;
+#endif
   } else if (k == "flat") {  // flat (1-D) tiles on narrow maps: -1 auto, 0 off, 1 wherever legal
     net->flat = value;
   } else if (k == "host_first") {  // crops in the first step of the host pipeline (-1: one grid row)

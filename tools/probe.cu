@@ -292,10 +292,18 @@ static int run_conv(int argc, char** argv) {
   const int ctas = argc > 13 ? atoi(argv[13]) : 0;
   const int cg = argc > 14 ? atoi(argv[14]) : 0;
   const int flat = argc > 15 ? atoi(argv[15]) : -1;
+#if NIND_PAIR_MODE
+  const int pair = argc > 16 ? atoi(argv[16]) : 0;   // EXPERIMENTAL pixel-pair mode (C_out = 64 layers)
+#endif
   const int tw = taps == 9 ? 3 : 1;
   const int Hv = Hs - (tw - 1), Wv = Ws - (tw - 1);
   const bool c8 = cin == 8;              // first-layer mode: 8-channel input, no-swizzle descriptors
+#if NIND_PAIR_MODE
+  // read a channel sub-range to exercise offsets (pair mode views the whole buffer as [rows, W/2, 2C])
+  const int Cbuf = c8 ? 8 : (pair ? cin : cin + 64), coff = (c8 || pair) ? 0 : 64;
+#else
   const int Cbuf = c8 ? 8 : cin + 64, coff = c8 ? 0 : 64;  // read a channel sub-range to exercise offsets
+#endif
   const int act = ACT_PRELU;
   const float slope = 0.25f;
 
@@ -341,7 +349,19 @@ static int run_conv(int argc, char** argv) {
     CK(cudaMemcpy(dw8, w8.data(), w8.size() * 2, cudaMemcpyHostToDevice));
     s.c8 = true;
   }
+#if NIND_PAIR_MODE
+  __nv_bfloat16* dwp = nullptr;
+  if (pair) {
+    std::vector<__nv_bfloat16> wp;
+    pack_pair_weights(hw.data(), cin, &wp);
+    CK(cudaMalloc(&dwp, wp.size() * 2));
+    CK(cudaMemcpy(dwp, wp.data(), wp.size() * 2, cudaMemcpyHostToDevice));
+    s.pair = true;
+  }
+  s.in_coff = coff; s.cin = cin; s.taps = taps; s.w = c8 ? dw8 : (pair ? dwp : dw); s.n_total = n_total; s.bias = dbias;
+#else
   s.in_coff = coff; s.cin = cin; s.taps = taps; s.w = c8 ? dw8 : dw; s.n_total = n_total; s.bias = dbias;
+#endif
   s.act = act; s.slope = slope; s.epi_mode = epi; (void)a_mode; (void)bo_mode;
   s.n_tile = n_tile; s.force_ws = ws; s.max_ctas = ctas; s.cg = cg; s.flat = flat;
   const int halo = 2, ocoff = 32;
