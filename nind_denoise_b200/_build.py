@@ -33,7 +33,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
     """Compile csrc/*.cu -> libnind_b200.so (sm_100a).  Returns the library path."""
     if not force and not is_stale():
         return LIB_PATH
-    cmd = [find_nvcc()] + NVCC_FLAGS + ["-o", LIB_PATH] + SOURCES
+    # NIND_NVCC_EXTRA="-DNIND_PAIR_MODE=1" compiles experimental code paths in (development only)
+    cmd = [find_nvcc()] + NVCC_FLAGS + os.environ.get("NIND_NVCC_EXTRA", "").split() + ["-o", LIB_PATH] + SOURCES
     if verbose:
         print(" ".join(cmd))
     r = subprocess.run(cmd, capture_output=True, text=True)
