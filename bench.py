@@ -192,6 +192,8 @@ def main():
     ap.add_argument("--gather", default="rows", choices=["rows", "bands"],
                     help="N>1: seam exchange + owned-row gather (default) or whole-band gather summed on rank 0")
     ap.add_argument("--layers", action="store_true", help="print the per-layer timing table to stderr")
+    ap.add_argument("--opt", action="append", default=[], metavar="KEY=VALUE",
+                    help="nind_set_option knob for A/B runs (e.g. pair64=0); not used for the headline")
     args = ap.parse_args()
     set_workload(args.network)
     if args.cs <= 0:
@@ -222,6 +224,9 @@ def main():
 
     torch.manual_seed(0)  # default init == the reference class's default init under the same seed
     model = (nb.UtNet() if NETWORK == "UtNet" else nb.UNet()).to(dev).eval()
+    for kv in args.opt:
+        k, v = kv.split("=")
+        model.set_option(k, int(v))
     g = torch.Generator(device="cpu").manual_seed(1)
     img_host = torch.rand((3, H_IMG, W_IMG), generator=g).pin_memory()
     out_host = torch.empty_like(img_host).pin_memory()
@@ -359,7 +364,7 @@ def main():
         if True:
             roof["memory_bound_kernels"] = {
                 k: {"GB/s": v[3] / (v[0] * 1e-3) / 1e9, "frac_of_hbm_peak": v[3] / (v[0] * 1e-3) / 1e9 / pk["hbm"]}
-                for k, v in agg.items() if k in ("gather+im2col", "convs1.0+gather", "up4", "up3", "convs1.0") and v[0] > 0}
+                for k, v in agg.items() if k in ("gather+pad8", "up4", "up3", "convs1.0", "inc.conv.conv.0", "up4.up", "up3.up") and v[0] > 0}
         if args.layers:
             for k, tm, f, b_ in layer_rows:
                 print(f"{k:28s} {tm:8.3f} ms  {f / 1e9:10.1f} GFLOP  {f / (tm * 1e-3) / 1e12 if tm else 0:8.1f} TF/s"

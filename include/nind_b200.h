@@ -12,9 +12,12 @@
  * nind_last_error() returns a human-readable description of the most recent failure on the
  * calling thread.  The caller owns every buffer it passes in; the library owns its packed
  * weights and activation arena.  A handle is bound to the CUDA device that was current when it was
- * created; it is not thread-safe, different handles are independent.  All work is enqueued on
- * the `stream` argument (a cudaStream_t passed as void*; NULL = default stream) and is complete
- * once that stream is synchronised — except the *_host entry point, which synchronises itself.
+ * created (every entry point switches to that device for the duration of the call; nind_net_device()
+ * reports it); it is not thread-safe, different handles are independent — also on different devices of
+ * one process.  All work is enqueued on the `stream` argument (a cudaStream_t passed as void*; NULL =
+ * default stream) and is complete once that stream is synchronised — except the *_host entry point, which
+ * synchronises itself.  Consecutive calls on one handle may use different streams: the scratch memory the
+ * entry points share is ordered by an internal event, no synchronisation is needed in between.
  * There is no CPU fallback: without an sm_100 device every compute entry point fails.
  */
 #ifndef NIND_B200_H
@@ -40,6 +43,8 @@ enum {
 
 enum { NIND_ARCH_UTNET = 0, NIND_ARCH_UNET = 1 };
 enum { NIND_ACT_PRELU = 0, NIND_ACT_ELU = 1, NIND_ACT_HARDSWISH = 2 };
+enum { NIND_FWD_CLAMP01 = 1 };                           /* nind_net_forward_ex flags */
+enum { NIND_PIX_U8 = 0, NIND_PIX_U16 = 1, NIND_PIX_F32 = 2 };  /* interleaved image pixel types */
 
 /* One entry of a PyTorch state_dict: fp32, contiguous, host or device memory. */
 typedef struct {
@@ -74,6 +79,13 @@ void nind_net_destroy(nind_net* net);
  * of 16. */
 int nind_net_forward(nind_net* net, const float* in_nchw, float* out_nchw, int batch, int h, int w,
                      void* stream);
+/* Same with flags.  NIND_FWD_CLAMP01 replaces Generator.denoise_batch = model(x).clip(0, 1)
+ * (nn_common.py:198-199, used by the validation / test passes of nn_train.py:51-93): the clamp is fused
+ * into the epilogue of the 1x1 output head. */
+int nind_net_forward_ex(nind_net* net, const float* in_nchw, float* out_nchw, int batch, int h, int w, int flags,
+                        void* stream);
+/* CUDA device ordinal the handle is bound to. */
+int nind_net_device(nind_net* net, int* device);
 
 /* Crop grid (OneImageDS.__init__/__getitem__).  Pass table = NULL to query the count. */
 int nind_crop_table(int width, int height, int cs, int ucs, int ol, nind_crop* table, int* n_crops);
@@ -129,6 +141,19 @@ int nind_host_join(nind_net* net, void* stream);
 int nind_host_register(void* ptr, size_t bytes);
 int nind_host_unregister(void* ptr);
 
+/* File formats either side of the path, on the current device (src and dst are device pointers):
+ *   nind_image_to_chw_f32  replaces the conversion of img_path_to_np_flt (common/libs/np_imgops.py:19-28):
+ *                          a decoded interleaved [h,w,3] image (BGR order if bgr != 0, as cv2 returns it) of
+ *                          type NIND_PIX_* -> planar RGB fp32 [3,h,w]; u8/255, u16/65535, float unchanged
+ *                          (bit-identical to the numpy expressions);
+ *   nind_chw_f32_to_image  replaces the quantisation of tensor_to_imgfile (common/libs/pt_helpers.py:24-32):
+ *                          NIND_PIX_U16 clip(0,1)*65535 rounded half to even, NIND_PIX_U8 clip(0,1)*255+0.5
+ *                          truncated (torchvision.utils.save_image), NIND_PIX_F32 unclamped. */
+int nind_image_to_chw_f32(const void* src_hwc, int dtype, int height, int width, int bgr, float* dst_chw,
+                          void* stream);
+int nind_chw_f32_to_image(const float* src_chw, int height, int width, int dtype, int bgr, void* dst_hwc,
+                          void* stream);
+
 /* Number of CUDA kernels this library has launched on the calling process so far. */
 int64_t nind_kernel_launches(void);
 
@@ -141,9 +166,9 @@ int nind_get_layer_times(nind_net* net, int max_layers, const char** names, floa
 int nind_get_layer_bytes(nind_net* net, int max_layers, double* bytes, int* n_layers);
 
 /* Tuning knobs (affect plans built afterwards): "n_tile_deep" (128|256), "max_ctas",
- * "cta_group" (0 auto | 1 | 2), "fuse_pool" (0|1), "first_c8" (0|1), "flat" (-1 auto | 0 off: 1-D tiles on
- * narrow maps); host pipeline: "host_first" /
- * "host_last" = crops in its first / last step (-1: one grid row). */
+ * "cta_group" (0 auto | 1 | 2), "fuse_pool" (0|1), "pair64" (0|1: pixel-pair mode of the C_out = 64 3x3
+ * layers), "flat" (-1 auto | 0 off: 1-D tiles on narrow maps); host pipeline: "host_first" / "host_last" =
+ * crops in its first / last step (-1: up to / from the nearest grid-row boundary). */
 int nind_set_option(nind_net* net, const char* key, int value);
 
 const char* nind_last_error(void);

@@ -9,6 +9,8 @@ from . import _build
 
 NIND_ARCH_UTNET, NIND_ARCH_UNET = 0, 1
 NIND_ACT = {"PReLU": 0, "ELU": 1, "Hardswish": 2}
+NIND_FWD_CLAMP01 = 1
+NIND_PIX_U8, NIND_PIX_U16, NIND_PIX_F32 = 0, 1, 2
 
 
 class NindTensor(C.Structure):
@@ -35,6 +37,11 @@ SIGNATURES = {
     "nind_net_load": (C.c_int, [C.c_void_p, C.POINTER(NindTensor), C.c_int]),
     "nind_net_destroy": (None, [C.c_void_p]),
     "nind_net_forward": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]),
+    "nind_net_forward_ex": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int,
+                                      C.c_void_p]),
+    "nind_net_device": (C.c_int, [C.c_void_p, C.POINTER(C.c_int)]),
+    "nind_image_to_chw_f32": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
+    "nind_chw_f32_to_image": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
     "nind_crop_table": (C.c_int, [C.c_int] * 5 + [C.POINTER(NindCrop), C.POINTER(C.c_int)]),
     "nind_tiled_denoise": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p] + [C.c_int] * 8 +
                            [C.POINTER(C.c_int), C.POINTER(C.c_int), C.c_void_p]),

@@ -1,60 +1,13 @@
-// Memory-bound kernels around the convolutions: crop gather (+ in-network pad + first-layer
-// im2col), 2x2 max-pool, and the output-centric stitch.  All are coalesced 16-byte-vector kernels.
+// Memory-bound kernels around the convolutions: crop gather (+ in-network pad), 2x2 max-pool, the
+// output-centric stitch and the file-format conversions either side of the path.
 #pragma once
 #include "gather_common.cuh"
 #include "ptx.cuh"
 
 namespace nind {
 
-__global__ void __launch_bounds__(256) gather_im2col_kernel(const GatherParams p) {
-  // One thread per output pixel of the first convolution: 6 index computations, 27 coalesced loads
-  // (neighbouring threads read neighbouring pixels).  The 128-byte bf16 row of each pixel goes through
-  // an XOR-swizzled shared staging tile so that a warp writes its 32 pixels as 4 KB of contiguous,
-  // fully coalesced 16-byte stores (the destination is dense [crops][out_h][out_w][64]).
-  __shared__ __align__(16) uint8_t stage[8][4096];
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const long long total = (long long)p.n_crops * p.out_h * p.out_w;
-  const long long total_r = (total + 31) & ~31LL;  // whole warps
-  for (long long gid = blockIdx.x * (long long)blockDim.x + threadIdx.x; gid < total_r;
-       gid += (long long)gridDim.x * blockDim.x) {
-    float h[64];
-    if (gid < total) {
-      long long pix = gid;
-      const int x = (int)(pix % p.out_w);
-      pix /= p.out_w;
-      const int y = (int)(pix % p.out_h);
-      const int b = (int)(pix / p.out_h);
-      im2col_row(p, b, y, x, h);
-    } else {
-#pragma unroll
-      for (int k = 0; k < 64; ++k) h[k] = 0.f;
-    }
-    uint8_t* st = stage[warp];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      uint4 o;
-      o.x = pack_bf16x2(h[8 * j + 0], h[8 * j + 1]);
-      o.y = pack_bf16x2(h[8 * j + 2], h[8 * j + 3]);
-      o.z = pack_bf16x2(h[8 * j + 4], h[8 * j + 5]);
-      o.w = pack_bf16x2(h[8 * j + 6], h[8 * j + 7]);
-      *reinterpret_cast<uint4*>(st + lane * 128 + ((j ^ (lane & 7)) << 4)) = o;
-    }
-    __syncwarp();
-    const long long warp_first = gid - lane;  // first pixel of this warp
-    uint8_t* dst = reinterpret_cast<uint8_t*>(p.dst) + warp_first * 128;
-    const int sub = lane >> 3, ch = lane & 7;
-#pragma unroll
-    for (int it = 0; it < 8; ++it) {
-      const int rr = it * 4 + sub;
-      const uint4 o = *reinterpret_cast<const uint4*>(st + rr * 128 + ((ch ^ (rr & 7)) << 4));
-      if (warp_first + rr < total) *reinterpret_cast<uint4*>(dst + it * 512 + lane * 16) = o;
-    }
-    __syncwarp();
-  }
-}
-
 // ------------------------------------------------------------------ crop gather -> padded 8-channel tensor
-// Same indexing as gather_im2col_kernel, but writes the PADDED crop itself (no im2col) as 8 bf16 channels
+// Writes the PADDED crop as 8 bf16 channels
 // per pixel — R,G,B hi parts, R,G,B lo parts (x - bf16(x)), two zeros = 16 B — for the first layer's
 // 3x3 implicit GEMM (igemm_kernel C8 mode).  out_h/out_w = crop + 2*pad.
 __global__ void __launch_bounds__(256) gather_pad8_kernel(const GatherParams p) {
@@ -233,6 +186,70 @@ __global__ void __launch_bounds__(256) gather_crops_kernel(const CropGatherParam
     const int2 o = p.origin[b];
     const int iy = sym_index(o.y + rr, p.src_h), ix = sym_index(o.x + q, p.src_w);
     p.dst[gid] = __ldg(p.src + c * p.src_plane + (long long)iy * p.src_w + ix);
+  }
+}
+
+// ------------------------------------------------------------------ file formats either side of the path
+// image_to_chw_kernel = img_path_to_np_flt after the decode (common/libs/np_imgops.py:19-28): interleaved HWC
+// pixels as cv2 returns them (BGR when bgr = 1) of type u8 / u16 / f32 -> planar RGB fp32, x/255, x/65535 or
+// unchanged (IEEE division: bit-identical to numpy's).
+// chw_to_image_kernel = the quantisation of tensor_to_imgfile (common/libs/pt_helpers.py:24-32): u16
+// clip(0,1)*65535 rounded half-to-even; u8 clip(0,1)*255 + 0.5 truncated (torchvision.utils.save_image);
+// f32 unclamped.
+struct PixConvParams {
+  void* hwc;
+  float* chw;
+  int h, w;
+  int dtype;  // 0 u8, 1 u16, 2 f32
+  int bgr;
+};
+
+__global__ void __launch_bounds__(256) image_to_chw_kernel(const PixConvParams p) {
+  const long long plane = (long long)p.h * p.w;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < plane;
+       i += (long long)gridDim.x * blockDim.x) {
+    float v[3];
+    if (p.dtype == 0) {
+      const uint8_t* s = static_cast<const uint8_t*>(p.hwc) + 3 * i;
+#pragma unroll
+      for (int c = 0; c < 3; ++c) v[c] = __fdiv_rn((float)s[c], 255.f);
+    } else if (p.dtype == 1) {
+      const uint16_t* s = static_cast<const uint16_t*>(p.hwc) + 3 * i;
+#pragma unroll
+      for (int c = 0; c < 3; ++c) v[c] = __fdiv_rn((float)s[c], 65535.f);
+    } else {
+      const float* s = static_cast<const float*>(p.hwc) + 3 * i;
+#pragma unroll
+      for (int c = 0; c < 3; ++c) v[c] = s[c];
+    }
+#pragma unroll
+    for (int c = 0; c < 3; ++c) p.chw[(p.bgr ? 2 - c : c) * plane + i] = v[c];
+  }
+}
+
+__global__ void __launch_bounds__(256) chw_to_image_kernel(const PixConvParams p) {
+  const long long plane = (long long)p.h * p.w;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < plane;
+       i += (long long)gridDim.x * blockDim.x) {
+    float v[3];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) v[c] = p.chw[(p.bgr ? 2 - c : c) * plane + i];
+    if (p.dtype == 0) {
+      uint8_t* d = static_cast<uint8_t*>(p.hwc) + 3 * i;
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        const float q = __fadd_rn(__fmul_rn(fminf(fmaxf(v[c], 0.f), 1.f), 255.f), 0.5f);
+        d[c] = (uint8_t)fminf(fmaxf(q, 0.f), 255.f);
+      }
+    } else if (p.dtype == 1) {
+      uint16_t* d = static_cast<uint16_t*>(p.hwc) + 3 * i;
+#pragma unroll
+      for (int c = 0; c < 3; ++c) d[c] = (uint16_t)rintf(__fmul_rn(fminf(fmaxf(v[c], 0.f), 1.f), 65535.f));
+    } else {
+      float* d = static_cast<float*>(p.hwc) + 3 * i;
+#pragma unroll
+      for (int c = 0; c < 3; ++c) d[c] = v[c];
+    }
   }
 }
 

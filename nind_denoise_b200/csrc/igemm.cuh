@@ -1,11 +1,10 @@
-// Implicit-GEMM convolution for sm_100a: TMA -> shared memory -> tcgen05.mma -> TMEM -> fused epilogue.
+// Implicit-GEMM convolution for sm_100a: TMA -> shared memory -> tcgen05.mma -> TMEM -> fused epilogue -> TMA.
 //
 // One kernel serves every dense layer of the NIND denoisers (reference:
 // src/nind_denoise/networks/UtNet.py:27-88, ThirdPartyNets.py:62-136):
 //   * 3x3 "valid" convolution over an NHWC bf16 buffer (Conv2d k=3; ConvTranspose2d k=3 s=1 and
 //     Conv2d k=3 p=1 become valid convolutions because their inputs are stored with a zero frame),
-//   * 1x1 convolution / per-pixel GEMM (the first layer after im2col, ConvTranspose2d k=2 s=2 with a
-//     depth-to-space scatter epilogue),
+//   * 1x1 convolution / per-pixel GEMM (ConvTranspose2d k=2 s=2 with a depth-to-space epilogue),
 //   * the 1x1 output head fused into the epilogue of the last 3x3 layer.
 //
 // GEMM view: M = output pixels (tile = 16 rows x 8 pixels = 128 UMMA rows), N = output channels,
@@ -17,13 +16,15 @@
 // issuing thread pays one barrier round-trip per 12 MMAs; when the whole weight tensor of the layer
 // fits in shared memory it is loaded once per CTA and kept ("weights stationary").
 //
-// Warp roles (384 threads, 1 CTA/SM, persistent over tiles):
+// Warp roles (128 + 128*ES threads, 1 CTA/SM, persistent over tiles):
 //   warp 0: TMA producer for activation patches      warp 1: TMA producer for weight tiles
 //   warp 2: tcgen05.mma issuer (one elected lane)    warp 3: TMEM allocator
-//   warps 4-7 / 8-11: two epilogue sets, one per TMEM accumulator buffer (even / odd tiles):
-//              tcgen05.ld -> bias/activation -> bf16 -> swizzled smem staging -> coalesced 16-byte
-//              global stores (8 pixels x 64 B per warp instruction); the epilogue of a tile overlaps
-//              the MMAs of the next two tiles.
+//   warps 4.. : ES epilogue sets of four warps, one per TMEM accumulator stage:
+//              tcgen05.ld -> bias/activation -> bf16 -> 64B-swizzled smem staging -> ONE TMA store per warp and
+//              32-channel half (cp.async.bulk.tensor, bulk-group completion).  The tensor map clips tile edges
+//              and the garbage rows of the batch-flattened row space, so the store path has no per-pixel
+//              address or validity math and no LDS / STG pass through the L1 data pipe — which the operand
+//              fetch of the MMAs shares and which bounds the C_out = 64 layers (ncu, profiles/r02_*).
 #pragma once
 #include <type_traits>
 #include "ptx.cuh"
@@ -38,21 +39,21 @@ constexpr int IG_BAR_BYTES = 2048;     // mbarriers + TMEM base slot
 #ifndef NIND_SETS64
 #define NIND_SETS64 4
 #endif
-// EXPERIMENTAL pixel-pair mode for the C_out = 64 3x3 layers (see the comment above igemm_kernel): compiled only
-// with -DNIND_PAIR_MODE=1.  With the default 0 every line it touches is the round-1 code that was measured.
-#ifndef NIND_PAIR_MODE
-#define NIND_PAIR_MODE 0
+#ifndef NIND_SETS_PM
+#define NIND_SETS_PM 2
 #endif
 #ifndef NIND_EPI_X16
 #define NIND_EPI_X16 1
 #endif
 constexpr int IG_MAX_SETS = 4;         // epilogue warp sets (= TMEM accumulator stages)
-constexpr int IG_EPI_BYTES = IG_MAX_SETS * 3072;  // per set: staged bias [2][256] fp32 + head weights [3][64]+[3]
+constexpr int IG_EPI_BYTES = IG_MAX_SETS * 3072;  // per set: staged bias [2][256] fp32 (+ spare)
 constexpr int IG_SET_STAGE_BYTES = 8192;          // per set: 4 warps x 32 rows x 64 B of store staging
 // Epilogue sets per kernel: N_TILE = 64 layers are epilogue-bound with two sets (their MMA phase per tile
 // is short), and their accumulators are small, so they get four (B200 A/B, same box: 64->64 572 / 651 / 680 TFLOP/s with 2 / 3 / 4 sets).
-__host__ __device__ constexpr int ig_sets(int n_tile) { return n_tile == 64 ? NIND_SETS64 : 2; }
-__host__ __device__ constexpr int ig_threads(int n_tile) { return 128 + 128 * ig_sets(n_tile); }
+__host__ __device__ constexpr int ig_sets(int n_tile, bool pm = false) {
+  return pm ? NIND_SETS_PM : (n_tile == 64 ? NIND_SETS64 : 2);
+}
+__host__ __device__ constexpr int ig_threads(int n_tile, bool pm = false) { return 128 + 128 * ig_sets(n_tile, pm); }
 constexpr int IG_TILE_H = 16;
 constexpr int IG_TILE_W = 8;
 
@@ -75,6 +76,10 @@ struct IgemmParams {
   int epi_mode, act;
   float slope;
   const float* bias;
+  // TMA-store modes (16x8 tiles): destination = tensor maps tmC4 / tmC1 over the destination's interior
+  // [C][sub-x][x][y][image]; c_coff = first channel of the layer's range in the destination buffer
+  int c_coff;
+  // flat-tile modes: per-pixel stores through `out`
   __nv_bfloat16* out;      // already offset by halo and channel offset
   long long o_img, o_row;  // element strides
   int o_pix;
@@ -89,7 +94,7 @@ struct IgemmParams {
   __nv_bfloat16* pool_out; // already offset by halo; null = no pooling
   long long pl_img, pl_row;
   int pl_pix;
-  // EPI_HEAD: 1x1 conv to 3 channels (+ optional sigmoid), fp32 planar output
+  // EPI_HEAD: 1x1 conv to 3 channels (+ optional sigmoid / clamp), fp32 planar output
   float head_c[196];       // [3][64] weights + [3] bias (copied from the device arrays when the launch is built)
   float* head_out;
   long long h_img, h_plane;
@@ -97,7 +102,9 @@ struct IgemmParams {
   int h_unpad;             // output pixel (y,x) -> (y-h_unpad, x-h_unpad)
   int h_size_y, h_size_x;  // output plane size
   int head_sigmoid;
-  int* err;
+  int head_clamp;          // clip(0,1) of the output (Generator.denoise_batch, nn_common.py:198-199)
+  int* err;                // mapped host memory: role code of a pipeline time-out
+  long long wait_cycles;   // bound of every mbarrier wait (SM cycles)
   long long* trace;        // optional [64 tiles][8 events] clock64 stamps written by CTA 0 (debug)
 };
 
@@ -108,11 +115,12 @@ enum { TR_A_ISSUE = 0, TR_MMA_TEMPTY = 1, TR_MMA_AFULL = 2, TR_MMA_DONE = 3, TR_
   do {                                                                                      \
     if (p.trace && blockIdx.x == 0 && (tl) < 64 && lane == 0) p.trace[(tl) * 8 + (ev)] = clock64(); \
   } while (0)
+#define NIND_MBW(bar, parity, code) mbar_wait((bar), (parity), p.err, (code), p.wait_cycles)
 
 __host__ __device__ inline size_t igemm_smem_bytes(int n_tile, int tps, int cg, int sa, uint32_t a_stage_bytes,
-                                                   int sb) {
+                                                   int sb, bool pm = false) {
   return 1024 + (size_t)sa * a_stage_bytes + (size_t)sb * tps * (n_tile / cg) * 128 + IG_BAR_BYTES +
-         IG_EPI_BYTES + (size_t)ig_sets(n_tile) * IG_SET_STAGE_BYTES;
+         IG_EPI_BYTES + (size_t)ig_sets(n_tile, pm) * IG_SET_STAGE_BYTES;
 }
 
 // N_TILE: GEMM N per tile (64/128/256).  TPS: taps per weight pipeline stage (1 or 3).
@@ -126,30 +134,25 @@ __host__ __device__ inline size_t igemm_smem_bytes(int n_tile, int tps, int cg, 
 // WITHOUT swizzle, and one K=16 MMA covers two taps x 8 channels through the no-swizzle descriptor's
 // leading-dimension offset (LBO = distance between the two taps' pixels, SBO = one patch row); five MMAs
 // per tile (the tenth half-K has zero weights).  Descriptor semantics verified by `tools/probe desc0`.
-#if NIND_PAIR_MODE
-// PM ("pixel pair", EXPERIMENTAL, off by default, not yet validated on hardware): a C_out = 64 3x3 layer as an
-// N = 128 GEMM over the NHWC input viewed as [rows, W/2, 2C]: GEMM row = a pair of x-adjacent pixels, GEMM
-// columns = (pixel of the pair a, c_out).  Output pixel 2P+a reads input pixels 2P+a .. 2P+a+2 = pair P+j,
-// pixel e with kx = 2j + e - a.  Per 64-channel chunk of input pixel e and kernel row ky this is one N = 128
-// MMA (pair tap j = 1-e: both output pixels) and one N = 64 MMA (j = e: only output pixel a = e, written to
-// its half of the accumulator) — the same FLOPs as the 3x3 form, but 12 instead of 18 A-operand fetches per
-// 256 output pixels, which is what bounds the N_TILE = 64 kernels (tests/test_pair_reformulation.py has
-// the algebra).  Weights are resident; tools/probe `pair` checks it against the naive convolution.
+// PM ("pixel pair"): a C_out = 64 3x3 layer as an N = 128 GEMM over the NHWC input viewed as [rows, W/2, 2C]:
+// GEMM row = a pair of x-adjacent pixels, GEMM columns = (pixel of the pair a, c_out).  Output pixel 2P+a
+// reads input pixels 2P+a .. 2P+a+2 = pair P+j, pixel e with kx = 2j + e - a.  Per 64-channel chunk of input
+// pixel e and kernel row ky this is one N = 128 MMA (pair tap j = 1-e: both output pixels) and one N = 64 MMA
+// (j = e: only output pixel a = e, written to its half of the accumulator) — the same FLOPs as the 3x3 form,
+// but 12 instead of 18 A-operand fetches per 256 output pixels, which is what bounds the N_TILE = 64 kernels
+// (tests/test_pair_reformulation.py has the algebra; validated on B200 by `tools/probe conv ... pair=1`,
+// profiles/r02_pair_mode_first_light.log).  Weights are resident.
 template <int N_TILE, int TPS, int CG, bool C8 = false, bool PM = false>
-#else
-template <int N_TILE, int TPS, int CG, bool C8 = false>
-#endif
-__global__ void __launch_bounds__(ig_threads(N_TILE), 1)
+__global__ void __launch_bounds__(ig_threads(N_TILE, PM), 1)
 igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+             const __grid_constant__ CUtensorMap tmC4, const __grid_constant__ CUtensorMap tmC1,
              const IgemmParams p) {
-#if NIND_PAIR_MODE
   static_assert(!PM || (N_TILE == 128 && CG == 2 && TPS == 1 && !C8), "pair mode is N_TILE 128 on CTA pairs");
-#endif
   extern __shared__ uint8_t smem_raw[];
   constexpr uint32_t B_ROWS = N_TILE / CG;           // weight rows held by this CTA
   constexpr uint32_t B_TAP_BYTES = B_ROWS * 128;
   constexpr uint32_t B_BYTES = TPS * B_TAP_BYTES;
-  constexpr int ES = ig_sets(N_TILE);  // epilogue sets = accumulator stages
+  constexpr int ES = ig_sets(N_TILE, PM);  // epilogue sets = accumulator stages
   constexpr uint32_t TMEM_COLS = ES * N_TILE <= 128 ? 128 : (ES * N_TILE <= 256 ? 256 : 512);
   constexpr uint32_t IDESC = umma_idesc_bf16(128 * CG, N_TILE);
   const uint32_t cg_rank = CG == 2 ? cluster_ctarank() : 0u;
@@ -178,7 +181,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       mbar_init(a_full + 8 * s, 1);
       mbar_init(a_empty + 8 * s, 1);
     }
-    for (int s = 0; s < p.sb; ++s) {
+    for (int s = 0; s < p.sb && s < IG_MAX_STAGES; ++s) {
       mbar_init(b_full + 8 * s, 1);
       mbar_init(b_empty + 8 * s, 1);
     }
@@ -219,7 +222,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         int yt = r / p.tiles_x, xt = r - yt * p.tiles_x;
         if (CG == 2) { if (p.pair_y) yt = yt * 2 + (int)cg_rank; else xt = xt * 2 + (int)cg_rank; }
         for (int kc = 0; kc < p.kchunks; ++kc) {
-          mbar_wait(a_empty + 8 * s, ph ^ 1, p.err, 1);
+          NIND_MBW(a_empty + 8 * s, ph ^ 1, 1);
           if (kc == 0) NIND_TRACE(tl, TR_A_ISSUE);
           if (p.flat) {  // yt is the flat tile index (tiles_x == 1, pairs along "y")
             if (CG == 2) {
@@ -231,6 +234,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
             }
           } else if (CG == 2) {
             // both CTAs' patches complete on the leader's barrier; only the leader arms it
+            // (pair mode: kc walks the [2C] channel axis of the pixel-pair view, xt counts tiles of 8 pairs)
             if (cg_rank == 0) mbar_arrive_expect_tx(a_full + 8 * s, 2 * p.a_tx_bytes);
             tma_load_3d_cg2(a_base + s * p.a_stage_bytes, &tmA, mapa_shared(a_full + 8 * s, 0), kc * 64,
                             xt * IG_TILE_W, yt * IG_TILE_H);
@@ -256,7 +260,6 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         mbar_arrive_expect_tx(b_full, 10240);
         tma_load_3d(b_base, &tmB, b_full, 0, 0, 0);
       }
-#if NIND_PAIR_MODE
       if (PM) {  // resident weights: per (chunk, ky) one block of 64 (N=128 MMA) + 32 (N=64 MMA) rows per CTA
         const int blocks = p.kchunks * 3;
         if (cg_rank == 0) mbar_arrive_expect_tx(b_full, 2u * blocks * 12288u);
@@ -265,14 +268,11 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
           tma_load_2d_cg2(b_base + g * 12288, &tmB, bar, 0, ((int)cg_rank * blocks + g) * 96);
       }
       for (int tile = tile0; tile < p.total_tiles && !C8 && !PM; tile += tstep, ++tl) {
-#else
-      for (int tile = tile0; tile < p.total_tiles && !C8; tile += tstep, ++tl) {
-#endif
         if (p.ws && tl > 0) break;
         const int nt = tile / tiles_xy;
         for (int kc = 0; kc < p.kchunks; ++kc) {
           for (int g = 0; g < groups; ++g) {
-            if (!p.ws) mbar_wait(b_empty + 8 * s, ph ^ 1, p.err, 2);
+            if (!p.ws) NIND_MBW(b_empty + 8 * s, ph ^ 1, 2);
             if (CG == 2) {
               if (cg_rank == 0) mbar_arrive_expect_tx(b_full + 8 * s, 2 * B_BYTES);
               const uint32_t bar = mapa_shared(b_full + 8 * s, 0);
@@ -302,15 +302,15 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     uint32_t sa_i = 0, pha = 0, sb_i = 0, phb = 0, acc = 0, aph = 0;
     int tl = 0;
     for (int tile = tile0; tile < p.total_tiles; tile += tstep, ++tl) {
-      mbar_wait(t_empty + 8 * acc, aph ^ 1, p.err, 3);
+      NIND_MBW(t_empty + 8 * acc, aph ^ 1, 3);
       tc_fence_after();
       NIND_TRACE(tl, TR_MMA_TEMPTY);
       const uint32_t d = tmem_base + acc * N_TILE;
       uint32_t accum = 0;
       if (C8) {
-        mbar_wait(a_full + 8 * sa_i, pha, p.err, 4);
+        NIND_MBW(a_full + 8 * sa_i, pha, 4);
         NIND_TRACE(tl, TR_MMA_AFULL);
-        if (tl == 0) mbar_wait(b_full, 0, p.err, 5);
+        if (tl == 0) NIND_MBW(b_full, 0, 5);
         tc_fence_after();
         // patch pixel (py, px) lives at (py*10 + px) * 16 B; tap t = ky*3 + kx
         constexpr uint32_t HI_A = (160u >> 4) | (1u << 14);            // SBO = one patch row (10 px), no swizzle
@@ -331,14 +331,13 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         __syncwarp();
         if (++sa_i == (uint32_t)p.sa) { sa_i = 0; pha ^= 1; }
       }
-#if NIND_PAIR_MODE
       if (PM) {
         constexpr uint32_t IDESC64 = umma_idesc_bf16(256, 64);
         const int half_chunks = p.kchunks >> 1;
         for (int kc = 0; kc < p.kchunks; ++kc) {
-          mbar_wait(a_full + 8 * sa_i, pha, p.err, 4);
+          NIND_MBW(a_full + 8 * sa_i, pha, 4);
           if (kc == 0) NIND_TRACE(tl, TR_MMA_AFULL);
-          if (tl == 0 && kc == 0) mbar_wait(b_full, 0, p.err, 5);
+          if (tl == 0 && kc == 0) NIND_MBW(b_full, 0, 5);
           tc_fence_after();
           const uint32_t e = kc >= half_chunks ? 1u : 0u;  // which pixel of the input pair this chunk holds
           const uint32_t a_lo0 = (((a_base + sa_i * p.a_stage_bytes) >> 4) & 0x3FFF) | (1u << 16);
@@ -366,15 +365,12 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         }
       }
       for (int kc = 0; kc < p.kchunks && !C8 && !PM; ++kc) {
-#else
-      for (int kc = 0; kc < p.kchunks && !C8; ++kc) {
-#endif
-        mbar_wait(a_full + 8 * sa_i, pha, p.err, 4);
+        NIND_MBW(a_full + 8 * sa_i, pha, 4);
         if (kc == 0) NIND_TRACE(tl, TR_MMA_AFULL);
         const uint32_t a_lo0 = (((a_base + sa_i * p.a_stage_bytes) >> 4) & 0x3FFF) | (1u << 16);
         uint32_t ky = 0, kx = 0;  // tap of the first MMA of the group
         for (int g = 0; g < groups; ++g) {
-          if (!(p.ws && tl > 0)) mbar_wait(b_full + 8 * sb_i, phb, p.err, 5);
+          if (!(p.ws && tl > 0)) NIND_MBW(b_full + 8 * sb_i, phb, 5);
           tc_fence_after();
           const uint32_t a_lo = a_lo0 + ky * pitch16 + kx * 8;  // (ky*pitch + kx) rows of 128 B
           const uint32_t b_lo = (((b_base + sb_i * B_BYTES) >> 4) & 0x3FFF) | (1u << 16);
@@ -431,16 +427,20 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     const int etid = threadIdx.x - 128 - eset * 128;  // 0..127 inside the set
     uint8_t* smem_gen = smem_raw + (sbase - smem_u32(smem_raw));
     float* bias_s = reinterpret_cast<float*>(smem_gen + (epi_base - sbase) + eset * 3072);  // [2][256] per set
-    uint8_t* stg = smem_gen + (stg_base - sbase) + (eset * 4 + quarter) * 2048;  // 32 rows x 64 B
+    const uint32_t stg_off = (stg_base - sbase) + (eset * 4 + quarter) * 2048;
+    uint8_t* stg = smem_gen + stg_off;       // this warp's staging: 32 rows x 64 B, rows = (tile row, pixel)
+    const uint32_t stg_s = sbase + stg_off;  // same, shared-space address (TMA source)
     constexpr int n_groups = N_TILE / 64;
-    constexpr int CW = (N_TILE == 64 && NIND_EPI_X16) ? 16 : 32;  // accumulator columns per TMEM load
+    constexpr int CW = ((N_TILE == 64 && NIND_EPI_X16) || (PM && ig_sets(N_TILE, PM) > 2)) ? 16 : 32;  // accumulator columns per TMEM load
     const uint32_t acc = eset;
     const uint32_t t_empty_addr = CG == 2 ? mapa_shared(t_empty + 8 * acc, 0) : (t_empty + 8 * acc);
-    // Lane roles.  TMEM side: thread = accumulator row (pixel quarter*32 + lane), registers = channels.
-    // Store side: 4 lanes cover one pixel's 32 channels (64 B); lane (sub, ch) writes pixel column `sub` of
-    // the warp's four tile rows, so its four destinations are plain per-tile integer math (no shuffles).
+    // Lane roles.  TMEM side: thread = accumulator row (pixel quarter*32 + lane), registers = channels; it writes
+    // its 32 channels as four 16-byte chunks of staging row `lane`, chunk index XORed with (lane >> 1) & 3 — the
+    // TMA 64B swizzle, bank-conflict free for these row-wise writes.
+    // Read side (fused pool, flat tiles): 4 lanes cover one pixel's 32 channels; lane (sub, ch) reads pixel
+    // column `sub` of the warp's four tile rows.
     const int sub = lane >> 2, ch = lane & 3;
-    uint8_t* const stg_w = stg + lane * 64;               // this thread's staging row (16-byte chunks swizzled)
+    uint8_t* const stg_w = stg + lane * 64;
     const int sw_w = (lane >> 1) & 3;
     const uint8_t* const stg_r = stg + sub * 64 + ((ch ^ ((sub >> 1) & 3)) << 4);  // + it * 512
     // fused 2x2 max-pool: lane -> (pooled pixel sub, 16-byte chunk ch); source rows r00, +1, +8, +9
@@ -448,11 +448,13 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     const uint8_t* const stg_p = stg + r00 * 64 + ((ch ^ ((r00 >> 1) & 3)) << 4);
 
     // The tile loop is instantiated per (store mode, activation) so that nothing is decided per element:
-    // MODE 0 store, 1 store + fused max-pool, 2 depth-to-space, 3 fused 1x1 head;
+    // MODE 0 store, 1 store + fused max-pool, 2 depth-to-space (all three: TMA stores), 3 fused 1x1 head,
+    //      4 flat-tile store, 5 flat-tile depth-to-space (per-pixel 16-byte stores);
     // ACT 0 none, 1 PReLU/ReLU with 0 <= slope <= 1 (max(x, a*x)), 2 anything else.
     auto run = [&](auto mode_c, auto act_c) {
       constexpr int MODE = decltype(mode_c)::value;
       constexpr int ACT = decltype(act_c)::value;
+      constexpr bool HEAD = MODE == 3, TMA = MODE < 3, D2S = MODE == 2 || MODE == 5, POOL = MODE == 1;
       int prev_nt = -1, bsel = 1;
       uint32_t aph = 0;
       int tl = eset;
@@ -468,114 +470,82 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
           for (int i = etid; i < N_TILE; i += 128) {
             const int n = nt * N_TILE + i;
             float bv = 0.f;
-#if NIND_PAIR_MODE
             if (PM) bv = __ldg(p.bias + (i & 63));  // columns = (pixel of the pair, c_out)
-            else if (n < p.n_total) bv = __ldg(p.bias + (MODE == 2 ? n % p.d2s_cout : n));
-#else
-            if (n < p.n_total) bv = __ldg(p.bias + (MODE == 2 ? n % p.d2s_cout : n));
-#endif
+            else if (n < p.n_total) bv = __ldg(p.bias + (D2S ? n % p.d2s_cout : n));
             bias_s[bsel * 256 + i] = bv;
           }
           asm volatile("bar.sync %0, 128;" ::"r"(eset + 1) : "memory");
         }
 
         // ---- per-tile destination geometry
-        // (element offsets fit 32 bits: build_igemm rejects larger destination buffers)
-        uint32_t dst[4];            // MODE 0..2: channel 0 of the layer's range at this lane's four pixels
-        uint32_t vmask = 0;         //            which of them exist
-        uint32_t pdst = 0;
-        bool pvalid = false;        // MODE 1: pooled pixel
-#if NIND_PAIR_MODE
-        uint32_t pdst1 = 0, pvmask = 0;  // MODE 1, pair mode: second pooled row of this lane; validity bits
-        uint4 pkeep[2][2];          // MODE 1, pair mode: vertical maxima of the pair's first pixel [half][row pair]
-#endif
-        float* hdst = nullptr;      // MODE 3: this thread's output pixel (nullptr: none)
-#if NIND_PAIR_MODE
-        float* hdst1 = nullptr;     //         pair mode: the second pixel of this thread's pair
-#endif
-        if (MODE == 3) {
+        const int yf0 = yt * IG_TILE_H + quarter * 4;  // first of this warp's four (batch-flattened) tile rows
+        int tb = 0, ty = 0;         // TMA modes: image and row of yf0
+        bool one_box = false;       //            the four rows lie in one image: a single 4-row box
+        uint32_t dst[4];            // flat modes: channel 0 of the layer's range at this lane's four pixels
+        uint32_t vmask = 0;         //             which of them exist
+        uint32_t pdst = 0, pdst1 = 0, pvmask = 0;  // POOL: pooled pixel(s) of this lane (pair mode: two rows)
+        uint4 pkeep[2][2];          // POOL, pair mode: vertical maxima of the pair's first pixel [half][row pair]
+        float* hdst = nullptr;      // HEAD: this thread's output pixel (nullptr: none)
+        float* hdst1 = nullptr;     //       pair mode: the second pixel of this thread's pair
+        if (HEAD) {
           const int row = quarter * 32 + lane;
           const int yflat = yt * IG_TILE_H + (row >> 3);
-#if NIND_PAIR_MODE
           const int x = (xt * IG_TILE_W + (row & 7)) * (PM ? 2 : 1);
-#else
-          const int x = xt * IG_TILE_W + (row & 7);
-#endif
           const int b = yflat / p.hs_in;
           const int y = yflat - b * p.hs_in;
           const int oy = y - p.h_unpad, ox = x - p.h_unpad;
-#if NIND_PAIR_MODE
           const bool row_ok = (yflat < p.rows_total) && (y < p.h_valid) && oy >= 0 && oy < p.h_size_y;
           if (row_ok && (x < p.w_valid) && ox >= 0 && ox < p.h_size_x)
-#else
-          if ((yflat < p.rows_total) && (y < p.h_valid) && (x < p.w_valid) && oy >= 0 && ox >= 0 && oy < p.h_size_y &&
-              ox < p.h_size_x)
-#endif
             hdst = p.head_out + b * p.h_img + (long long)oy * p.h_row + ox;
-#if NIND_PAIR_MODE
           if (PM && row_ok && (x + 1 < p.w_valid) && ox + 1 >= 0 && ox + 1 < p.h_size_x)
             hdst1 = p.head_out + b * p.h_img + (long long)oy * p.h_row + ox + 1;
-#endif
+        } else if (TMA) {
+          tb = yf0 / p.hs_in;
+          ty = yf0 - tb * p.hs_in;
+          one_box = !D2S && (ty + 3 < p.hs_in);
+          if (POOL) {
+            // pooled pixel of this lane: tile origins and map sizes are even, so the validity of the top-left
+            // source pixel covers all four
+            if (PM) {  // lane column `sub` is a pixel pair = one pooled column; rows (0,1) and (2,3)
+              const int xo = xt * IG_TILE_W + sub;
+#pragma unroll
+              for (int m = 0; m < 2; ++m) {
+                int b = tb, y = ty + 2 * m;
+                if (y >= p.hs_in) { y -= p.hs_in; ++b; }
+                const uint32_t po = (uint32_t)(b * p.pl_img + (long long)(y >> 1) * p.pl_row + (long long)xo * p.pl_pix) + ch * 8;
+                if (m == 0) pdst = po; else pdst1 = po;
+                pvmask |= (uint32_t)((yf0 + 2 * m < p.rows_total) && (y < p.h_valid) && (2 * xo < p.w_valid)) << m;
+              }
+            } else {
+              const int xp = xt * IG_TILE_W + (sub & 3) * 2, pit = (sub >> 2) * 2;
+              int b = tb, y = ty + pit;
+              if (y >= p.hs_in) { y -= p.hs_in; ++b; }
+              pdst = (uint32_t)(b * p.pl_img + (long long)(y >> 1) * p.pl_row + (long long)(xp >> 1) * p.pl_pix) + ch * 8;
+              pvmask = (uint32_t)((yf0 + pit < p.rows_total) && (y < p.h_valid) && (xp < p.w_valid));
+            }
+          }
         } else {
-          if (p.flat) {
-            // flat tile: this lane's four pixels are 8 apart in the row-major (b, y, x) index space
-            const int i0 = yt * 128 + quarter * 32 + sub;
+          // flat tile: this lane's four pixels are 8 apart in the row-major (b, y, x) index space
+          // (element offsets fit 32 bits: build_igemm rejects larger destination buffers)
+          const int i0 = yt * 128 + quarter * 32 + sub;
 #pragma unroll
-            for (int it = 0; it < 4; ++it) {
-              const int i = i0 + it * 8;
-              const int yf = i / p.flat_pitch;
-              const int x = i - yf * p.flat_pitch;
-              const int b = yf / p.hs_in;
-              const int y = yf - b * p.hs_in;
-              vmask |= (uint32_t)((yf < p.rows_total) && (y < p.h_valid) && (x < p.w_valid)) << it;
-              const long long o = MODE == 2 ? b * p.o_img + (long long)(2 * y) * p.o_row + (long long)(2 * x) * p.o_pix
-                                            : b * p.o_img + (long long)y * p.o_row + (long long)x * p.o_pix;
-              dst[it] = (uint32_t)o + ch * 8;
-            }
-          } else {
-#if NIND_PAIR_MODE
-            // pair mode: lane column `sub` is a pixel PAIR; dst[] addresses its first pixel (the second one is
-            // the next 64-column group, one pixel further)
-            const int x = (xt * IG_TILE_W + sub) * (PM ? 2 : 1);
-#else
-            const int x = xt * IG_TILE_W + sub;
-#endif
-            const int yf0 = yt * IG_TILE_H + quarter * 4;
-            int b = yf0 / p.hs_in;
-            int y = yf0 - b * p.hs_in;
-            const int xp = xt * IG_TILE_W + (sub & 3) * 2, pit = (sub >> 2) * 2;
-#pragma unroll
-            for (int it = 0; it < 4; ++it) {
-              const bool row_ok = (yf0 + it < p.rows_total) && (y < p.h_valid);
-              vmask |= (uint32_t)(row_ok && (x < p.w_valid)) << it;
-              const long long o = MODE == 2 ? b * p.o_img + (long long)(2 * y) * p.o_row + (long long)(2 * x) * p.o_pix
-                                            : b * p.o_img + (long long)y * p.o_row + (long long)x * p.o_pix;
-              dst[it] = (uint32_t)o + ch * 8;
-#if NIND_PAIR_MODE
-              if (MODE == 1 && !PM && it == pit) {
-#else
-              if (MODE == 1 && it == pit) {
-#endif
-                pdst = (uint32_t)(b * p.pl_img + (long long)(y >> 1) * p.pl_row + (long long)(xp >> 1) * p.pl_pix) + ch * 8;
-                pvalid = row_ok && (xp < p.w_valid);
-#if NIND_PAIR_MODE
-              }
-              if (MODE == 1 && PM && !(it & 1)) {  // pooled pixel (pair index, row pair it/2); even map sizes
-                const uint32_t po = (uint32_t)(b * p.pl_img + (long long)(y >> 1) * p.pl_row +
-                                               (long long)(x >> 1) * p.pl_pix) + ch * 8;
-                if (it == 0) pdst = po; else pdst1 = po;
-                pvmask |= (uint32_t)(row_ok && (x < p.w_valid)) << (it >> 1);
-#endif
-              }
-              if (++y == p.hs_in) { y = 0; ++b; }
-            }
+          for (int it = 0; it < 4; ++it) {
+            const int i = i0 + it * 8;
+            const int yf = i / p.flat_pitch;
+            const int x = i - yf * p.flat_pitch;
+            const int b = yf / p.hs_in;
+            const int y = yf - b * p.hs_in;
+            vmask |= (uint32_t)((yf < p.rows_total) && (y < p.h_valid) && (x < p.w_valid)) << it;
+            const long long o = D2S ? b * p.o_img + (long long)(2 * y) * p.o_row + (long long)(2 * x) * p.o_pix
+                                    : b * p.o_img + (long long)y * p.o_row + (long long)x * p.o_pix;
+            dst[it] = (uint32_t)o + ch * 8;
           }
         }
         // number of 64-column groups of this tile that hold real output columns
         int live = (p.n_total - nt * N_TILE + 63) / 64;
         live = live > n_groups ? n_groups : live;
 
-        mbar_wait(t_full + 8 * acc, aph, p.err, 6);
+        NIND_MBW(t_full + 8 * acc, aph, 6);
         tc_fence_after();
         if (quarter == 0) NIND_TRACE(tl, TR_EPI_TFULL);
         const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * N_TILE;
@@ -584,18 +554,22 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
 #pragma unroll 1
         for (int c64 = 0; c64 < live; ++c64) {
           const int n = nt * N_TILE + c64 * 64;
-#if NIND_PAIR_MODE
-          uint32_t extra = PM ? (uint32_t)(c64 * p.o_pix) : (uint32_t)n;  // offset of this group's first channel from dst[]
-#else
-          uint32_t extra = n;  // element offset of this group's first channel from dst[]
-#endif
-          if (MODE == 2) {
+          // where this 64-column group goes: TMA coordinates (channel, sub-x, row step) / flat element offset
+          int c_chan = p.c_coff + n, c_sx = 0, c_dy = 0;
+          uint32_t extra = n;  // flat modes: element offset of this group's first channel from dst[]
+          if (PM) {
+            c_chan = p.c_coff;
+            c_sx = c64;
+          } else if (D2S) {
             const int q = n / p.d2s_cout;
+            c_chan = p.c_coff + (n - q * p.d2s_cout);
+            c_sx = q & 1;
+            c_dy = q >> 1;
             extra = (uint32_t)((long long)(q >> 1) * p.o_row + (long long)(q & 1) * p.o_pix + (n - q * p.d2s_cout));
           }
 #pragma unroll
           for (int half = 0; half < 2; ++half) {
-            // CW accumulator columns at a time (16 for the 640-thread N_TILE = 64 kernels, whose 96-register
+            // CW accumulator columns at a time (16 for the 640-thread kernels, whose 96-register
             // budget a 32-wide chunk overflows)
 #pragma unroll
             for (int q = 0; q < 32 / CW; ++q) {
@@ -645,7 +619,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
                   for (int j = 0; j < CW; ++j) f[j] = f[j] * fminf(fmaxf(f[j] + 3.f, 0.f), 6.f) * (1.f / 6.f);
                 }
               }
-              if (MODE == 3) {
+              if (HEAD) {
                 // 1x1 head: three dot products over this pixel's 64 channels.  The weights are kernel
                 // parameters, i.e. constant-bank operands of the FFMAs: no shared-memory reads in a kernel
                 // whose shared-memory pipe is the bottleneck.
@@ -656,8 +630,11 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
                   h2 = fmaf(f[j], p.head_c[128 + half * 32 + q * CW + j], h2);
                 }
               } else {
-                // this thread's channels -> staging row (64 B per half); 16-byte chunks XOR-swizzled so that
-                // both the row-wise writes and the pixel-wise reads below are bank-conflict free
+                if (TMA && q == 0) {  // the TMA store of the previous half has finished reading the staging rows
+                  if (lane == 0) bulk_wait_group_read<0>();
+                  __syncwarp();
+                }
+                // this thread's channels -> staging row (64 B per half), 16-byte chunks XOR-swizzled
 #pragma unroll
                 for (int j = 0; j < CW / 8; ++j) {
                   uint4 o;
@@ -669,30 +646,18 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
                 }
               }
             }
-            if (MODE != 3) {
+            if (TMA) {
+              fence_proxy_async_smem();
               __syncwarp();
-              // coalesced write-out: 8 pixels x 64 B per warp instruction
-              const uint32_t e = extra + half * 32;
-#if NIND_PAIR_MODE
-              uint4 ov[4];
-#endif
-#pragma unroll
-              for (int it = 0; it < 4; ++it) {
-                const uint4 o = *reinterpret_cast<const uint4*>(stg_r + it * 512);
-                if (vmask & (1u << it)) *reinterpret_cast<uint4*>(p.out + (dst[it] + e)) = o;
-#if NIND_PAIR_MODE
-                if (MODE == 1 && PM) ov[it] = o;
-#endif
-              }
-#if NIND_PAIR_MODE
-              if (MODE == 1 && PM) {
-                // fused 2x2 max-pool across the two column groups: rows (0,1) and (2,3) of this lane's pair
-                // column reduce in registers; group 0 (first pixel) is kept until group 1 arrives
+              if (POOL && PM) {
+                // fused 2x2 max-pool across the two column groups (= the two pixels of a pair): rows (0,1) and
+                // (2,3) of this lane's pair column reduce in registers; group 0 is kept until group 1 arrives
 #pragma unroll
                 for (int m = 0; m < 2; ++m) {
-                  uint4 v = ov[2 * m];
+                  uint4 v = *reinterpret_cast<const uint4*>(stg_r + (2 * m) * 512);
+                  const uint4 w = *reinterpret_cast<const uint4*>(stg_r + (2 * m + 1) * 512);
                   __nv_bfloat162* pv = reinterpret_cast<__nv_bfloat162*>(&v);
-                  const __nv_bfloat162* pw = reinterpret_cast<const __nv_bfloat162*>(&ov[2 * m + 1]);
+                  const __nv_bfloat162* pw = reinterpret_cast<const __nv_bfloat162*>(&w);
 #pragma unroll
                   for (int q4 = 0; q4 < 4; ++q4) pv[q4] = __hmax2(pv[q4], pw[q4]);
                   if (c64 == 0) {
@@ -702,16 +667,11 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
 #pragma unroll
                     for (int q4 = 0; q4 < 4; ++q4) pv[q4] = __hmax2(pv[q4], pk[q4]);
                     if (pvmask & (1u << m))
-                      *reinterpret_cast<uint4*>(p.pool_out + ((m ? pdst1 : pdst) + nt * 64 + half * 32)) = v;
+                      *reinterpret_cast<uint4*>(p.pool_out + ((m ? pdst1 : pdst) + half * 32)) = v;
                   }
                 }
-              } else if (MODE == 1) {
-#else
-              if (MODE == 1) {
-#endif
-                // fused 2x2 max-pool: this warp's 32 rows are 4 tile rows x 8 pixels = 2 x 4 pooled pixels;
-                // tile origins and map sizes are even, so the validity of the top-left source pixel covers
-                // all four
+              } else if (POOL) {
+                // this warp's 32 rows are 4 tile rows x 8 pixels = 2 x 4 pooled pixels
                 uint4 m = *reinterpret_cast<const uint4*>(stg_p);
                 const int rs[3] = {64, 512, 576};
 #pragma unroll
@@ -720,15 +680,37 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
                   __nv_bfloat162* pm = reinterpret_cast<__nv_bfloat162*>(&m);
                   const __nv_bfloat162* pt = reinterpret_cast<const __nv_bfloat162*>(&t);
 #pragma unroll
-                  for (int q = 0; q < 4; ++q) pm[q] = __hmax2(pm[q], pt[q]);
+                  for (int q4 = 0; q4 < 4; ++q4) pm[q4] = __hmax2(pm[q4], pt[q4]);
                 }
-                if (pvalid) *reinterpret_cast<uint4*>(p.pool_out + (pdst + n + half * 32)) = m;
+                if (pvmask) *reinterpret_cast<uint4*>(p.pool_out + (pdst + n + half * 32)) = m;
+              }
+              if (lane == 0) {
+                const int cc = c_chan + half * 32, x0 = xt * IG_TILE_W;
+                if (one_box) {
+                  tma_store_5d(&tmC4, stg_s, cc, c_sx, x0, ty, tb);
+                } else {
+                  int b = tb, y = ty;
+#pragma unroll
+                  for (int it = 0; it < 4; ++it) {
+                    tma_store_5d(&tmC1, stg_s + it * 512, cc, c_sx, x0, D2S ? 2 * y + c_dy : y, b);
+                    if (++y == p.hs_in) { y = 0; ++b; }
+                  }
+                }
+                bulk_commit_group();
+              }
+            } else if (!HEAD) {
+              __syncwarp();
+              // flat tiles: coalesced write-out, 8 pixels x 64 B per warp instruction
+              const uint32_t e = extra + half * 32;
+#pragma unroll
+              for (int it = 0; it < 4; ++it) {
+                const uint4 o = *reinterpret_cast<const uint4*>(stg_r + it * 512);
+                if (vmask & (1u << it)) *reinterpret_cast<uint4*>(p.out + (dst[it] + e)) = o;
               }
               __syncwarp();
             }
           }
-#if NIND_PAIR_MODE
-          if (MODE == 3 && PM) {  // this column group was one pixel of the pair: write it, start the next
+          if (HEAD && PM) {  // this column group was one pixel of the pair: write it, start the next
             float* hd = c64 ? hdst1 : hdst;
             if (hd) {
               float o0 = h0 + p.head_c[192], o1 = h1 + p.head_c[193], o2 = h2 + p.head_c[194];
@@ -737,51 +719,85 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
                 o1 = 1.f / (1.f + __expf(-o1));
                 o2 = 1.f / (1.f + __expf(-o2));
               }
+              if (p.head_clamp) {
+                o0 = fminf(fmaxf(o0, 0.f), 1.f);
+                o1 = fminf(fmaxf(o1, 0.f), 1.f);
+                o2 = fminf(fmaxf(o2, 0.f), 1.f);
+              }
               hd[0] = o0;
               hd[p.h_plane] = o1;
               hd[2 * p.h_plane] = o2;
             }
             h0 = h1 = h2 = 0.f;
           }
-#endif
         }
         if (quarter == 0) NIND_TRACE(tl, TR_EPI_DONE);
-#if NIND_PAIR_MODE
-        if (MODE == 3 && !PM && hdst) {
-#else
-        if (MODE == 3 && hdst) {
-#endif
+        if (HEAD && !PM && hdst) {
           float o0 = h0 + p.head_c[192], o1 = h1 + p.head_c[193], o2 = h2 + p.head_c[194];
           if (p.head_sigmoid) {
             o0 = 1.f / (1.f + __expf(-o0));
             o1 = 1.f / (1.f + __expf(-o1));
             o2 = 1.f / (1.f + __expf(-o2));
           }
+          if (p.head_clamp) {
+            o0 = fminf(fmaxf(o0, 0.f), 1.f);
+            o1 = fminf(fmaxf(o1, 0.f), 1.f);
+            o2 = fminf(fmaxf(o2, 0.f), 1.f);
+          }
           hdst[0] = o0;
           hdst[p.h_plane] = o1;
           hdst[2 * p.h_plane] = o2;
         }
       }
+      // the staging rows must stay valid until the last TMA store has read them
+      if (TMA && lane == 0) bulk_wait_group<0>();
     };
-    const int mode = p.epi_mode == EPI_HEAD ? 3 : (p.epi_mode == EPI_D2S ? 2 : (p.pool_out ? 1 : 0));
+    const int mode = p.epi_mode == EPI_HEAD ? 3
+                     : (p.flat ? (p.epi_mode == EPI_D2S ? 5 : 4) : (p.epi_mode == EPI_D2S ? 2 : (p.pool_out ? 1 : 0)));
     const int actk = p.act == ACT_NONE ? 0 : ((p.act == ACT_PRELU && p.slope >= 0.f && p.slope <= 1.f) ? 1 : 2);
     using I0 = std::integral_constant<int, 0>;
     using I1 = std::integral_constant<int, 1>;
     using I2 = std::integral_constant<int, 2>;
     using I3 = std::integral_constant<int, 3>;
-    switch (mode * 3 + actk) {
-      case 0: run(I0{}, I0{}); break;
-      case 1: run(I0{}, I1{}); break;
-      case 2: run(I0{}, I2{}); break;
-      case 3: run(I1{}, I0{}); break;
-      case 4: run(I1{}, I1{}); break;
-      case 5: run(I1{}, I2{}); break;
-      case 6: run(I2{}, I0{}); break;
-      case 7: run(I2{}, I1{}); break;
-      case 8: run(I2{}, I2{}); break;
-      case 9: run(I3{}, I0{}); break;
-      case 10: run(I3{}, I1{}); break;
-      default: run(I3{}, I2{}); break;
+    using I4 = std::integral_constant<int, 4>;
+    using I5 = std::integral_constant<int, 5>;
+    if (PM) {  // 3x3 layers with C_out = 64 only: store / store + pool / head
+      switch ((mode == 3 ? 2 : mode) * 3 + actk) {
+        case 0: run(I0{}, I0{}); break;
+        case 1: run(I0{}, I1{}); break;
+        case 2: run(I0{}, I2{}); break;
+        case 3: run(I1{}, I0{}); break;
+        case 4: run(I1{}, I1{}); break;
+        case 5: run(I1{}, I2{}); break;
+        case 6: run(I3{}, I0{}); break;
+        case 7: run(I3{}, I1{}); break;
+        default: run(I3{}, I2{}); break;
+      }
+    } else if (C8) {  // first layer: plain store
+      switch (actk) {
+        case 0: run(I0{}, I0{}); break;
+        case 1: run(I0{}, I1{}); break;
+        default: run(I0{}, I2{}); break;
+      }
+    } else {
+      switch (mode * 3 + actk) {
+        case 0: run(I0{}, I0{}); break;
+        case 1: run(I0{}, I1{}); break;
+        case 2: run(I0{}, I2{}); break;
+        case 3: run(I1{}, I0{}); break;
+        case 4: run(I1{}, I1{}); break;
+        case 5: run(I1{}, I2{}); break;
+        case 6: run(I2{}, I0{}); break;   // depth-to-space layers (the 2x2/s2 up-convs) carry no activation;
+        case 7: case 8: run(I2{}, I2{}); break;  // anything else takes the generic path
+        case 9: run(I3{}, I0{}); break;
+        case 10: run(I3{}, I1{}); break;
+        case 11: run(I3{}, I2{}); break;
+        case 12: run(I4{}, I0{}); break;
+        case 13: run(I4{}, I1{}); break;
+        case 14: run(I4{}, I2{}); break;
+        case 15: run(I5{}, I0{}); break;
+        default: run(I5{}, I2{}); break;
+      }
     }
   }
 

@@ -1,6 +1,8 @@
 // Host side of the implicit-GEMM kernel: tensor-map encoding, tiling/pipeline choices, launch.
 #pragma once
 #include <cstdio>
+#include <cstdlib>
+#include <vector>
 #include <algorithm>
 #include <cstring>
 #include <string>
@@ -34,12 +36,10 @@ struct ConvSpec {
   const float* head_w = nullptr;
   const float* head_b = nullptr;
   float* head_out = nullptr;  // [B][3][hy][hx] fp32
-  int head_unpad = 0, head_hy = 0, head_hx = 0, head_sigmoid = 0;
+  int head_unpad = 0, head_hy = 0, head_hx = 0, head_sigmoid = 0, head_clamp = 0;
   // tuning
-#if NIND_PAIR_MODE
   bool pair = false;  // EXPERIMENTAL pixel-pair mode (C_out = 64 3x3 layers as N = 128 GEMMs); `w` must then point to
                       // the weights re-packed by pack_pair_weights()
-#endif
   int flat = -1;  // flat (1-D) tiles for narrow maps: -1 auto, 0 off, 1 force (error if illegal), 2 wherever legal
   int n_tile = 0;     // 0 = auto
   int cg = 0;         // CTAs per tile group: 0 = auto, 1, or 2 (cta_group::2 pair)
@@ -50,15 +50,14 @@ struct ConvSpec {
 
 struct IgemmLaunch {
   CUtensorMap tmA, tmB;
+  CUtensorMap tmC4, tmC1;  // destination (TMA-store epilogue): 4-row and 1-row boxes of 8 pixels x 32 channels
   IgemmParams p;
   int n_tile = 0, tps = 1, cg = 1;
   bool c8 = false;  // first layer: 3x3 conv over an 8-channel (16 B/pixel) tensor, no-swizzle descriptors
-#if NIND_PAIR_MODE
   bool pm = false;  // pixel-pair mode
-#endif
   size_t smem = 0;
   int grid = 0;
-  double flops = 0;  // algorithmic 2*MAC actually useful (valid outputs only)
+  double flops = 0;  // EXECUTED 2*MAC over the valid output pixels (see build_igemm)
 };
 
 typedef CUresult (*PFN_tmapEncodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
@@ -79,9 +78,10 @@ inline PFN_tmapEncodeTiled tmap_encoder() {
 }
 
 // bf16 tensor map, 128-byte swizzle, zero OOB fill.  dims/strides innermost first.
+// swizzle: 128 (default), 64, or 0 (none)
 inline bool encode_tmap_bf16(CUtensorMap* m, const void* base, int rank, const uint64_t* dims,
                              const uint64_t* strides_bytes /* rank-1 */, const uint32_t* box,
-                             std::string* why, bool swizzle128 = true) {
+                             std::string* why, int swizzle = 128) {
   PFN_tmapEncodeTiled enc = tmap_encoder();
   if (!enc) {
     if (why) *why = "cuTensorMapEncodeTiled entry point not available";
@@ -97,7 +97,8 @@ inline bool encode_tmap_bf16(CUtensorMap* m, const void* base, int rank, const u
   }
   CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), gd, gs,
                    bx, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                   swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE,
+                   swizzle == 128 ? CU_TENSOR_MAP_SWIZZLE_128B
+                                  : (swizzle == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_NONE),
                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     if (why) {
@@ -116,17 +117,17 @@ inline bool encode_tmap_bf16(CUtensorMap* m, const void* base, int rank, const u
 constexpr size_t IG_SMEM_LIMIT = 227 * 1024;
 
 inline int device_sm_count() {
-  static int n = 0;
-  if (!n) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
-    if (n <= 0) n = 148;
+  static int n[64] = {0};  // per device ordinal
+  int dev = 0;
+  cudaGetDevice(&dev);
+  dev = dev < 0 || dev >= 64 ? 0 : dev;
+  if (!n[dev]) {
+    cudaDeviceGetAttribute(&n[dev], cudaDevAttrMultiProcessorCount, dev);
+    if (n[dev] <= 0) n[dev] = 148;
   }
-  return n;
+  return n[dev];
 }
 
-#if NIND_PAIR_MODE
 // Pixel-pair mode weights.  `w9` = the tap-major packing every 3x3 layer uses, [9][64][C] (host copy);
 // result = [CTA rank 0..1][block g = chunk*3 + ky][96 rows][64 k]: rows 0..63 = this CTA's half of the
 // N = 128 MMA's weight tile (pair tap j = 1-e; CTA rank a = output pixel a: kx = 2 - a for e = 0, 1 - a for
@@ -150,7 +151,6 @@ inline void pack_pair_weights(const __nv_bfloat16* w9, int C, std::vector<__nv_b
     }
 }
 
-#endif
 inline bool build_igemm(const ConvSpec& s, IgemmLaunch* L, std::string* why) {
   auto fail = [&](const char* m) {
     if (why) *why = m;
@@ -169,40 +169,28 @@ inline bool build_igemm(const ConvSpec& s, IgemmLaunch* L, std::string* why) {
   const int shrink = s.taps == 9 ? 2 : 0;
   IgemmParams& p = L->p;
   memset(&p, 0, sizeof p);
+  memset(&L->tmC4, 0, sizeof L->tmC4);
+  memset(&L->tmC1, 0, sizeof L->tmC1);
 
-#if NIND_PAIR_MODE
   if (s.pair && (s.taps != 9 || s.c8 || s.n_total != 64 || s.in_coff != 0 || s.cin != s.in.c ||
                  (s.cin != 64 && s.cin != 128) || (s.in.ws & 1) || s.epi_mode == EPI_D2S))
     return fail("pixel-pair mode needs a 3x3 layer with C_out = 64, C_in = 64|128 filling its buffer, even width");
   L->pm = s.pair;
-#endif
   int n_tile = s.n_tile;
-#if NIND_PAIR_MODE
   if (s.pair) n_tile = 128;  // GEMM N = (pixel of the pair, c_out)
-#endif
   if (n_tile == 0) n_tile = s.n_total >= 256 ? 256 : (s.n_total >= 128 ? 128 : 64);
   if (n_tile != 64 && n_tile != 128 && n_tile != 256) return fail("n_tile must be 64/128/256");
-#if NIND_PAIR_MODE
   if (s.epi_mode == EPI_HEAD && ((n_tile != 64 && !s.pair) || s.n_total != 64)) return fail("head needs N=64");
-#else
-  if (s.epi_mode == EPI_HEAD && (n_tile != 64 || s.n_total != 64)) return fail("head needs N=64");
-#endif
   L->n_tile = n_tile;
 
   p.w_valid = s.in.ws - shrink;
   p.h_valid = s.in.hs - shrink;
   p.hs_in = s.in.hs;
   p.rows_total = s.in.b * s.in.hs;
-#if NIND_PAIR_MODE
   // pair mode tiles 8 pixel PAIRS across
   const int tiles_x_real = s.pair ? (p.w_valid / 2 + IG_TILE_W - 1) / IG_TILE_W : (p.w_valid + IG_TILE_W - 1) / IG_TILE_W;
-#else
-  const int tiles_x_real = (p.w_valid + IG_TILE_W - 1) / IG_TILE_W;
-#endif
   int cg = s.cg;
-#if NIND_PAIR_MODE
   if (s.pair) cg = 2;
-#endif
   // measured on B200 (profiles/r01_probe_cta_pair.log): the CTA pair wins on every 3x3 layer except
   // 64->128 (-3 %), and on the 1x1 / 2x2-s2 GEMMs only when K is large (C_in >= 512)
   if (s.c8) cg = 1;
@@ -219,11 +207,7 @@ inline bool build_igemm(const ConvSpec& s, IgemmLaunch* L, std::string* why) {
   {
     const int box_rows = s.taps == 9 ? 130 + 2 * s.in.ws : 128;
     const double eff_tile = (double)p.w_valid / (IG_TILE_W * tiles_x_real), eff_flat = (double)p.w_valid / s.in.ws;
-#if NIND_PAIR_MODE
     const bool can = !s.c8 && !s.pair && s.epi_mode != EPI_HEAD && !s.pool.ptr && box_rows <= 256;
-#else
-    const bool can = !s.c8 && s.epi_mode != EPI_HEAD && !s.pool.ptr && box_rows <= 256;
-#endif
     if (s.flat == 1 && !can) return fail("flat tiles need a narrow map (<= 63 px), no fused pool / head, not the first layer");
     flat = can && (s.flat >= 1 || (s.flat == -1 && eff_flat > eff_tile + 0.02));
   }
@@ -243,17 +227,9 @@ inline bool build_igemm(const ConvSpec& s, IgemmLaunch* L, std::string* why) {
     p.tiles_x = p.pair_y ? tiles_x_real : (tiles_x_real + cg - 1) / cg;
     p.tiles_y = p.pair_y ? (tiles_y_real + 1) / 2 : tiles_y_real;
   }
-#if NIND_PAIR_MODE
   p.tiles_n = s.pair ? 1 : (s.n_total + n_tile - 1) / n_tile;
-#else
-  p.tiles_n = (s.n_total + n_tile - 1) / n_tile;
-#endif
   p.total_tiles = p.tiles_x * p.tiles_y * p.tiles_n;
-#if NIND_PAIR_MODE
   p.kchunks = s.c8 ? 1 : (s.pair ? 2 * s.cin / 64 : s.cin / 64);
-#else
-  p.kchunks = s.c8 ? 1 : s.cin / 64;
-#endif
   p.taps = s.taps;
 
   // A operand: one TMA box per (tile, 64-channel chunk).  3x3: the (16+2) x (8+2) pixel patch, whose
@@ -264,11 +240,9 @@ inline bool build_igemm(const ConvSpec& s, IgemmLaunch* L, std::string* why) {
     boxA[0] = 64; boxA[1] = s.taps == 9 ? 130 + 2 * s.in.ws : 128; boxA[2] = 1;
     p.a_tx_bytes = boxA[1] * 128; p.a_stage_bytes = (p.a_tx_bytes + 1023) & ~1023; p.a_sbo = 1024;
     p.tap_pitch16 = (uint32_t)s.in.ws * 8;
-#if NIND_PAIR_MODE
   } else if (s.pair) {  // 8 + 1 pixel pairs x 16 + 2 rows of the [rows, W/2, 2C] view
     boxA[0] = 64; boxA[1] = 9; boxA[2] = 18;
     p.a_tx_bytes = 9 * 18 * 128; p.a_stage_bytes = 21504; p.a_sbo = 1152;
-#endif
   } else if (s.taps == 1) {
     boxA[0] = 64; boxA[1] = 8; boxA[2] = 16;
     p.a_tx_bytes = 16384; p.a_stage_bytes = 16384; p.a_sbo = 1024;
@@ -283,22 +257,17 @@ inline bool build_igemm(const ConvSpec& s, IgemmLaunch* L, std::string* why) {
   if (!flat) p.tap_pitch16 = p.a_sbo >> 4;
 
   // pipeline depth / weights-stationary decision
-#if NIND_PAIR_MODE
   const int tps = (s.c8 || s.pair) ? 1 : ((s.taps == 9 && n_tile <= 128) ? 3 : 1);  // taps per weight stage
-#else
-  const int tps = s.c8 ? 1 : ((s.taps == 9 && n_tile <= 128) ? 3 : 1);  // taps per weight stage
-#endif
   L->tps = tps;
   const int kt = s.c8 ? 2 : p.kchunks * (p.taps / tps);  // c8: 10 KB of weights in two 8 KB "stages"
   bool ws = false;
   if (s.force_ws != 0 && p.tiles_n == 1 && kt <= IG_MAX_STAGES &&
-      igemm_smem_bytes(n_tile, tps, cg, 2, p.a_stage_bytes, kt) <= IG_SMEM_LIMIT)
+      igemm_smem_bytes(n_tile, tps, cg, 2, p.a_stage_bytes, kt, s.pair) <= IG_SMEM_LIMIT)
     ws = true;
   if (s.force_ws == 1 && !ws) return fail("weights do not fit in shared memory");
   auto fits = [&](int sa, int sb) {
-    return igemm_smem_bytes(n_tile, tps, cg, sa, p.a_stage_bytes, sb) <= IG_SMEM_LIMIT;
+    return igemm_smem_bytes(n_tile, tps, cg, sa, p.a_stage_bytes, sb, s.pair) <= IG_SMEM_LIMIT;
   };
-#if NIND_PAIR_MODE
   if (s.pair) {  // resident weights: 36 KB per (e, 64-channel block) per CTA, counted in 8 KB "stages"
     ws = true;
     p.sb = p.kchunks * 9 / 2;
@@ -306,9 +275,6 @@ inline bool build_igemm(const ConvSpec& s, IgemmLaunch* L, std::string* why) {
     if (!fits(p.sa, p.sb)) return fail("pixel-pair weights do not fit in shared memory");
     while (p.sa < 4 && fits(p.sa + 1, p.sb)) ++p.sa;
   } else if (ws) {
-#else
-  if (ws) {
-#endif
     p.sb = kt;
     p.sa = 2;
     while (p.sa < 6 && fits(p.sa + 1, p.sb)) ++p.sa;
@@ -323,7 +289,7 @@ inline bool build_igemm(const ConvSpec& s, IgemmLaunch* L, std::string* why) {
     while (p.sa < 4 && fits(p.sa + 1, p.sb)) ++p.sa;
   }
   p.ws = ws ? 1 : 0;
-  L->smem = igemm_smem_bytes(n_tile, tps, cg, p.sa, p.a_stage_bytes, p.sb);
+  L->smem = igemm_smem_bytes(n_tile, tps, cg, p.sa, p.a_stage_bytes, p.sb, s.pair);
 
   // tensor maps
   {
@@ -333,13 +299,11 @@ inline bool build_igemm(const ConvSpec& s, IgemmLaunch* L, std::string* why) {
       const uint64_t dimsA[2] = {(uint64_t)s.in.ws * 8, (uint64_t)p.rows_total};
       const uint64_t stridesA[1] = {(uint64_t)s.in.ws * 16};
       const uint32_t boxA2[2] = {80, 18};
-      if (!encode_tmap_bf16(&L->tmA, s.in.ptr, 2, dimsA, stridesA, boxA2, why, false)) return false;
-#if NIND_PAIR_MODE
+      if (!encode_tmap_bf16(&L->tmA, s.in.ptr, 2, dimsA, stridesA, boxA2, why, 0)) return false;
     } else if (s.pair) {  // [rows][W/2 pairs][2C channels]
       const uint64_t dimsA[3] = {(uint64_t)2 * s.cin, (uint64_t)s.in.ws / 2, (uint64_t)p.rows_total};
       const uint64_t stridesA[2] = {(uint64_t)s.in.c * 4, (uint64_t)s.in.ws * s.in.c * 2};
       if (!encode_tmap_bf16(&L->tmA, s.in.ptr, 3, dimsA, stridesA, boxA, why)) return false;
-#endif
     } else if (flat) {  // [all pixels of the buffer][channels]
       const uint64_t dimsA[2] = {(uint64_t)s.cin, (uint64_t)p.rows_total * s.in.ws};
       const uint64_t stridesA[1] = {(uint64_t)s.in.c * 2};
@@ -351,14 +315,12 @@ inline bool build_igemm(const ConvSpec& s, IgemmLaunch* L, std::string* why) {
       const uint64_t dimsB[3] = {8, 64, 10};
       const uint64_t stridesB[2] = {16, 1024};
       const uint32_t boxB[3] = {8, 64, 10};
-      if (!encode_tmap_bf16(&L->tmB, s.w, 3, dimsB, stridesB, boxB, why, false)) return false;
-#if NIND_PAIR_MODE
+      if (!encode_tmap_bf16(&L->tmB, s.w, 3, dimsB, stridesB, boxB, why, 0)) return false;
     } else if (s.pair) {  // pack_pair_weights(): [2 ranks x blocks x 96 rows][64]
       const uint64_t dimsB[2] = {64, (uint64_t)2 * p.kchunks * 3 * 96};
       const uint64_t stridesB[1] = {128};
       const uint32_t boxB[2] = {64, 96};
       if (!encode_tmap_bf16(&L->tmB, s.w, 2, dimsB, stridesB, boxB, why)) return false;
-#endif
     } else {
       const uint64_t dimsB[2] = {(uint64_t)s.cin, (uint64_t)s.taps * s.n_total};
       const uint64_t stridesB[1] = {(uint64_t)s.cin * 2};
@@ -368,11 +330,7 @@ inline bool build_igemm(const ConvSpec& s, IgemmLaunch* L, std::string* why) {
   }
 
   // epilogue
-#if NIND_PAIR_MODE
   p.n_total = s.pair ? 128 : s.n_total;
-#else
-  p.n_total = s.n_total;
-#endif
   p.epi_mode = s.epi_mode;
   p.act = s.act;
   p.slope = s.slope;
@@ -387,6 +345,7 @@ inline bool build_igemm(const ConvSpec& s, IgemmLaunch* L, std::string* why) {
     p.h_unpad = s.head_unpad; p.h_size_y = s.head_hy; p.h_size_x = s.head_hx;
     p.h_row = s.head_hx; p.h_plane = (long long)s.head_hy * s.head_hx; p.h_img = 3 * p.h_plane;
     p.head_sigmoid = s.head_sigmoid;
+    p.head_clamp = s.head_clamp;
   } else {
     const int up = s.epi_mode == EPI_D2S ? 2 : 1;
     if (s.out.hs < up * p.h_valid + 2 * s.out_halo || s.out.ws < up * p.w_valid + 2 * s.out_halo)
@@ -399,6 +358,24 @@ inline bool build_igemm(const ConvSpec& s, IgemmLaunch* L, std::string* why) {
     p.o_img = (long long)s.out.hs * p.o_row;
     p.out = s.out.ptr + (long long)s.out_halo * p.o_row + (long long)s.out_halo * p.o_pix + s.out_coff;
     p.d2s_cout = s.d2s_cout;
+    p.c_coff = s.out_coff;
+    if (!flat) {
+      // Destination of the TMA-store epilogue: the interior of the output buffer as
+      // [channel][sub-x][x][row][image]; "sub-x" is 1 for a plain store, the pixel of the pair in pair mode and
+      // dx of the 2x2 block for depth-to-space (whose rows are 2y + dy).  The extents are the VALID ones, so the
+      // tensor map clips tile overhang, the garbage rows between the images of the batch-flattened row space
+      // and rows past the last image.
+      const int sx = (s.pair || s.epi_mode == EPI_D2S) ? 2 : 1;
+      const uint64_t wv = s.pair ? (uint64_t)p.w_valid / 2 : (uint64_t)p.w_valid;
+      const uint64_t hv = s.epi_mode == EPI_D2S ? 2 * (uint64_t)p.h_valid : (uint64_t)p.h_valid;
+      const uint64_t dimsC[5] = {(uint64_t)s.out.c, (uint64_t)sx, wv, hv, (uint64_t)s.out.b};
+      const uint64_t stridesC[4] = {(uint64_t)p.o_pix * 2, (uint64_t)p.o_pix * 2 * sx, (uint64_t)p.o_row * 2,
+                                    (uint64_t)p.o_img * 2};
+      const uint32_t box4[5] = {32, 1, 8, 4, 1}, box1[5] = {32, 1, 8, 1, 1};
+      const __nv_bfloat16* baseC = s.out.ptr + (long long)s.out_halo * p.o_row + (long long)s.out_halo * p.o_pix;
+      if (!encode_tmap_bf16(&L->tmC4, baseC, 5, dimsC, stridesC, box4, why, 64)) return false;
+      if (!encode_tmap_bf16(&L->tmC1, baseC, 5, dimsC, stridesC, box1, why, 64)) return false;
+    }
     if (s.pool.ptr) {
       if (s.epi_mode != EPI_STORE) return fail("fused pooling needs a plain store epilogue");
       if ((p.h_valid | p.w_valid | p.hs_in) & 1) return fail("fused pooling needs even map sizes");
@@ -416,31 +393,32 @@ inline bool build_igemm(const ConvSpec& s, IgemmLaunch* L, std::string* why) {
     const int groups_max = std::max(1, sms / cg);
     L->grid = cg * (p.total_tiles < groups_max ? p.total_tiles : groups_max);
   }
+  // Executed work: every valid OUTPUT pixel x taps x C_in x C_out.  For the ConvTranspose2d 3x3 layers (valid
+  // convolutions over a zero-framed input) this includes the taps that fall on the zero frame, so it is ~5 %
+  // above SURVEY §8d's algorithmic count (ConvTranspose2d: INPUT pixels), which nind_denoise_b200/flops.py
+  // restates and bench.py's roofline uses.
   L->flops = 2.0 * s.in.b * (double)p.h_valid * p.w_valid * s.n_total * (s.c8 ? 3 : s.cin) * s.taps;
   return true;
 }
 
-#if NIND_PAIR_MODE
+// One launcher per kernel variant.  The variants are spread over several translation units (igemm_inst_*.cu)
+// so that nvcc compiles them in parallel; NIND_IGEMM_SINGLE_TU (tools/probe.cu) defines all of them here.
 template <int N, int T, int CG, bool G = false, bool PM = false>
-#else
-template <int N, int T, int CG, bool G = false>
-#endif
 inline cudaError_t igemm_launch_t(const IgemmLaunch& L, const IgemmParams& p, cudaStream_t st) {
-  static bool attr_done = false;
-  if (!attr_done) {
-#if NIND_PAIR_MODE
+  static bool attr_done[64] = {false};  // cudaFuncSetAttribute is per device
+  int dev = 0;
+  cudaGetDevice(&dev);
+  dev = dev < 0 || dev >= 64 ? 0 : dev;
+  if (!attr_done[dev]) {
     cudaError_t e = cudaFuncSetAttribute(igemm_kernel<N, T, CG, G, PM>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-#else
-    cudaError_t e = cudaFuncSetAttribute(igemm_kernel<N, T, CG, G>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-#endif
                                          (int)IG_SMEM_LIMIT);
     if (e != cudaSuccess) return e;
-    attr_done = true;
+    attr_done[dev] = true;
   }
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof cfg);
   cfg.gridDim = dim3(L.grid);
-  cfg.blockDim = dim3(ig_threads(N));
+  cfg.blockDim = dim3(ig_threads(N, PM));
   cfg.dynamicSmemBytes = L.smem;
   cfg.stream = st;
   cudaLaunchAttribute attr[1];
@@ -450,11 +428,36 @@ inline cudaError_t igemm_launch_t(const IgemmLaunch& L, const IgemmParams& p, cu
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-#if NIND_PAIR_MODE
-  return cudaLaunchKernelEx(&cfg, igemm_kernel<N, T, CG, G, PM>, L.tmA, L.tmB, p);
-#else
-  return cudaLaunchKernelEx(&cfg, igemm_kernel<N, T, CG, G>, L.tmA, L.tmB, p);
+  return cudaLaunchKernelEx(&cfg, igemm_kernel<N, T, CG, G, PM>, L.tmA, L.tmB, L.tmC4, L.tmC1, p);
+}
+
+#define NIND_IGEMM_VARIANTS(X)                                                                      \
+  X(6411, 64, 1, 1, false, false) X(6431, 64, 3, 1, false, false) X(6412, 64, 1, 2, false, false)   \
+  X(6432, 64, 3, 2, false, false) X(64118, 64, 1, 1, true, false)                                   \
+  X(12811, 128, 1, 1, false, false) X(12831, 128, 3, 1, false, false) X(12812, 128, 1, 2, false, false) \
+  X(12832, 128, 3, 2, false, false) X(128129, 128, 1, 2, false, true)                               \
+  X(25611, 256, 1, 1, false, false) X(25612, 256, 1, 2, false, false)
+#define NIND_IGEMM_DECLARE(key, N, T, CG, G, PM) \
+  cudaError_t igemm_launch_##key(const IgemmLaunch& L, const IgemmParams& p, cudaStream_t st);
+#define NIND_IGEMM_DEFINE(key, N, T, CG, G, PM)                                               \
+  cudaError_t igemm_launch_##key(const IgemmLaunch& L, const IgemmParams& p, cudaStream_t st) { \
+    return igemm_launch_t<N, T, CG, G, PM>(L, p, st);                                         \
+  }
+NIND_IGEMM_VARIANTS(NIND_IGEMM_DECLARE)
+#ifdef NIND_IGEMM_SINGLE_TU
+NIND_IGEMM_VARIANTS(NIND_IGEMM_DEFINE)
 #endif
+
+inline long long default_wait_cycles() {
+  // bound of every mbarrier wait: NIND_WAIT_MS (default ~1 s at 2 GHz); under ncu replay, a debugger or
+  // time-slicing a healthy kernel can need more
+  static long long c = 0;
+  if (!c) {
+    const char* e = getenv("NIND_WAIT_MS");
+    const double ms = e ? atof(e) : 0.0;
+    c = ms > 0 ? (long long)(ms * 2.0e6) : (1ll << 31);
+  }
+  return c;
 }
 
 inline cudaError_t launch_igemm(const IgemmLaunch& L, int* err_flag, cudaStream_t st,
@@ -462,22 +465,21 @@ inline cudaError_t launch_igemm(const IgemmLaunch& L, int* err_flag, cudaStream_
   IgemmParams p = L.p;
   p.err = err_flag;
   p.trace = trace;
-  if (L.c8) return igemm_launch_t<64, 1, 1, true>(L, p, st);
-#if NIND_PAIR_MODE
-  if (L.pm) return igemm_launch_t<128, 1, 2, false, true>(L, p, st);
-#endif
+  p.wait_cycles = default_wait_cycles();
+  if (L.c8) return igemm_launch_64118(L, p, st);
+  if (L.pm) return igemm_launch_128129(L, p, st);
   const int key = L.n_tile * 100 + L.tps * 10 + L.cg;
   switch (key) {
-    case 6411: return igemm_launch_t<64, 1, 1>(L, p, st);
-    case 6431: return igemm_launch_t<64, 3, 1>(L, p, st);
-    case 12811: return igemm_launch_t<128, 1, 1>(L, p, st);
-    case 12831: return igemm_launch_t<128, 3, 1>(L, p, st);
-    case 25611: return igemm_launch_t<256, 1, 1>(L, p, st);
-    case 6412: return igemm_launch_t<64, 1, 2>(L, p, st);
-    case 6432: return igemm_launch_t<64, 3, 2>(L, p, st);
-    case 12812: return igemm_launch_t<128, 1, 2>(L, p, st);
-    case 12832: return igemm_launch_t<128, 3, 2>(L, p, st);
-    case 25612: return igemm_launch_t<256, 1, 2>(L, p, st);
+    case 6411: return igemm_launch_6411(L, p, st);
+    case 6431: return igemm_launch_6431(L, p, st);
+    case 12811: return igemm_launch_12811(L, p, st);
+    case 12831: return igemm_launch_12831(L, p, st);
+    case 25611: return igemm_launch_25611(L, p, st);
+    case 6412: return igemm_launch_6412(L, p, st);
+    case 6432: return igemm_launch_6432(L, p, st);
+    case 12812: return igemm_launch_12812(L, p, st);
+    case 12832: return igemm_launch_12832(L, p, st);
+    case 25612: return igemm_launch_25612(L, p, st);
     default: return cudaErrorInvalidValue;
   }
 }

@@ -35,6 +35,7 @@ int fail(int code, const std::string& m) {
 struct PackedLayer {
   int taps = 9, cin = 0, n_total = 0, cout = 0;
   __nv_bfloat16* w = nullptr;  // device [taps][n_total][cin]
+  __nv_bfloat16* w_pair = nullptr;  // device, pack_pair_weights() layout (3x3 layers with C_out = 64, C_in = 64 | 128)
   float* bias = nullptr;       // device
   int act = ACT_NONE;
   float slope = 0.f;
@@ -50,7 +51,6 @@ struct Step {
   PoolParams pl;
   double flops = 0;
   double bytes = 0;  // algorithmic bytes moved (memory-bound steps)
-  bool pad8 = false; // STEP_GATHER: padded 8-channel crop (C8 first layer) instead of the 64-wide im2col
 };
 
 struct Plan {
@@ -108,7 +108,9 @@ struct nind_net {
   std::map<std::string, PackedLayer> layers;
   float* head_w = nullptr;
   float* head_b = nullptr;
-  int* err_flag = nullptr;
+  int* err_flag = nullptr;      // device alias of err_host
+  int* err_host = nullptr;      // mapped, page-locked: survives a kernel trap
+  cudaEvent_t ev_last = nullptr; // last use of the shared scratch (plan arenas, crops_buf, origin_buf)
   std::map<std::vector<int>, std::unique_ptr<Plan>> plans;
   unsigned long long plan_tick = 0;
   // tiled driver scratch
@@ -131,16 +133,10 @@ struct nind_net {
   std::vector<cudaEvent_t> ev_in, ev_done;
   cudaEvent_t ev_join = nullptr;
   int flat = -1;
-#if NIND_PAIR_MODE
-  int pair64 = 0;  // EXPERIMENTAL, not validated on hardware yet
-#endif
+  int pair64 = 1;  // pixel-pair mode for the C_out = 64 3x3 layers (validated on B200, profiles/r02_pair_mode_first_light.log)
   int host_first = -1, host_last = -1;  // crops in the first / last pipeline step (-1: one grid row)
   // options
   int n_tile_deep = 256, max_ctas = 0, cg = 0, fuse_pool = 1;
-  // First layer: 3x3 implicit GEMM over the 8-channel padded-crop tensor (1) or K=64 GEMM over an im2col (0).
-  // (A third variant, building the im2col tile in shared memory inside the GEMM kernel with two builder
-  // warps, was correct but latency-bound: 7.5 ms vs 2.9 ms per 24 MP image; removed.)
-  int first_c8 = 1;
   // timing
   int timing = 0;
   std::vector<std::string> t_names;
@@ -150,6 +146,7 @@ struct nind_net {
   void free_layers() {
     for (auto& kv : layers) {
       cudaFree(kv.second.w);
+      cudaFree(kv.second.w_pair);
       cudaFree(kv.second.bias);
     }
     layers.clear();
@@ -160,7 +157,8 @@ struct nind_net {
   ~nind_net() {
     plans.clear();
     free_layers();
-    cudaFree(err_flag);
+    if (err_host) cudaFreeHost(err_host);
+    if (ev_last) cudaEventDestroy(ev_last);
     cudaFree(crops_buf);
     cudaFree(origin_buf);
     for (auto& sl : slots) {
@@ -187,6 +185,8 @@ int fetch(const nind_tensor* ts, int n, const std::string& name, const std::vect
           HostTensor* out) {
   for (int i = 0; i < n; ++i) {
     if (name != ts[i].name) continue;
+    if (ts[i].ndim < 0 || ts[i].ndim > 4 || !ts[i].data)
+      return fail(NIND_E_WEIGHTS, "tensor " + name + " has an illegal descriptor (ndim must be 0..4, data non-null)");
     size_t count = 1;
     std::vector<int64_t> shp(ts[i].shape, ts[i].shape + ts[i].ndim);
     for (auto d : shp) count *= (size_t)d;
@@ -211,6 +211,12 @@ int upload_layer(nind_net* net, const std::string& name, PackedLayer& L, const s
   CUDA_TRY(cudaMemcpy(L.w, w.data(), w.size() * sizeof(__nv_bfloat16), cudaMemcpyHostToDevice));
   CUDA_TRY(cudaMalloc(&L.bias, bias.size() * sizeof(float)));
   CUDA_TRY(cudaMemcpy(L.bias, bias.data(), bias.size() * sizeof(float), cudaMemcpyHostToDevice));
+  if (L.taps == 9 && L.n_total == 64 && (L.cin == 64 || L.cin == 128)) {  // pixel-pair mode candidate (igemm.cuh "PM")
+    std::vector<__nv_bfloat16> wp;
+    pack_pair_weights(w.data(), L.cin, &wp);
+    CUDA_TRY(cudaMalloc(&L.w_pair, wp.size() * sizeof(__nv_bfloat16)));
+    CUDA_TRY(cudaMemcpy(L.w_pair, wp.data(), wp.size() * sizeof(__nv_bfloat16), cudaMemcpyHostToDevice));
+  }
   net->layers[name] = L;
   return 0;
 }
@@ -245,19 +251,6 @@ void pack_up2(const float* w, int ci, int co, std::vector<__nv_bfloat16>* out) {
       for (int q = 0; q < 4; ++q)
         (*out)[((size_t)q * co + o) * ci + i] = __float2bfloat16(w[((size_t)i * co + o) * 4 + q]);
 }
-// First conv [co][3][3][3] -> [co][64]: k<27 hi taps, 27..53 the same weights for the lo parts.
-void pack_first(const float* w, int co, const float* scale, std::vector<__nv_bfloat16>* out) {
-  out->assign((size_t)co * 64, __float2bfloat16(0.f));
-  for (int o = 0; o < co; ++o)
-    for (int e = 0; e < 27; ++e) {
-      const int t = e / 3, c = e % 3;
-      float v = w[((size_t)o * 3 + c) * 9 + t];
-      if (scale) v *= scale[o];
-      (*out)[(size_t)o * 64 + e] = __float2bfloat16(v);
-      (*out)[(size_t)o * 64 + 27 + e] = __float2bfloat16(v);
-    }
-}
-
 // First conv [co][3][3][3] for the 8-channel path: [5 MMAs][2 K-halves][co][8], K-half (j,h) = tap 2j+h except the
 // last MMA, whose halves are (zero block, tap 8); the 8 channels are R,G,B hi | R,G,B lo | 0 0, so hi and lo
 // parts meet the same weight.
@@ -317,21 +310,17 @@ int load_utnet(nind_net* net, const nind_tensor* ts, int n) {
     else pack_conv3(w.v.data(), co, ci, nullptr, &pw);
     return upload_layer(net, name, L, pw, b.v);
   };
-  // first layer: 3 -> f as a K=64 per-pixel GEMM over the im2col'ed input
+  // first layer: 3 -> f as a 3x3 implicit GEMM over the 8-channel (hi/lo split) padded crop
   {
     HostTensor w, b;
     if ((rc = fetch(ts, n, "convs1.0.weight", {f, 3, 3, 3}, &w))) return rc;
     if ((rc = fetch(ts, n, "convs1.0.bias", {f}, &b))) return rc;
     PackedLayer L;
-    L.cin = 64; L.cout = f; L.n_total = f; L.taps = 1;
+    L.cin = 8; L.cout = f; L.n_total = f; L.taps = 9;
     if ((rc = act_of("convs1.1", &L))) return rc;
     std::vector<__nv_bfloat16> pw;
-    pack_first(w.v.data(), f, nullptr, &pw);
-    if ((rc = upload_layer(net, "convs1.0", L, pw, b.v))) return rc;
-    PackedLayer L8 = L;
-    L8.w = nullptr; L8.bias = nullptr; L8.cin = 8; L8.taps = 9;
     pack_first_c8(w.v.data(), f, nullptr, &pw);
-    if ((rc = upload_layer(net, "convs1.0@c8", L8, pw, b.v))) return rc;
+    if ((rc = upload_layer(net, "convs1.0", L, pw, b.v))) return rc;
   }
   if ((rc = conv("convs1.2", "convs1.3", f, f, false))) return rc;
   int c = f;
@@ -382,12 +371,8 @@ int load_unet(nind_net* net, const nind_tensor* ts, int n) {
     L.cout = co; L.n_total = co; L.act = ACT_PRELU; L.slope = 0.f;  // ReLU
     std::vector<__nv_bfloat16> pw;
     if (first) {
-      PackedLayer L8 = L;
-      L8.cin = 8; L8.taps = 9;
+      L.cin = 8; L.taps = 9;
       pack_first_c8(w.v.data(), co, scale.data(), &pw);
-      if ((rc = upload_layer(net, conv_name + "@c8", L8, pw, bias))) return rc;
-      L.cin = 64; L.taps = 1;
-      pack_first(w.v.data(), co, scale.data(), &pw);
     } else {
       L.cin = ci; L.taps = 9;
       pack_conv3(w.v.data(), co, ci, scale.data(), &pw);
@@ -473,10 +458,8 @@ struct PlanBuilder {
     s.cg = net->cg;
     s.flat = net->flat == 1 ? 2 : net->flat;  // 1 = on every layer where it is legal
     if (L.n_total >= 256) s.n_tile = net->n_tile_deep;
-#if NIND_PAIR_MODE
     maybe_pair(s, L, in, in_coff);
     if (rc) return;
-#endif
     Step st;
     st.kind = STEP_IGEMM; st.name = name;
     std::string why;
@@ -491,33 +474,16 @@ struct PlanBuilder {
     plan->steps.push_back(st);
   }
 
-#if NIND_PAIR_MODE
-  // EXPERIMENTAL (option "pair64", off by default): run an eligible C_out = 64 3x3 layer in pixel-pair mode;
-  // its re-packed weights live in a plan-owned buffer.
+  // Pixel-pair mode (option "pair64"): eligible C_out = 64 3x3 layers run as N = 128 GEMMs over pixel pairs.
   void maybe_pair(ConvSpec& s, const PackedLayer& L, const ActBuf& in, int in_coff) {
-    if (rc || !net->pair64 || L.taps != 9 || L.n_total != 64 || in_coff != 0 || L.cin != in.c ||
-        (L.cin != 64 && L.cin != 128) || (in.ws & 1) || s.epi_mode == EPI_D2S || s.c8)
+    if (rc || !net->pair64 || !L.w_pair || in_coff != 0 || L.cin != in.c || (in.ws & 1) || s.epi_mode == EPI_D2S ||
+        s.c8)
       return;
-    std::vector<__nv_bfloat16> w9((size_t)9 * 64 * L.cin), wp;
-    if (cudaMemcpy(w9.data(), L.w, w9.size() * sizeof(__nv_bfloat16), cudaMemcpyDeviceToHost) != cudaSuccess) {
-      rc = fail(NIND_E_CUDA, "pair64: cannot read the packed weights");
-      return;
-    }
-    pack_pair_weights(w9.data(), L.cin, &wp);
-    void* d = nullptr;
-    if (cudaMalloc(&d, wp.size() * sizeof(__nv_bfloat16)) != cudaSuccess ||
-        cudaMemcpy(d, wp.data(), wp.size() * sizeof(__nv_bfloat16), cudaMemcpyHostToDevice) != cudaSuccess) {
-      if (d) cudaFree(d);
-      rc = fail(NIND_E_CUDA, "pair64: cannot upload the re-packed weights");
-      return;
-    }
-    plan->bufs.push_back(d);
-    s.w = static_cast<const __nv_bfloat16*>(d);
+    s.w = L.w_pair;
     s.pair = true;
     s.flat = 0;
   }
 
-#endif
   void head(const std::string& name, const ActBuf& in, int unpad, int hy, int hx, int sigmoid) {
     if (rc) return;
     auto it = net->layers.find(name);
@@ -530,10 +496,8 @@ struct PlanBuilder {
     s.head_unpad = unpad; s.head_hy = hy; s.head_hx = hx; s.head_sigmoid = sigmoid;
     s.max_ctas = net->max_ctas;
     s.cg = net->cg;
-#if NIND_PAIR_MODE
     maybe_pair(s, L, in, 0);
     if (rc) return;
-#endif
     Step st;
     st.kind = STEP_IGEMM; st.name = name + "+head";
     std::string why;
@@ -566,11 +530,10 @@ struct PlanBuilder {
     return g;
   }
 
-  void gather(const ActBuf& x0, int crop_h, int crop_w, int pad, int reflect, bool pad8 = false) {
+  void gather(const ActBuf& x0, int crop_h, int crop_w, int pad, int reflect) {
     if (rc) return;
     Step st;
-    st.kind = STEP_GATHER; st.name = pad8 ? "gather+pad8" : "gather+im2col";
-    st.pad8 = pad8;
+    st.kind = STEP_GATHER; st.name = "gather+pad8";
     GatherParams& g = st.g;
     g = gather_geom(x0, crop_h, crop_w, pad, reflect);
     st.bytes = (double)x0.b * (3.0 * crop_h * crop_w * 4 + (double)x0.hs * x0.ws * x0.c * 2);
@@ -596,21 +559,15 @@ int build_utnet_plan(nind_net* net, Plan* plan, int B, int H, int W) {
   }
   // encoder
   // first layer input: the padded crops as 8 bf16 channels/pixel (default), or the 64-wide im2col
-  ActBuf x0;
-  if (net->first_c8) {
-    x0 = pb.alloc(B, H + 4, W + 4, 8);
-    pb.gather(x0, H, W, 2, 1, true);
-  } else {
-    x0 = pb.alloc(B, H + 2, W + 2, 64);
-    pb.gather(x0, H, W, 2, 1);
-  }
+  ActBuf x0 = pb.alloc(B, H + 4, W + 4, 8);
+  pb.gather(x0, H, W, 2, 1);
   ActBuf cat[5];
   ActBuf cur;  // input of the level's first conv
   for (int l = 1; l <= 4; ++l) {
     const int c = f << (l - 1);
     const std::string p = "convs" + std::to_string(l);
     ActBuf a = pb.alloc(B, eh[l] + 2, ew[l] + 2, c);
-    if (l == 1) pb.conv(net->first_c8 ? p + ".0@c8" : p + ".0", x0, 0, a, 0, 0, EPI_STORE, nullptr, 0, net->first_c8);
+    if (l == 1) pb.conv(p + ".0", x0, 0, a, 0, 0, EPI_STORE, nullptr, 0, true);
     else pb.conv(p + ".0", cur, 0, a, 0, 0, EPI_STORE);
     cat[l] = pb.alloc(B, eh[l] + 4, ew[l] + 4, 2 * c);  // [up | skip], 2-px zero frame for the ConvT
     cur = pb.alloc(B, ph[l], pw[l], c);
@@ -652,14 +609,8 @@ int build_unet_plan(nind_net* net, Plan* plan, int B, int H, int W) {
   int sh[5], sw[5];
   for (int l = 0; l < 5; ++l) { sh[l] = H >> l; sw[l] = W >> l; }
   const int ch[5] = {64, 128, 256, 512, 512};
-  ActBuf x0;
-  if (net->first_c8) {
-    x0 = pb.alloc(B, H + 2, W + 2, 8);
-    pb.gather(x0, H, W, 1, 0, true);
-  } else {
-    x0 = pb.alloc(B, H, W, 64);
-    pb.gather(x0, H, W, 1, 0);
-  }
+  ActBuf x0 = pb.alloc(B, H + 2, W + 2, 8);
+  pb.gather(x0, H, W, 1, 0);
   // every 3x3 conv is padding=1: its input buffer carries a 1-px zero frame
   ActBuf cat[4];  // [skip | up] for decoder levels, skip written by the encoder
   ActBuf cur;
@@ -668,7 +619,7 @@ int build_unet_plan(nind_net* net, Plan* plan, int B, int H, int W) {
   for (int l = 0; l < 5; ++l) {
     const std::string p = enc_name[l];
     ActBuf mid = pb.alloc(B, sh[l] + 2, sw[l] + 2, ch[l]);
-    if (l == 0) pb.conv(net->first_c8 ? p + ".0@c8" : p + ".0", x0, 0, mid, 0, 1, EPI_STORE, nullptr, 0, net->first_c8);
+    if (l == 0) pb.conv(p + ".0", x0, 0, mid, 0, 1, EPI_STORE, nullptr, 0, true);
     else pb.conv(p + ".0", cur, 0, mid, 0, 1, EPI_STORE);
     if (l < 4) {
       cat[l] = pb.alloc(B, sh[l] + 2, sw[l] + 2, 2 * ch[l]);
@@ -735,7 +686,8 @@ int grid_for(long long work_items) {
   return (int)std::max(1LL, std::min(blocks, cap));
 }
 
-int run_plan(nind_net* net, Plan* plan, const GatherParams& gsrc, float* head_out, cudaStream_t st) {
+int run_plan(nind_net* net, Plan* plan, const GatherParams& gsrc, float* head_out, cudaStream_t st,
+             int head_clamp = 0) {
   std::vector<cudaEvent_t> ev;
   if (net->timing) {
     ev.resize(plan->steps.size() + 1);
@@ -748,13 +700,12 @@ int run_plan(nind_net* net, Plan* plan, const GatherParams& gsrc, float* head_ou
       GatherParams g = s.g;
       g.src = gsrc.src; g.src_img = gsrc.src_img; g.src_plane = gsrc.src_plane;
       g.src_w = gsrc.src_w; g.src_h = gsrc.src_h; g.origin = gsrc.origin;
-      if (s.pad8) gather_pad8_kernel<<<grid_for((long long)g.n_crops * g.out_h * g.out_w), 256, 0, st>>>(g);
-      else gather_im2col_kernel<<<grid_for((long long)g.n_crops * g.out_h * g.out_w), 256, 0, st>>>(g);
+      gather_pad8_kernel<<<grid_for((long long)g.n_crops * g.out_h * g.out_w), 256, 0, st>>>(g);
     } else if (s.kind == STEP_POOL) {
       maxpool2_kernel<<<grid_for((long long)s.pl.n * s.pl.ho * s.pl.wo * (s.pl.c / 8)), 256, 0, st>>>(s.pl);
     } else {
       IgemmLaunch L = s.ig;
-      if ((int)i == plan->head_step) L.p.head_out = head_out;
+      if ((int)i == plan->head_step) { L.p.head_out = head_out; L.p.head_clamp = head_clamp; }
 
       cudaError_t e = launch_igemm(L, net->err_flag, st);
       if (e != cudaSuccess) return fail(NIND_E_CUDA, s.name + ": " + cudaGetErrorString(e));
@@ -779,10 +730,41 @@ int run_plan(nind_net* net, Plan* plan, const GatherParams& gsrc, float* head_ou
   return 0;
 }
 
+// The role code of a pipeline time-out lives in mapped host memory: readable without a CUDA call, also after
+// the trap has poisoned the context.
 int check_err_flag(nind_net* net) {
-  int h = 0;
-  CUDA_TRY(cudaMemcpy(&h, net->err_flag, sizeof h, cudaMemcpyDeviceToHost));
-  if (h) return fail(NIND_E_KERNEL, "kernel pipeline time-out, role code " + std::to_string(h));
+  const int h = *reinterpret_cast<volatile int*>(net->err_host);
+  if (h) return fail(NIND_E_KERNEL, "kernel pipeline time-out, role code " + std::to_string(h) +
+                                        " (1 A-producer, 2 B-producer, 3 MMA/TMEM, 4 MMA/A, 5 MMA/B, 6 epilogue)");
+  return 0;
+}
+
+// Every entry point runs on the handle's device, whatever the caller's current device is.
+struct DeviceGuard {
+  int prev = -1;
+  bool ok = true;
+  explicit DeviceGuard(int dev) {
+    if (cudaGetDevice(&prev) != cudaSuccess) { ok = false; return; }
+    if (prev != dev && cudaSetDevice(dev) != cudaSuccess) ok = false;
+    if (prev == dev) prev = -1;
+  }
+  ~DeviceGuard() {
+    if (prev >= 0) cudaSetDevice(prev);
+  }
+};
+#define ENTER(net)                                                              \
+  DeviceGuard guard_((net)->device);                                            \
+  if (!guard_.ok) return fail(NIND_E_CUDA, "cannot switch to the handle's device"); \
+  { int rc_ = check_err_flag(net); if (rc_) return rc_; }
+
+// The plan arenas, crops_buf and origin_buf are shared by every entry point of a handle: a call's compute
+// stream first waits for the last use recorded by the previous call (which may have been on another stream).
+int scratch_acquire(nind_net* net, cudaStream_t st) {
+  CUDA_TRY(cudaStreamWaitEvent(st, net->ev_last, 0));
+  return 0;
+}
+int scratch_release(nind_net* net, cudaStream_t st) {
+  CUDA_TRY(cudaEventRecord(net->ev_last, st));
   return 0;
 }
 
@@ -831,8 +813,10 @@ int nind_net_create(int arch, int funit, int activation, const nind_tensor* tens
   net->funit = funit;
   net->act_kind = activation == NIND_ACT_PRELU ? ACT_PRELU : (activation == NIND_ACT_ELU ? ACT_ELU : ACT_HARDSWISH);
   CUDA_TRY(cudaGetDevice(&net->device));
-  CUDA_TRY(cudaMalloc(&net->err_flag, sizeof(int)));
-  CUDA_TRY(cudaMemset(net->err_flag, 0, sizeof(int)));
+  CUDA_TRY(cudaHostAlloc(reinterpret_cast<void**>(&net->err_host), sizeof(int), cudaHostAllocMapped));
+  *net->err_host = 0;
+  CUDA_TRY(cudaHostGetDevicePointer(reinterpret_cast<void**>(&net->err_flag), net->err_host, 0));
+  CUDA_TRY(cudaEventCreateWithFlags(&net->ev_last, cudaEventDisableTiming));
   if ((rc = load_weights(net.get(), tensors, n_tensors))) return rc;
   *out = net.release();
   return 0;
@@ -840,14 +824,22 @@ int nind_net_create(int arch, int funit, int activation, const nind_tensor* tens
 
 int nind_net_load(nind_net* net, const nind_tensor* tensors, int n_tensors) {
   if (!net || !tensors) return fail(NIND_E_INVALID, "null argument");
+  ENTER(net);
   CUDA_TRY(cudaDeviceSynchronize());
   return load_weights(net, tensors, n_tensors);
 }
 
 void nind_net_destroy(nind_net* net) {
   if (!net) return;
+  DeviceGuard guard(net->device);
   cudaDeviceSynchronize();
   delete net;
+}
+
+int nind_net_device(nind_net* net, int* device) {
+  if (!net || !device) return fail(NIND_E_INVALID, "null argument");
+  *device = net->device;
+  return 0;
 }
 
 int nind_set_timing(nind_net* net, int enabled) {
@@ -880,7 +872,16 @@ int nind_get_layer_bytes(nind_net* net, int max_layers, double* bytes, int* n_la
 
 int nind_set_option(nind_net* net, const char* key, int value) {
   if (!net || !key) return fail(NIND_E_INVALID, "null argument");
+  ENTER(net);
   const std::string k = key;
+  if (k == "host_first") {  // crops in the first step of the host pipeline (-1: up to the first grid-row boundary)
+    net->host_first = value;
+    return 0;
+  }
+  if (k == "host_last") {
+    net->host_last = value;
+    return 0;
+  }
   if (k == "n_tile_deep") {
     if (value != 128 && value != 256) return fail(NIND_E_INVALID, "n_tile_deep must be 128 or 256");
     net->n_tile_deep = value;
@@ -891,39 +892,41 @@ int nind_set_option(nind_net* net, const char* key, int value) {
     net->cg = value;
   } else if (k == "fuse_pool") {
     net->fuse_pool = value ? 1 : 0;
-  } else if (k == "first_c8") {
-    net->first_c8 = value ? 1 : 0;
-#if NIND_PAIR_MODE
-  } else if (k == "pair64") {  // EXPERIMENTAL pixel-pair mode for the C_out = 64 3x3 layers (0 | 1)
+  } else if (k == "pair64") {  // pixel-pair mode for the C_out = 64 3x3 layers (0 | 1)
     net->pair64 = value ? 1 : 0;
-#endif
   } else if (k == "flat") {  // flat (1-D) tiles on narrow maps: -1 auto, 0 off, 1 wherever legal
     net->flat = value;
-  } else if (k == "host_first") {  // crops in the first step of the host pipeline (-1: one grid row)
-    net->host_first = value;
-    return 0;
-  } else if (k == "host_last") {
-    net->host_last = value;
-    return 0;
   } else {
     return fail(NIND_E_INVALID, "unknown option " + k);
   }
+  CUDA_TRY(cudaDeviceSynchronize());  // plans still in flight own the arenas that are about to be freed
   net->plans.clear();
   return 0;
 }
 
-int nind_net_forward(nind_net* net, const float* in_nchw, float* out_nchw, int batch, int h, int w,
-                     void* stream) {
+int nind_net_forward_ex(nind_net* net, const float* in_nchw, float* out_nchw, int batch, int h, int w, int flags,
+                        void* stream) {
   if (!net || !in_nchw || !out_nchw) return fail(NIND_E_INVALID, "null argument");
   if (batch <= 0) return fail(NIND_E_INVALID, "batch must be positive");
+  if (flags & ~NIND_FWD_CLAMP01) return fail(NIND_E_INVALID, "unknown forward flag");
+  ENTER(net);
   Plan* plan = nullptr;
   int rc = get_plan(net, batch, h, w, &plan);
   if (rc) return rc;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
   GatherParams g;
   memset(&g, 0, sizeof g);
   g.src = in_nchw; g.src_img = 3LL * h * w; g.src_plane = (long long)h * w; g.src_w = w; g.src_h = h;
   g.origin = nullptr;
-  return run_plan(net, plan, g, out_nchw, static_cast<cudaStream_t>(stream));
+  if ((rc = scratch_acquire(net, st))) return rc;
+  rc = run_plan(net, plan, g, out_nchw, st, (flags & NIND_FWD_CLAMP01) ? 1 : 0);
+  scratch_release(net, st);
+  return rc;
+}
+
+int nind_net_forward(nind_net* net, const float* in_nchw, float* out_nchw, int batch, int h, int w,
+                     void* stream) {
+  return nind_net_forward_ex(net, in_nchw, out_nchw, batch, h, w, 0, stream);
 }
 
 int nind_crop_table(int width, int height, int cs, int ucs, int ol, nind_crop* table, int* n_crops) {
@@ -994,11 +997,13 @@ static int check_range(int width, int height, int cs, int ucs, int ol, int crop_
 int nind_gather_crops(nind_net* net, const float* img_chw, int height, int width, int cs, int ucs, int ol,
                       int crop_begin, int crop_end, float* crops_out, void* stream) {
   if (!net || !img_chw || !crops_out) return fail(NIND_E_INVALID, "null argument");
+  ENTER(net);
   GridGeom g;
   int rc;
   if ((rc = check_range(width, height, cs, ucs, ol, crop_begin, crop_end, &g))) return rc;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const int n = crop_end - crop_begin;
+  if ((rc = scratch_acquire(net, st))) return rc;
   if ((rc = upload_origins(net, g, crop_begin, n, st))) return rc;
   CropGatherParams p;
   p.src = img_chw; p.src_plane = (long long)height * width; p.src_w = width; p.src_h = height;
@@ -1006,7 +1011,7 @@ int nind_gather_crops(nind_net* net, const float* img_chw, int height, int width
   gather_crops_kernel<<<grid_for((long long)n * 3 * cs * cs), 256, 0, st>>>(p);
   ++g_launches;
   CUDA_TRY(cudaGetLastError());
-  return 0;
+  return scratch_release(net, st);
 }
 
 int nind_stitch_crops(const float* crops, int height, int width, int cs, int ucs, int ol, int crop_begin,
@@ -1022,62 +1027,101 @@ int nind_stitch_crops(const float* crops, int height, int width, int cs, int ucs
   return launch_stitch(g, crops, crop_begin, crop_end, out_band, y0, y1, false, static_cast<cudaStream_t>(stream));
 }
 
+// Crops [a, b) in forwards of at most `batch` crops, balanced: ceil(n / batch) forwards of near-equal size
+// (532 crops at batch 168 run as 4 x 133, not 3 x 168 + 28: the small tail plan is the least efficient one).
+static void balanced_steps(int a, int b, int batch, std::vector<std::pair<int, int>>* steps) {
+  const int n = b - a;
+  if (n <= 0) return;
+  const int k = (n + batch - 1) / batch;
+  for (int i = 0; i < k; ++i) steps->push_back({a + (int)((long long)n * i / k), a + (int)((long long)n * (i + 1) / k)});
+}
+
 int nind_tiled_denoise(nind_net* net, const float* img_chw, float* out_band, int height, int width,
                        int cs, int ucs, int ol, int crop_begin, int crop_end, int batch,
                        int* band_y0, int* band_y1, void* stream) {
   if (!net || !img_chw || !out_band) return fail(NIND_E_INVALID, "null argument");
+  ENTER(net);
   GridGeom g;
   int rc;
   if ((rc = check_range(width, height, cs, ucs, ol, crop_begin, crop_end, &g))) return rc;
   if (batch <= 0) return fail(NIND_E_INVALID, "batch must be positive");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const int n = crop_end - crop_begin;
+  if ((rc = scratch_acquire(net, st))) return rc;
   if ((rc = ensure(reinterpret_cast<void**>(&net->crops_buf), &net->crops_cap,
                    (size_t)n * 3 * cs * cs * sizeof(float))))
     return rc;
   if ((rc = upload_origins(net, g, crop_begin, n, st))) return rc;
-  for (int i0 = 0; i0 < n; i0 += batch) {
-    const int b = std::min(batch, n - i0);
+  std::vector<std::pair<int, int>> steps;
+  balanced_steps(0, n, batch, &steps);
+  for (auto& sp : steps) {
     Plan* plan = nullptr;
-    if ((rc = get_plan(net, b, cs, cs, &plan))) return rc;
+    if ((rc = get_plan(net, sp.second - sp.first, cs, cs, &plan))) return rc;
     GatherParams gp;
     memset(&gp, 0, sizeof gp);
     gp.src = img_chw; gp.src_img = 0; gp.src_plane = (long long)height * width; gp.src_w = width; gp.src_h = height;
-    gp.origin = net->origin_buf + i0;
-    if ((rc = run_plan(net, plan, gp, net->crops_buf + (size_t)i0 * 3 * cs * cs, st))) return rc;
+    gp.origin = net->origin_buf + sp.first;
+    if ((rc = run_plan(net, plan, gp, net->crops_buf + (size_t)sp.first * 3 * cs * cs, st))) return rc;
   }
   int y0, y1;
   band_of(g, crop_begin, crop_end, &y0, &y1);
   if (band_y0) *band_y0 = y0;
   if (band_y1) *band_y1 = y1;
-  return launch_stitch(g, net->crops_buf, crop_begin, crop_end, out_band, y0, y1, false, st);
+  if ((rc = launch_stitch(g, net->crops_buf, crop_begin, crop_end, out_band, y0, y1, false, st))) return rc;
+  return scratch_release(net, st);
+}
+
+// Pipeline steps of the host entry for crops [cb, ce): the first and the last step end / start at a grid-row
+// boundary (so that compute starts after one grid row of the image has been uploaded and only one grid row of
+// output is downloaded after the last forward), unless that would make them shorter than half a grid row — a
+// tiny forward costs more than the copy it hides —; the crops in between run in balanced forwards of at most
+// `batch` crops.  host_first / host_last (nind_set_option) override the two end steps.
+static void host_steps(const nind_net* net, const GridGeom& g, int cb, int ce, int batch,
+                       std::vector<std::pair<int, int>>* steps) {
+  const int n = ce - cb;
+  int first = 0, last = 0;
+  if (n > batch || n > 2 * g.nx) {
+    const int row_end = (cb / g.nx + 1) * g.nx;        // first grid-row boundary after cb
+    const int row_begin = ((ce - 1) / g.nx) * g.nx;    // start of the grid row that holds the last crop
+    first = row_end - cb;
+    while (first < (g.nx + 1) / 2) first += g.nx;
+    last = ce - row_begin;
+    while (last < (g.nx + 1) / 2) last += g.nx;
+    first = std::min(first, batch);
+    last = std::min(last, batch);
+  }
+  if (net->host_first >= 0) first = net->host_first;
+  if (net->host_last >= 0) last = net->host_last;
+  if (first + last >= n) {  // short range: two steps (first | rest), or one
+    if (first > 0 && first < n) last = n - first;
+    else first = last = 0;
+  }
+  if (first) steps->push_back({cb, cb + first});
+  balanced_steps(cb + first, ce - last, batch, steps);
+  if (last) steps->push_back({ce - last, ce});
 }
 
 // Enqueue crops [cb, ce) of one image on the three-stream host pipeline (no synchronisation).  Rows
 // [d2h_y0, d2h_y1) of the stitched band are downloaded to `out_chw_host` as they complete; `d_out`
 // (optional) receives the device image (full [3][H][W] layout) the band is stitched into.
-static int enqueue_host_range(nind_net* net, const float* img_chw_host, float* out_chw_host, int height, int width,
-                              int cs, int ucs, int ol, int batch, int cb, int ce, int d2h_y0, int d2h_y1,
-                              float** d_out) {
+static int enqueue_host_range_impl(nind_net* net, const float* img_chw_host, float* out_chw_host, int height,
+                                   int width, int cs, int ucs, int ol, int batch, int cb, int ce, int d2h_y0,
+                                   int d2h_y1, float** d_out, bool* enqueued) {
   // Pipelined over steps of crops in raster order: the H2D copy of the image rows a step needs, the
   // forward of its crops, the stitch of the output rows it completes and their D2H copy run on three
   // streams, so PCIe traffic hides behind compute when the host buffers are pinned.  Two device
   // (image, output) slots let image k+1's upload overlap image k's compute and download.
-  if (!net || !img_chw_host || !out_chw_host) return fail(NIND_E_INVALID, "null argument");
-  if (batch <= 0) return fail(NIND_E_INVALID, "batch must be positive");
   GridGeom g;
   int rc;
   if ((rc = check_range(width, height, cs, ucs, ol, cb, ce, &g))) return rc;
   if (d2h_y0 < 0 || d2h_y1 > height || d2h_y0 > d2h_y1) return fail(NIND_E_INVALID, "illegal download row range");
   const size_t plane = (size_t)height * width;
   const size_t bytes = 3 * plane * sizeof(float);
-  nind_net::HostSlot& S = net->slots[net->host_seq++ & 1];
+  nind_net::HostSlot& S = net->slots[net->host_seq & 1];
   if ((rc = ensure(reinterpret_cast<void**>(&S.img), &S.img_cap, bytes))) return rc;
   if ((rc = ensure(reinterpret_cast<void**>(&S.out), &S.out_cap, bytes))) return rc;
   if (d_out) *d_out = S.out;
   const int n = ce - cb;
-  if ((rc = ensure(reinterpret_cast<void**>(&net->crops_buf), &net->crops_cap, (size_t)n * 3 * cs * cs * sizeof(float))))
-    return rc;
   if (!net->s_in) {
     CUDA_TRY(cudaStreamCreateWithFlags(&net->s_in, cudaStreamNonBlocking));
     CUDA_TRY(cudaStreamCreateWithFlags(&net->s_comp, cudaStreamNonBlocking));
@@ -1087,15 +1131,8 @@ static int enqueue_host_range(nind_net* net, const float* img_chw_host, float* o
     CUDA_TRY(cudaEventCreateWithFlags(&S.img_free, cudaEventDisableTiming));
     CUDA_TRY(cudaEventCreateWithFlags(&S.out_free, cudaEventDisableTiming));
   }
-  // Steps.  The first and the last are about one grid row of crops, so that compute starts after a small
-  // part of the upload and only a small part of the download is exposed; the rest are `batch` crops.
   std::vector<std::pair<int, int>> steps;
-  int first = net->host_first >= 0 ? net->host_first : (n > 2 * g.nx && batch > g.nx ? g.nx : 0);
-  int last = net->host_last >= 0 ? net->host_last : (n > 2 * g.nx && batch > g.nx ? g.nx : 0);
-  if (first + last >= n) first = last = 0;
-  if (first) steps.push_back({cb, cb + first});
-  for (int i = cb + first; i < ce - last; i += batch) steps.push_back({i, std::min(ce - last, i + batch)});
-  if (last) steps.push_back({ce - last, ce});
+  host_steps(net, g, cb, ce, batch, &steps);
   while (net->ev_in.size() < steps.size()) {
     cudaEvent_t a, b;
     CUDA_TRY(cudaEventCreateWithFlags(&a, cudaEventDisableTiming));
@@ -1103,7 +1140,15 @@ static int enqueue_host_range(nind_net* net, const float* img_chw_host, float* o
     net->ev_in.push_back(a);
     net->ev_done.push_back(b);
   }
+  // plans first: building one allocates (and zero-fills) its arena, which must not happen between enqueues
+  std::vector<Plan*> plans(steps.size(), nullptr);
+  for (size_t k = 0; k < steps.size(); ++k)
+    if ((rc = get_plan(net, steps[k].second - steps[k].first, cs, cs, &plans[k]))) return rc;
+  if ((rc = scratch_acquire(net, net->s_comp))) return rc;
+  if ((rc = ensure(reinterpret_cast<void**>(&net->crops_buf), &net->crops_cap, (size_t)n * 3 * cs * cs * sizeof(float))))
+    return rc;
   if ((rc = upload_origins(net, g, cb, n, net->s_comp))) return rc;
+  *enqueued = true;
   if (S.used) {  // the image that used this slot two calls ago must be done with it
     CUDA_TRY(cudaStreamWaitEvent(net->s_in, S.img_free, 0));
     CUDA_TRY(cudaStreamWaitEvent(net->s_comp, S.out_free, 0));
@@ -1136,16 +1181,11 @@ static int enqueue_host_range(nind_net* net, const float* img_chw_host, float* o
   for (size_t k = 0; k < steps.size(); ++k) {
     const int ia = steps[k].first, ib = steps[k].second;
     CUDA_TRY(cudaStreamWaitEvent(net->s_comp, net->ev_in[k], 0));
-    for (int i0 = ia; i0 < ib; i0 += batch) {
-      const int b = std::min(batch, ib - i0);
-      Plan* plan = nullptr;
-      if ((rc = get_plan(net, b, cs, cs, &plan))) return rc;
-      GatherParams gp;
-      memset(&gp, 0, sizeof gp);
-      gp.src = S.img; gp.src_img = 0; gp.src_plane = (long long)plane; gp.src_w = width; gp.src_h = height;
-      gp.origin = net->origin_buf + (i0 - cb);
-      if ((rc = run_plan(net, plan, gp, net->crops_buf + (size_t)(i0 - cb) * 3 * cs * cs, net->s_comp))) return rc;
-    }
+    GatherParams gp;
+    memset(&gp, 0, sizeof gp);
+    gp.src = S.img; gp.src_img = 0; gp.src_plane = (long long)plane; gp.src_w = width; gp.src_h = height;
+    gp.origin = net->origin_buf + (ia - cb);
+    if ((rc = run_plan(net, plans[k], gp, net->crops_buf + (size_t)(ia - cb) * 3 * cs * cs, net->s_comp))) return rc;
     if (ib == ce) CUDA_TRY(cudaEventRecord(S.img_free, net->s_comp));
     // output rows completed by this step: every crop of the range that touches them has index < ib
     const int r0 = done;
@@ -1163,9 +1203,32 @@ static int enqueue_host_range(nind_net* net, const float* img_chw_host, float* o
       }
     }
   }
+  if ((rc = scratch_release(net, net->s_comp))) return rc;
   CUDA_TRY(cudaEventRecord(S.out_free, net->s_out));
   S.used = true;
+  ++net->host_seq;
   return 0;
+}
+
+static int enqueue_host_range(nind_net* net, const float* img_chw_host, float* out_chw_host, int height, int width,
+                              int cs, int ucs, int ol, int batch, int cb, int ce, int d2h_y0, int d2h_y1,
+                              float** d_out) {
+  if (!net || !img_chw_host || !out_chw_host) return fail(NIND_E_INVALID, "null argument");
+  if (batch <= 0) return fail(NIND_E_INVALID, "batch must be positive");
+  ENTER(net);
+  bool enqueued = false;
+  const int rc = enqueue_host_range_impl(net, img_chw_host, out_chw_host, height, width, cs, ucs, ol, batch, cb, ce,
+                                         d2h_y0, d2h_y1, d_out, &enqueued);
+  if (rc && enqueued) {
+    // Part of the image is already in flight: wait for it, so that the caller may free its (pinned) buffers
+    // as soon as it sees the error, and leave the slot bookkeeping as it was (host_seq only advances on success).
+    const std::string keep = g_err;
+    cudaStreamSynchronize(net->s_in);
+    cudaStreamSynchronize(net->s_comp);
+    cudaStreamSynchronize(net->s_out);
+    g_err = keep;
+  }
+  return rc;
 }
 
 static int enqueue_host_image(nind_net* net, const float* img_chw_host, float* out_chw_host, int height, int width,
@@ -1178,6 +1241,7 @@ static int enqueue_host_image(nind_net* net, const float* img_chw_host, float* o
 
 int nind_host_sync(nind_net* net) {
   if (!net) return fail(NIND_E_INVALID, "null handle");
+  DeviceGuard guard(net->device);
   if (net->s_in) {
     CUDA_TRY(cudaStreamSynchronize(net->s_out));
     CUDA_TRY(cudaStreamSynchronize(net->s_comp));
@@ -1195,6 +1259,7 @@ int nind_tiled_denoise_host_range(nind_net* net, const float* img_chw_host, floa
 
 int nind_host_join(nind_net* net, void* stream) {
   if (!net) return fail(NIND_E_INVALID, "null handle");
+  ENTER(net);
   if (!net->s_comp) return 0;
   if (!net->ev_join) CUDA_TRY(cudaEventCreateWithFlags(&net->ev_join, cudaEventDisableTiming));
   CUDA_TRY(cudaEventRecord(net->ev_join, net->s_comp));
@@ -1224,6 +1289,33 @@ int nind_tiled_denoise_host(nind_net* net, const float* img_chw_host, float* out
   int rc = enqueue_host_image(net, img_chw_host, out_chw_host, height, width, cs, ucs, ol, batch);
   if (rc) return rc;
   return nind_host_sync(net);
+}
+
+// ---------------------------------------------------------------- file formats either side of the path
+int nind_image_to_chw_f32(const void* src_hwc, int dtype, int height, int width, int bgr, float* dst_chw,
+                          void* stream) {
+  if (!src_hwc || !dst_chw) return fail(NIND_E_INVALID, "null argument");
+  if (dtype < NIND_PIX_U8 || dtype > NIND_PIX_F32) return fail(NIND_E_INVALID, "unknown pixel type");
+  if (height <= 0 || width <= 0) return fail(NIND_E_INVALID, "illegal image size");
+  PixConvParams p;
+  p.hwc = const_cast<void*>(src_hwc); p.chw = dst_chw; p.h = height; p.w = width; p.dtype = dtype; p.bgr = bgr ? 1 : 0;
+  image_to_chw_kernel<<<grid_for((long long)height * width), 256, 0, static_cast<cudaStream_t>(stream)>>>(p);
+  ++g_launches;
+  CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+
+int nind_chw_f32_to_image(const float* src_chw, int height, int width, int dtype, int bgr, void* dst_hwc,
+                          void* stream) {
+  if (!src_chw || !dst_hwc) return fail(NIND_E_INVALID, "null argument");
+  if (dtype < NIND_PIX_U8 || dtype > NIND_PIX_F32) return fail(NIND_E_INVALID, "unknown pixel type");
+  if (height <= 0 || width <= 0) return fail(NIND_E_INVALID, "illegal image size");
+  PixConvParams p;
+  p.hwc = dst_hwc; p.chw = const_cast<float*>(src_chw); p.h = height; p.w = width; p.dtype = dtype; p.bgr = bgr ? 1 : 0;
+  chw_to_image_kernel<<<grid_for((long long)height * width), 256, 0, static_cast<cudaStream_t>(stream)>>>(p);
+  ++g_launches;
+  CUDA_TRY(cudaGetLastError());
+  return 0;
 }
 
 }  // extern "C"

@@ -71,13 +71,15 @@ __device__ __forceinline__ uint32_t mbar_try_wait(uint32_t bar, uint32_t parity)
       : "memory");
   return ok;
 }
-// Bounded wait.  `err` may be null.  `code` identifies the waiting role.
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int* err, int code) {
+// Bounded wait.  `err` may be null (it points to mapped, page-locked HOST memory, so the role code survives the
+// trap that poisons the context).  `code` identifies the waiting role.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int* err, int code,
+                                          long long limit = NIND_WAIT_CYCLES) {
   if (mbar_try_wait(bar, parity)) return;
   const long long t0 = clock64();
   while (!mbar_try_wait(bar, parity)) {
-    if (clock64() - t0 > NIND_WAIT_CYCLES) {
-      if (err) atomicExch(err, code);
+    if (clock64() - t0 > limit) {
+      if (err) *reinterpret_cast<volatile int*>(err) = code;
       __threadfence_system();
       __trap();
     }
@@ -103,6 +105,31 @@ __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* m, 
       "%5}], [%2];" ::"r"(dst),
       "l"(m), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
       : "memory");
+}
+
+// TMA stores (shared -> global, bulk async-group completion).  The epilogue writes its bf16 tile into a
+// 64B-swizzled staging buffer and one lane hands it to the TMA unit: no LDS / STG write-out pass through the
+// L1 data pipe, and out-of-range pixels (tile edges, rows past an image) are clipped by the tensor map.
+__device__ __forceinline__ void tma_store_5d(const CUtensorMap* m, uint32_t src, int c0, int c1, int c2, int c3,
+                                             int c4) {
+  asm volatile(
+      "cp.async.bulk.tensor.5d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5, %6}], [%1];" ::"l"(m),
+      "r"(src), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+      : "memory");
+}
+__device__ __forceinline__ void bulk_commit_group() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+// all but the newest N groups of this thread have finished READING their shared-memory source
+template <int N>
+__device__ __forceinline__ void bulk_wait_group_read() {
+  asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
+}
+template <int N>
+__device__ __forceinline__ void bulk_wait_group() {
+  asm volatile("cp.async.bulk.wait_group %0;" ::"n"(N) : "memory");
+}
+// generic-proxy shared-memory writes -> visible to the async proxy (TMA)
+__device__ __forceinline__ void fence_proxy_async_smem() {
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 }
 
 // ---------------------------------------------------------------- tcgen05 / TMEM

@@ -42,13 +42,18 @@ class _NativeNet(nn.Module):
         d["_packed_key"] = None
         return d
 
-    def __del__(self):
+    def _drop_handle(self):
         h = getattr(self, "_handle", None)
         if h:
             try:
                 _capi.lib().nind_net_destroy(h)
             except Exception:
                 pass
+        self._handle = None
+        self._packed_key = None
+
+    def __del__(self):
+        self._drop_handle()
 
     def _state_key(self):
         # storage identity + in-place version counter of every parameter and buffer: changes on
@@ -70,6 +75,9 @@ class _NativeNet(nn.Module):
         if dev.type != "cuda":
             raise RuntimeError(f"{type(self).__name__} (nind_denoise_b200) runs on CUDA sm_100 devices only; "
                                f"parameters are on {dev}. There is no CPU fallback.")
+        if self._handle is not None and dev != getattr(self, "_device", dev):
+            # .to(another GPU): the handle's streams, events, arenas and scratch live on the old device
+            self._drop_handle()
         lib = _capi.lib()
         with torch.cuda.device(dev):
             arr, n, keep = _capi.make_tensor_array(self.state_dict())
@@ -87,7 +95,7 @@ class _NativeNet(nn.Module):
         self._device = dev
         return self._handle
 
-    def _forward_native(self, x: torch.Tensor) -> torch.Tensor:
+    def _forward_native(self, x: torch.Tensor, flags: int = 0) -> torch.Tensor:
         if not x.is_cuda:
             raise RuntimeError(f"{type(self).__name__} (nind_denoise_b200): input must be a CUDA tensor, got "
                                f"{x.device}. There is no CPU fallback.")
@@ -100,9 +108,14 @@ class _NativeNet(nn.Module):
         out = torch.empty_like(xin)
         with torch.cuda.device(x.device):
             stream = torch.cuda.current_stream().cuda_stream
-            _capi.check(_capi.lib().nind_net_forward(h, xin.data_ptr(), out.data_ptr(), xin.shape[0], xin.shape[2],
-                                                     xin.shape[3], C.c_void_p(stream)))
+            _capi.check(_capi.lib().nind_net_forward_ex(h, xin.data_ptr(), out.data_ptr(), xin.shape[0], xin.shape[2],
+                                                        xin.shape[3], flags, C.c_void_p(stream)))
         return out
+
+    def denoise_batch(self, noisy_batch: torch.Tensor) -> torch.Tensor:
+        """``Generator.denoise_batch`` of the reference (nn_common.py:198-199: ``model(x).clip(0, 1)``), the call
+        its validation / test passes make (nn_train.py:51-93); the clamp runs inside the output head's epilogue."""
+        return self._forward_native(noisy_batch, _capi.NIND_FWD_CLAMP01)
 
     def layer_times(self, x: torch.Tensor):
         """Per-layer (name, ms, flops) of one forward, measured with CUDA events (debug/profiling aid)."""
@@ -211,6 +224,11 @@ class UNet(_NativeNet):
         if self.find_noise:  # ThirdPartyNets.py:167-168
             return x - y
         return y
+
+    def denoise_batch(self, noisy_batch: torch.Tensor) -> torch.Tensor:
+        if self.find_noise:  # the clamp applies to y - sigmoid(x), which is formed here
+            return self.forward(noisy_batch).clip(0, 1)
+        return self._forward_native(noisy_batch, _capi.NIND_FWD_CLAMP01)
 
 
 def register(nn_common_module=None):

@@ -20,7 +20,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 def test_library_exports_every_declared_symbol():
     hdr = open(os.path.join(ROOT, "include", "nind_b200.h")).read()
     hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
-    declared = set(re.findall(r"\b(nind_[a-z_]+)\s*\(", hdr))
+    declared = set(re.findall(r"\b(nind_[a-z0-9_]+)\s*\(", hdr))
     assert len(declared) >= 15
     lib = ctypes.CDLL(_build.build())
     for name in declared:

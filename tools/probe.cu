@@ -292,18 +292,13 @@ static int run_conv(int argc, char** argv) {
   const int ctas = argc > 13 ? atoi(argv[13]) : 0;
   const int cg = argc > 14 ? atoi(argv[14]) : 0;
   const int flat = argc > 15 ? atoi(argv[15]) : -1;
-#if NIND_PAIR_MODE
-  const int pair = argc > 16 ? atoi(argv[16]) : 0;   // EXPERIMENTAL pixel-pair mode (C_out = 64 layers)
-#endif
+  const int pair = argc > 16 ? atoi(argv[16]) : 0;   // pixel-pair mode (C_out = 64 layers)
+  const int pool = argc > 17 ? atoi(argv[17]) : 0;   // fused 2x2 max-pool into a second buffer (EPI_STORE, even sizes)
   const int tw = taps == 9 ? 3 : 1;
   const int Hv = Hs - (tw - 1), Wv = Ws - (tw - 1);
   const bool c8 = cin == 8;              // first-layer mode: 8-channel input, no-swizzle descriptors
-#if NIND_PAIR_MODE
   // read a channel sub-range to exercise offsets (pair mode views the whole buffer as [rows, W/2, 2C])
   const int Cbuf = c8 ? 8 : (pair ? cin : cin + 64), coff = (c8 || pair) ? 0 : 64;
-#else
-  const int Cbuf = c8 ? 8 : cin + 64, coff = c8 ? 0 : 64;  // read a channel sub-range to exercise offsets
-#endif
   const int act = ACT_PRELU;
   const float slope = 0.25f;
 
@@ -349,7 +344,6 @@ static int run_conv(int argc, char** argv) {
     CK(cudaMemcpy(dw8, w8.data(), w8.size() * 2, cudaMemcpyHostToDevice));
     s.c8 = true;
   }
-#if NIND_PAIR_MODE
   __nv_bfloat16* dwp = nullptr;
   if (pair) {
     std::vector<__nv_bfloat16> wp;
@@ -359,9 +353,6 @@ static int run_conv(int argc, char** argv) {
     s.pair = true;
   }
   s.in_coff = coff; s.cin = cin; s.taps = taps; s.w = c8 ? dw8 : (pair ? dwp : dw); s.n_total = n_total; s.bias = dbias;
-#else
-  s.in_coff = coff; s.cin = cin; s.taps = taps; s.w = c8 ? dw8 : dw; s.n_total = n_total; s.bias = dbias;
-#endif
   s.act = act; s.slope = slope; s.epi_mode = epi; (void)a_mode; (void)bo_mode;
   s.n_tile = n_tile; s.force_ws = ws; s.max_ctas = ctas; s.cg = cg; s.flat = flat;
   const int halo = 2, ocoff = 32;
@@ -392,6 +383,16 @@ static int run_conv(int argc, char** argv) {
     s.head_out = dhead;
   }
 
+  __nv_bfloat16* dpool = nullptr;
+  const int phalo = 1, Hp = Hv / 2 + 2 * phalo, Wp = Wv / 2 + 2 * phalo;
+  std::vector<__nv_bfloat16> hpool;
+  if (pool && epi == EPI_STORE) {
+    hpool.assign((size_t)B * Hp * Wp * n_total, __float2bfloat16(-77.f));
+    CK(cudaMalloc(&dpool, hpool.size() * 2));
+    CK(cudaMemcpy(dpool, hpool.data(), hpool.size() * 2, cudaMemcpyHostToDevice));
+    s.pool = ActBuf{dpool, B, Hp, Wp, n_total};
+    s.pool_halo = phalo;
+  }
   IgemmLaunch L;
   std::string why;
   if (!build_igemm(s, &L, &why)) { printf("build_igemm failed: %s\n", why.c_str()); return 2; }
@@ -490,6 +491,27 @@ static int run_conv(int argc, char** argv) {
     for (size_t i = 0; i < hout.size(); ++i)
       if (!touched[i] && __bfloat162float(hout[i]) != -77.f) ++stray;
     if (stray) { printf("  %lld stray writes outside the valid region\n", stray); bad += stray; }
+    if (dpool) {  // the pooled tensor must be exactly the 2x2 maximum of the stored (bf16) tensor
+      CK(cudaMemcpy(hpool.data(), dpool, hpool.size() * 2, cudaMemcpyDeviceToHost));
+      long long pbad = 0;
+      for (int b = 0; b < B; ++b)
+        for (int y = 0; y < Hp; ++y)
+          for (int x = 0; x < Wp; ++x)
+            for (int n = 0; n < n_total; ++n) {
+              const float got = __bfloat162float(hpool[(((size_t)b * Hp + y) * Wp + x) * n_total + n]);
+              float exp = -77.f;
+              const int py = y - phalo, px = x - phalo;
+              if (py >= 0 && py < Hv / 2 && px >= 0 && px < Wv / 2) {
+                exp = -1e30f;
+                for (int dy = 0; dy < 2; ++dy)
+                  for (int dx = 0; dx < 2; ++dx)
+                    exp = fmaxf(exp, __bfloat162float(hout[(((size_t)b * Ho + 2 * py + dy + halo) * Wo + 2 * px + dx + halo) * Co + ocoff + n]));
+              }
+              if (got != exp) { if (pbad < 6) printf("  pool mismatch b=%d y=%d x=%d n=%d got=%f exp=%f\n", b, y, x, n, got, exp); ++pbad; }
+            }
+      printf("  pool: %lld mismatches\n", pbad);
+      bad += pbad;
+    }
   }
   int herr = 0;
   CK(cudaMemcpy(&herr, derr, 4, cudaMemcpyDeviceToHost));
