@@ -18,7 +18,7 @@
 //
 // Warp roles (128 + 128*ES threads, 1 CTA/SM, persistent over tiles):
 //   warp 0: TMA producer for activation patches      warp 1: TMA producer for weight tiles
-//   warp 2: tcgen05.mma issuer (one elected lane)    warp 3: TMEM allocator
+//   warps 2, 3: tcgen05.mma issuers on alternate tiles (one elected lane each); warp 3 also allocates TMEM
 //   warps 4.. : ES epilogue sets of four warps, one per TMEM accumulator stage:
 //              tcgen05.ld -> bias/activation -> bf16 -> 64B-swizzled smem staging -> ONE TMA store per warp and
 //              32-channel half (cp.async.bulk.tensor, bulk-group completion).  The tensor map clips tile edges
@@ -40,14 +40,26 @@ constexpr int IG_BAR_BYTES = 2048;     // mbarriers + TMEM base slot
 #define NIND_SETS64 4
 #endif
 #ifndef NIND_SETS_PM
-#define NIND_SETS_PM 2
+#define NIND_SETS_PM 4
 #endif
 #ifndef NIND_EPI_X16
 #define NIND_EPI_X16 1
 #endif
 constexpr int IG_MAX_SETS = 4;         // epilogue warp sets (= TMEM accumulator stages)
 constexpr int IG_EPI_BYTES = IG_MAX_SETS * 3072;  // per set: staged bias [2][256] fp32 (+ spare)
-constexpr int IG_SET_STAGE_BYTES = 8192;          // per set: 4 warps x 32 rows x 64 B of store staging
+// Store staging: NBUF buffers of 32 rows x 64 B per epilogue warp, used round-robin by the warp's TMA stores
+// (bulk groups retire in order, so "all but the newest NBUF-1 groups have read their source" frees the next
+// buffer).  One buffer made every 32-channel half wait ~1500 clk for the previous half's store — the TMA unit
+// also serves the activation loads — (profiles/r02_pipeline_trace_tma_store.log).
+#ifndef NIND_STG_BUFS
+#define NIND_STG_BUFS 0
+#endif
+__host__ __device__ constexpr int ig_stg_bufs(int n_tile, bool pm = false) {
+  return NIND_STG_BUFS ? NIND_STG_BUFS : ((pm || n_tile == 64) ? 2 : 4);
+}
+__host__ __device__ constexpr int ig_set_stage_bytes(int n_tile, bool pm = false) {
+  return 4 * ig_stg_bufs(n_tile, pm) * 2048;  // per set: 4 warps x NBUF x 2 KB
+}
 // Epilogue sets per kernel: N_TILE = 64 layers are epilogue-bound with two sets (their MMA phase per tile
 // is short), and their accumulators are small, so they get four (B200 A/B, same box: 64->64 572 / 651 / 680 TFLOP/s with 2 / 3 / 4 sets).
 __host__ __device__ constexpr int ig_sets(int n_tile, bool pm = false) {
@@ -68,6 +80,7 @@ struct IgemmParams {
   uint32_t a_tx_bytes;     // bytes TMA delivers per A stage
   uint32_t a_sbo;          // bytes per patch row = distance between 8-row groups of the A operand
   int sa, sb, ws;          // stage counts; ws = weights stay resident in shared memory
+  int dual;                // two MMA issuer warps on alternate tiles (see the issuer role)
   // output geometry
   int hs_in;               // stored rows per image of the input buffer
   int rows_total;          // images * hs_in
@@ -120,7 +133,7 @@ enum { TR_A_ISSUE = 0, TR_MMA_TEMPTY = 1, TR_MMA_AFULL = 2, TR_MMA_DONE = 3, TR_
 __host__ __device__ inline size_t igemm_smem_bytes(int n_tile, int tps, int cg, int sa, uint32_t a_stage_bytes,
                                                    int sb, bool pm = false) {
   return 1024 + (size_t)sa * a_stage_bytes + (size_t)sb * tps * (n_tile / cg) * 128 + IG_BAR_BYTES +
-         IG_EPI_BYTES + (size_t)ig_sets(n_tile, pm) * IG_SET_STAGE_BYTES;
+         IG_EPI_BYTES + (size_t)ig_sets(n_tile, pm) * ig_set_stage_bytes(n_tile, pm);
 }
 
 // N_TILE: GEMM N per tile (64/128/256).  TPS: taps per weight pipeline stage (1 or 3).
@@ -161,7 +174,8 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
   const uint32_t a_base = sbase;
   const uint32_t b_base = a_base + (uint32_t)p.sa * p.a_stage_bytes;
   const uint32_t stg_base = b_base + (uint32_t)p.sb * B_BYTES;  // 1024-aligned
-  const uint32_t bar_base = stg_base + ES * IG_SET_STAGE_BYTES;
+  constexpr int NBUF = ig_stg_bufs(N_TILE, PM);
+  const uint32_t bar_base = stg_base + ES * ig_set_stage_bytes(N_TILE, PM);
   const uint32_t a_full = bar_base;
   const uint32_t a_empty = bar_base + 8 * IG_MAX_STAGES;
   const uint32_t b_full = bar_base + 16 * IG_MAX_STAGES;
@@ -169,6 +183,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
   const uint32_t t_full = bar_base + 32 * IG_MAX_STAGES;
   const uint32_t t_empty = t_full + 32;
   const uint32_t tmem_slot = t_full + 64;
+  const uint32_t go_bar = t_full + 80;  // two "go" batons of the dual MMA issuers
   const uint32_t epi_base = bar_base + IG_BAR_BYTES;
 
   const int warp = threadIdx.x >> 5;
@@ -189,6 +204,8 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       mbar_init(t_full + 8 * s, 1);
       mbar_init(t_empty + 8 * s, 4 * CG);
     }
+    mbar_init(go_bar, 1);
+    mbar_init(go_bar + 8, 1);
     mbar_fence_init();
   }
   if (warp == 3) {
@@ -292,23 +309,48 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         }
       }
     }
-  } else if (warp == 2 && cg_rank == 0) {
-    // ------------------------------------------------ MMA issuer (leader CTA only in a pair)
+  } else if ((warp == 2 || warp == 3) && cg_rank == 0) {
+    // ------------------------------------------------ MMA issuers (leader CTA only in a pair)
     // The whole warp walks the loop (warp-uniform control flow and addresses, so descriptors live
     // in uniform registers); one elected lane issues tcgen05.mma / tcgen05.commit.
+    //
+    // Two issuer warps take alternate tiles (p.dual).  Between the last MMA of a tile and the first MMA of the
+    // next a single issuer spends ~430 clk on two commits, two mbarrier waits (~90 clk each even when the phase
+    // completed long ago) and fences, and the tensor pipe — whose queue is only an MMA or two deep — idles:
+    // 22 % of a 64->64 tile, 12 % of a 128->64 tile (profiles/r02_pipeline_trace_tma_store.log).  With two
+    // issuers the other warp has already done its waits and only needs the "go" baton, which its peer passes
+    // right after issuing its last MMA, so the MMAs enter the pipe in exactly the single-issuer order.
+    // Ring positions are derived from the tile ordinal.  A parity wait must not run two fills ahead of the
+    // barrier: the first activation chunk of a tile may be waited for ahead of the baton when the previous fill
+    // of its stage belonged to this issuer's own previous tile or an earlier one (sa >= kchunks + 1);
+    // accumulator stages are safe because ES is even (the previous user of a stage is a tile of the same
+    // issuer); everything else is waited for in pipe order, after the baton.
     constexpr uint32_t DESC_HI_B = (1024u >> 4) | (1u << 14) | (2u << 29);
     const uint32_t desc_hi_a = (p.a_sbo >> 4) | (1u << 14) | (2u << 29);
     const uint32_t pitch16 = p.tap_pitch16;  // one patch row, in 16-byte units
-    uint32_t sa_i = 0, pha = 0, sb_i = 0, phb = 0, acc = 0, aph = 0;
-    int tl = 0;
-    for (int tile = tile0; tile < p.total_tiles; tile += tstep, ++tl) {
+    const int iw = warp - 2;
+    const bool dual = p.dual != 0;
+    const uint32_t go_mine = go_bar + 8 * iw, go_peer = go_bar + 8 * (iw ^ 1);
+    const bool pre_a = !dual || p.sa >= p.kchunks + 1;
+    uint32_t go_ph = 0;
+    for (int tl = dual ? iw : 0; (dual || iw == 0) && tile0 + tl * tstep < p.total_tiles; tl += dual ? 2 : 1) {
+      const uint32_t acc = (uint32_t)tl % (uint32_t)ES, aph = ((uint32_t)tl / (uint32_t)ES) & 1u;
+      const uint32_t c0 = (uint32_t)tl * (uint32_t)p.kchunks;
+      uint32_t sa_i = c0 % (uint32_t)p.sa, pha = (c0 / (uint32_t)p.sa) & 1u;
+      const uint32_t g0 = c0 * (uint32_t)groups;
+      uint32_t sb_i = g0 % (uint32_t)p.sb, phb = (g0 / (uint32_t)p.sb) & 1u;
       NIND_MBW(t_empty + 8 * acc, aph ^ 1, 3);
-      tc_fence_after();
       NIND_TRACE(tl, TR_MMA_TEMPTY);
+      if (pre_a) NIND_MBW(a_full + 8 * sa_i, pha, 4);
+      if (dual && tl > 0) {
+        NIND_MBW(go_mine, go_ph, 7);
+        go_ph ^= 1;
+      }
+      tc_fence_after();
       const uint32_t d = tmem_base + acc * N_TILE;
       uint32_t accum = 0;
       if (C8) {
-        NIND_MBW(a_full + 8 * sa_i, pha, 4);
+        if (!pre_a) NIND_MBW(a_full + 8 * sa_i, pha, 4);
         NIND_TRACE(tl, TR_MMA_AFULL);
         if (tl == 0) NIND_MBW(b_full, 0, 5);
         tc_fence_after();
@@ -319,28 +361,28 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         const uint32_t b0 = (b_base >> 4) & 0x3FFF;
         if (elect_one_sync()) {
           // (first tap pixel offset, LBO in pixels): taps (0,1) (2,3) (4,5) (6,7) (7*,8); 7* has zero weights
-          const uint32_t off[5] = {0, 2, 11, 20, 21}, lbo[5] = {1, 8, 1, 1, 1};
-#pragma unroll
-          for (int j = 0; j < 5; ++j) {
-            umma_bf16_lohi(d, (a0 + off[j]) | (lbo[j] << 16), HI_A, (b0 + j * 128) | ((1024u >> 4) << 16), HI_B, IDESC,
-                           accum);
-            accum = 1;
-          }
+          constexpr uint32_t BLO = (1024u >> 4) << 16;
+          umma_bf16_lohi(d, (a0 + 0) | (1u << 16), HI_A, (b0 + 0 * 128) | BLO, HI_B, IDESC, 0u);
+          umma_bf16_lohi(d, (a0 + 2) | (8u << 16), HI_A, (b0 + 1 * 128) | BLO, HI_B, IDESC, 1u);
+          umma_bf16_lohi(d, (a0 + 11) | (1u << 16), HI_A, (b0 + 2 * 128) | BLO, HI_B, IDESC, 1u);
+          umma_bf16_lohi(d, (a0 + 20) | (1u << 16), HI_A, (b0 + 3 * 128) | BLO, HI_B, IDESC, 1u);
+          umma_bf16_lohi(d, (a0 + 21) | (1u << 16), HI_A, (b0 + 4 * 128) | BLO, HI_B, IDESC, 1u);
+          if (dual) mbar_arrive(go_peer);
           umma_commit(a_empty + 8 * sa_i);
+          umma_commit(t_full + 8 * acc);
         }
-        __syncwarp();
-        if (++sa_i == (uint32_t)p.sa) { sa_i = 0; pha ^= 1; }
       }
       if (PM) {
         constexpr uint32_t IDESC64 = umma_idesc_bf16(256, 64);
         const int half_chunks = p.kchunks >> 1;
         for (int kc = 0; kc < p.kchunks; ++kc) {
-          NIND_MBW(a_full + 8 * sa_i, pha, 4);
+          if (!(pre_a && kc == 0)) NIND_MBW(a_full + 8 * sa_i, pha, 4);
           if (kc == 0) NIND_TRACE(tl, TR_MMA_AFULL);
           if (tl == 0 && kc == 0) NIND_MBW(b_full, 0, 5);
           tc_fence_after();
           const uint32_t e = kc >= half_chunks ? 1u : 0u;  // which pixel of the input pair this chunk holds
           const uint32_t a_lo0 = (((a_base + sa_i * p.a_stage_bytes) >> 4) & 0x3FFF) | (1u << 16);
+          const bool last = kc + 1 == p.kchunks;
           if (elect_one_sync()) {
 #pragma unroll
             for (uint32_t ky = 0; ky < 3; ++ky) {
@@ -357,15 +399,16 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
                 umma_bf16_lohi_cg2(d + e * 64, a64 + 2 * k, desc_hi_a, b_blk + (8192u >> 4) + 2 * k, DESC_HI_B, IDESC64,
                                    1u);
             }
+            if (dual && last) mbar_arrive(go_peer);
             umma_commit_cg2(a_empty + 8 * sa_i);
+            if (last) umma_commit_cg2(t_full + 8 * acc);
           }
-          __syncwarp();
           accum = 1;
           if (++sa_i == (uint32_t)p.sa) { sa_i = 0; pha ^= 1; }
         }
       }
       for (int kc = 0; kc < p.kchunks && !C8 && !PM; ++kc) {
-        NIND_MBW(a_full + 8 * sa_i, pha, 4);
+        if (!(pre_a && kc == 0)) NIND_MBW(a_full + 8 * sa_i, pha, 4);
         if (kc == 0) NIND_TRACE(tl, TR_MMA_AFULL);
         const uint32_t a_lo0 = (((a_base + sa_i * p.a_stage_bytes) >> 4) & 0x3FFF) | (1u << 16);
         uint32_t ky = 0, kx = 0;  // tap of the first MMA of the group
@@ -374,6 +417,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
           tc_fence_after();
           const uint32_t a_lo = a_lo0 + ky * pitch16 + kx * 8;  // (ky*pitch + kx) rows of 128 B
           const uint32_t b_lo = (((b_base + sb_i * B_BYTES) >> 4) & 0x3FFF) | (1u << 16);
+          const bool last_g = g + 1 == groups, last = last_g && kc + 1 == p.kchunks;
           if (elect_one_sync()) {
 #pragma unroll
             for (uint32_t j = 0; j < (uint32_t)TPS; ++j) {
@@ -388,12 +432,20 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
                 accum = 1;
               }
             }
+            if (dual && last) mbar_arrive(go_peer);  // the baton: the peer issuer's tile follows in the pipe
             if (!p.ws) {
               if (CG == 2) umma_commit_cg2(b_empty + 8 * sb_i);
               else umma_commit(b_empty + 8 * sb_i);
             }
+            if (last_g) {
+              if (CG == 2) umma_commit_cg2(a_empty + 8 * sa_i);
+              else umma_commit(a_empty + 8 * sa_i);
+            }
+            if (last) {
+              if (CG == 2) umma_commit_cg2(t_full + 8 * acc);
+              else umma_commit(t_full + 8 * acc);
+            }
           }
-          __syncwarp();
           accum = 1;
           if (++sb_i == (uint32_t)p.sb) { sb_i = 0; phb ^= 1; }
           if (TPS == 3) {
@@ -403,20 +455,9 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
             ++ky;
           }
         }
-        if (elect_one_sync()) {
-          if (CG == 2) umma_commit_cg2(a_empty + 8 * sa_i);
-          else umma_commit(a_empty + 8 * sa_i);
-        }
-        __syncwarp();
         if (++sa_i == (uint32_t)p.sa) { sa_i = 0; pha ^= 1; }
       }
-      if (elect_one_sync()) {
-        if (CG == 2) umma_commit_cg2(t_full + 8 * acc);
-        else umma_commit(t_full + 8 * acc);
-      }
-      __syncwarp();
       NIND_TRACE(tl, TR_MMA_DONE);
-      if (++acc == (uint32_t)ES) { acc = 0; aph ^= 1; }
     }
   } else if (warp >= 4) {
     // ------------------------------------------------ epilogue
@@ -427,9 +468,10 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     const int etid = threadIdx.x - 128 - eset * 128;  // 0..127 inside the set
     uint8_t* smem_gen = smem_raw + (sbase - smem_u32(smem_raw));
     float* bias_s = reinterpret_cast<float*>(smem_gen + (epi_base - sbase) + eset * 3072);  // [2][256] per set
-    const uint32_t stg_off = (stg_base - sbase) + (eset * 4 + quarter) * 2048;
-    uint8_t* stg = smem_gen + stg_off;       // this warp's staging: 32 rows x 64 B, rows = (tile row, pixel)
-    const uint32_t stg_s = sbase + stg_off;  // same, shared-space address (TMA source)
+    const uint32_t stg_off = (stg_base - sbase) + (eset * 4 + quarter) * (NBUF * 2048);
+    uint8_t* const stg0 = smem_gen + stg_off;  // this warp's NBUF staging buffers: 32 rows x 64 B, rows = (tile row, pixel)
+    const uint32_t stg_s0 = sbase + stg_off;   // same, shared-space address (TMA source)
+    uint32_t bufi = 0;                         // staging buffer of the next 32-channel half
     constexpr int n_groups = N_TILE / 64;
     constexpr int CW = ((N_TILE == 64 && NIND_EPI_X16) || (PM && ig_sets(N_TILE, PM) > 2)) ? 16 : 32;  // accumulator columns per TMEM load
     const uint32_t acc = eset;
@@ -440,12 +482,12 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     // Read side (fused pool, flat tiles): 4 lanes cover one pixel's 32 channels; lane (sub, ch) reads pixel
     // column `sub` of the warp's four tile rows.
     const int sub = lane >> 2, ch = lane & 3;
-    uint8_t* const stg_w = stg + lane * 64;
+    const uint32_t off_w = lane * 64;
     const int sw_w = (lane >> 1) & 3;
-    const uint8_t* const stg_r = stg + sub * 64 + ((ch ^ ((sub >> 1) & 3)) << 4);  // + it * 512
+    const uint32_t off_r = sub * 64 + ((ch ^ ((sub >> 1) & 3)) << 4);  // + it * 512
     // fused 2x2 max-pool: lane -> (pooled pixel sub, 16-byte chunk ch); source rows r00, +1, +8, +9
     const int r00 = (sub >> 2) * 16 + (sub & 3) * 2;
-    const uint8_t* const stg_p = stg + r00 * 64 + ((ch ^ ((r00 >> 1) & 3)) << 4);
+    const uint32_t off_p = r00 * 64 + ((ch ^ ((r00 >> 1) & 3)) << 4);
 
     // The tile loop is instantiated per (store mode, activation) so that nothing is decided per element:
     // MODE 0 store, 1 store + fused max-pool, 2 depth-to-space (all three: TMA stores), 3 fused 1x1 head,
@@ -569,6 +611,11 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
           }
 #pragma unroll
           for (int half = 0; half < 2; ++half) {
+            uint8_t* const stg = stg0 + bufi * 2048;  // staging buffer of this half
+            uint8_t* const stg_w = stg + off_w;
+            const uint8_t* const stg_r = stg + off_r;
+            const uint8_t* const stg_p = stg + off_p;
+            const uint32_t stg_s = stg_s0 + bufi * 2048;
             // CW accumulator columns at a time (16 for the 640-thread kernels, whose 96-register
             // budget a 32-wide chunk overflows)
 #pragma unroll
@@ -630,8 +677,8 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
                   h2 = fmaf(f[j], p.head_c[128 + half * 32 + q * CW + j], h2);
                 }
               } else {
-                if (TMA && q == 0) {  // the TMA store of the previous half has finished reading the staging rows
-                  if (lane == 0) bulk_wait_group_read<0>();
+                if (TMA && q == 0) {  // the TMA store that last used this staging buffer has finished reading it
+                  if (lane == 0) bulk_wait_group_read<NBUF - 1>();
                   __syncwarp();
                 }
                 // this thread's channels -> staging row (64 B per half), 16-byte chunks XOR-swizzled
@@ -698,6 +745,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
                 }
                 bulk_commit_group();
               }
+              bufi = bufi + 1 == NBUF ? 0 : bufi + 1;
             } else if (!HEAD) {
               __syncwarp();
               // flat tiles: coalesced write-out, 8 pixels x 64 B per warp instruction

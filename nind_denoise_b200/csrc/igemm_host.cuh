@@ -45,6 +45,7 @@ struct ConvSpec {
   int cg = 0;         // CTAs per tile group: 0 = auto, 1, or 2 (cta_group::2 pair)
   bool c8 = false;    // first layer over the 8-channel padded-crop tensor (C_in = 3 as hi/lo bf16)
   int force_ws = -1;  // -1 = auto
+  int dual = -1;      // two MMA issuer warps: -1 auto (on), 0 off, 1 on
   int max_ctas = 0;   // 0 = number of SMs
 };
 
@@ -289,6 +290,7 @@ inline bool build_igemm(const ConvSpec& s, IgemmLaunch* L, std::string* why) {
     while (p.sa < 4 && fits(p.sa + 1, p.sb)) ++p.sa;
   }
   p.ws = ws ? 1 : 0;
+  p.dual = s.dual != 0 ? 1 : 0;
   L->smem = igemm_smem_bytes(n_tile, tps, cg, p.sa, p.a_stage_bytes, p.sb, s.pair);
 
   // tensor maps

@@ -35,7 +35,7 @@ int fail(int code, const std::string& m) {
 struct PackedLayer {
   int taps = 9, cin = 0, n_total = 0, cout = 0;
   __nv_bfloat16* w = nullptr;  // device [taps][n_total][cin]
-  __nv_bfloat16* w_pair = nullptr;  // device, pack_pair_weights() layout (3x3 layers with C_out = 64, C_in = 64 | 128)
+  __nv_bfloat16* w_pair = nullptr;  // device, pack_pair_weights() layout (3x3 layers with C_out = C_in = 64)
   float* bias = nullptr;       // device
   int act = ACT_NONE;
   float slope = 0.f;
@@ -136,7 +136,7 @@ struct nind_net {
   int pair64 = 1;  // pixel-pair mode for the C_out = 64 3x3 layers (validated on B200, profiles/r02_pair_mode_first_light.log)
   int host_first = -1, host_last = -1;  // crops in the first / last pipeline step (-1: one grid row)
   // options
-  int n_tile_deep = 256, max_ctas = 0, cg = 0, fuse_pool = 1;
+  int n_tile_deep = 256, max_ctas = 0, cg = 0, fuse_pool = 1, dual = -1;
   // timing
   int timing = 0;
   std::vector<std::string> t_names;
@@ -211,7 +211,7 @@ int upload_layer(nind_net* net, const std::string& name, PackedLayer& L, const s
   CUDA_TRY(cudaMemcpy(L.w, w.data(), w.size() * sizeof(__nv_bfloat16), cudaMemcpyHostToDevice));
   CUDA_TRY(cudaMalloc(&L.bias, bias.size() * sizeof(float)));
   CUDA_TRY(cudaMemcpy(L.bias, bias.data(), bias.size() * sizeof(float), cudaMemcpyHostToDevice));
-  if (L.taps == 9 && L.n_total == 64 && (L.cin == 64 || L.cin == 128)) {  // pixel-pair mode candidate (igemm.cuh "PM")
+  if (L.taps == 9 && L.n_total == 64 && L.cin == 64) {  // pixel-pair mode candidate (igemm.cuh "PM")
     std::vector<__nv_bfloat16> wp;
     pack_pair_weights(w.data(), L.cin, &wp);
     CUDA_TRY(cudaMalloc(&L.w_pair, wp.size() * sizeof(__nv_bfloat16)));
@@ -456,6 +456,7 @@ struct PlanBuilder {
     s.c8 = c8;
     s.max_ctas = net->max_ctas;
     s.cg = net->cg;
+    s.dual = net->dual;
     s.flat = net->flat == 1 ? 2 : net->flat;  // 1 = on every layer where it is legal
     if (L.n_total >= 256) s.n_tile = net->n_tile_deep;
     maybe_pair(s, L, in, in_coff);
@@ -496,6 +497,7 @@ struct PlanBuilder {
     s.head_unpad = unpad; s.head_hy = hy; s.head_hx = hx; s.head_sigmoid = sigmoid;
     s.max_ctas = net->max_ctas;
     s.cg = net->cg;
+    s.dual = net->dual;
     maybe_pair(s, L, in, 0);
     if (rc) return;
     Step st;
@@ -894,6 +896,8 @@ int nind_set_option(nind_net* net, const char* key, int value) {
     net->fuse_pool = value ? 1 : 0;
   } else if (k == "pair64") {  // pixel-pair mode for the C_out = 64 3x3 layers (0 | 1)
     net->pair64 = value ? 1 : 0;
+  } else if (k == "dual_issuer") {  // two MMA issuer warps on alternate tiles (0 | 1)
+    net->dual = value ? 1 : 0;
   } else if (k == "flat") {  // flat (1-D) tiles on narrow maps: -1 auto, 0 off, 1 wherever legal
     net->flat = value;
   } else {

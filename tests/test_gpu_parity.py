@@ -425,35 +425,46 @@ def test_host_range_pipeline_composes_to_the_whole_image(utnet, world):
 
 @pytest.mark.gpu
 def test_dir_cli_matches_single_image_path(tmp_path):
-    """nind_denoise_b200.dir_cli (denoise_dir.py:76-103 without the per-image subprocess): a
-    directory streamed through the async host entry gives, file by file, what the single-image CLI writes."""
+    """nind_denoise_b200.dir_cli (denoise_dir.py:76-129 without the per-image subprocess): a directory
+    streamed through the async host entry gives, file by file, what the single-image CLI writes; the lowest-ISO
+    file is the baseline (dataset_torch_3.get_baseline_fpath) and the averaged mse / ssim / msssim losses land in
+    testres.json next to the model (json_saver.py)."""
+    import json
+
     import cv2
-    from nind_denoise_b200 import cli, dir_cli
+    from nind_denoise_b200 import cli, dir_cli, scoring
 
     rng = np.random.default_rng(31)
-    noisy = tmp_path / "noisy"
+    noisy = tmp_path / "set_200_176"
     noisy.mkdir()
-    shapes = {"a.tif": (150, 170), "b.png": (131, 200), "c.tif": (150, 170)}
+    shapes = {"NIND_x_ISO800.tif": (180, 170), "NIND_x_ISO3200.png": (180, 170), "NIND_x_ISO6400.tif": (180, 170)}
     for name, (h, w) in shapes.items():
-        img16 = (rng.random((h, w, 3)) * 65535).astype(np.uint16)
-        cv2.imwrite(str(noisy / name), img16)
-    clean = str(noisy / "clean.tif")
-    cv2.imwrite(clean, (rng.random((150, 170, 3)) * 65535).astype(np.uint16))
-    model_path = str(tmp_path / "generator_1.pt")
+        cv2.imwrite(str(noisy / name), (rng.random((h, w, 3)) * 65535).astype(np.uint16))
+    cv2.imwrite(str(noisy / "NIND_x_ISO200.tif"), (rng.random((180, 170, 3)) * 65535).astype(np.uint16))
+    mdir = tmp_path / "2021_model"
+    mdir.mkdir()
+    model_path = str(mdir / "generator_7.pt")
     torch.save(on.init_state_dict("UtNet", seed=0), model_path)
-    out_dir = tmp_path / "out"
-    rc = dir_cli.main(["--noisy_dir", str(noisy), "--result_dir", str(out_dir), "--network", "UtNet",
-                       "--model_path", model_path, "--cs", "120", "--ucs", "96", "--baseline", clean])
+    rc = dir_cli.main(["--noisy_dir", str(noisy), "--result_dir", str(tmp_path / "out"), "--network", "UtNet",
+                       "--model_path", model_path, "--cs", "120", "--ucs", "96"])
     assert rc == 0
-    assert sorted(os.listdir(out_dir)) == sorted(shapes)
+    out_dir = tmp_path / "out" / "2021_model"          # denoise_dir.py:59: result_dir / <model directory name>
+    assert sorted(os.listdir(out_dir)) == sorted(shapes)  # the ISO200 baseline is not denoised
+    clean = torch.from_numpy(cli.img_path_to_np_flt(str(noisy / "NIND_x_ISO200.tif")))
+    per_img = []
     for name in shapes:
         single = str(tmp_path / ("single_" + name))
         cli.main(["--network", "UtNet", "--model_path", model_path, "--input", str(noisy / name), "--output", single,
-                  "--cs", "120", "--ucs", "96"])
+                  "--cs", "120", "--ucs", "96", "--exif_method", "noexif"])
         a = cv2.imread(str(out_dir / name), cv2.IMREAD_UNCHANGED)
         b = cv2.imread(single, cv2.IMREAD_UNCHANGED)
         assert a.dtype == np.uint16 and a.shape == b.shape, name
         assert np.abs(a.astype(np.int64) - b.astype(np.int64)).max() <= 1, name   # same kernels, same batches
+        per_img.append(scoring.get_losses(clean, torch.from_numpy(cli.img_path_to_np_flt(str(out_dir / name)))))
+    res = json.load(open(mdir / "testres.json"))
+    assert set(res["7"]) == {"test_mse", "test_ssim", "test_msssim"} and res["best_epoch"]["test_mse"] == 7
+    for k in ("mse", "ssim", "msssim"):  # the scores are those of the files on disk, as pt_helpers.get_losses computes
+        assert abs(res["7"]["test_" + k] - np.mean([d[k] for d in per_img])) <= 1e-5, k
 
 
 @pytest.mark.gpu
@@ -471,3 +482,290 @@ def test_whole_image_mode(utnet):
         check_pixels(got, ref, f"whole image {h}x{w} pad {pad}")
     with pytest.raises(Exception):   # padded size 100+16 is not a legal UtNet size
         nb.denoise_whole_image(torch.zeros(3, 100, 100, device=dev()), utnet, 8)
+
+
+# ------------------------------------------------------------------ headline configurations (round 2)
+def exclusive_region_errors(img, out, sd, network, cs, ucs, ol, crops):
+    """For each sampled crop: the stitched pixels it owns exclusively (useful area minus the seam bands shared with
+    neighbours) against the fp32 oracle forward of that crop.  Returns (max abs error, sigma of the oracle values)."""
+    H, W = img.shape[1], img.shape[2]
+    g = og.crop_grid(W, H, cs, ucs, ol)
+    fwd = on.utnet_forward if network == "UtNet" else on.unet_forward
+    err, refs = 0.0, []
+    with torch.no_grad():
+        for i in crops:
+            e = og.crop_entry(g, i)
+            y = fwd(sd, torch.from_numpy(og.gather_crop(img, g, i)).unsqueeze(0))[0].numpy()
+            xlo, ylo, xhi, yhi = e["usefuldim"]
+            ax, ay = e["usefulstart"]
+            h, w = yhi - ylo, xhi - xlo
+            l, t = (ol if ax != 0 else 0), (ol if ay != 0 else 0)
+            r = ol if (ax + ucs < W and ol) else 0
+            b = ol if (ay + ucs < H and ol) else 0
+            ref = y[:, ylo + t:yhi - b, xlo + l:xhi - r]
+            got = out[:, ay + t:ay + h - b, ax + l:ax + w - r]
+            assert got.shape == ref.shape and ref.size > 0
+            err = max(err, float(np.abs(got.astype(np.float64) - ref).max()))
+            refs.append(ref.ravel())
+    return err, float(np.concatenate(refs).std())
+
+
+def corner_edge_interior(nx, ny):
+    return [0, nx - 1, (ny - 1) * nx, nx * ny - 1, nx // 2, (ny // 2) * nx + nx // 2]
+
+
+@pytest.mark.parametrize("cs", [248, 504])
+def test_headline_24mp_image_against_oracle(utnet, cs):
+    """BASELINE configs[1]: the full 6000x4000 image at the benchmarked plan (default batch), six sampled crops
+    (corners, an edge, the interior) against the oracle, and equality with a batch-4 run."""
+    W, H, ucs, ol = 6000, 4000, cs - 24, 6
+    sd = on.init_state_dict("UtNet", seed=0)
+    img = torch.rand((3, H, W), generator=torch.Generator().manual_seed(1))
+    dimg = img.to(dev())
+    out = nb.denoise_tiled(dimg, utnet, cs, ucs, ol)          # default batch = bench.py's plan
+    g = og.crop_grid(W, H, cs, ucs, ol)
+    crops = corner_edge_interior(g.nx, g.ny) if cs == 248 else [0, g.size - 1, (g.ny // 2) * g.nx + g.nx // 2]
+    err, sigma = exclusive_region_errors(img.numpy(), out.cpu().numpy(), sd, "UtNet", cs, ucs, ol, crops)
+    print(f"24 MP cs {cs}: max abs {err:.3e}, sigma_out {sigma:.4f}, err/sigma {err / sigma:.3f}")
+    assert err <= MAX_ABS and err <= MAX_REL_SIGMA * sigma
+    out4 = nb.denoise_tiled(dimg, utnet, cs, ucs, ol, batch=4)
+    assert float((out4 - out).abs().max()) <= 1e-6
+    # the host-buffer entry (what bench.py's e2e leg calls) gives the same image
+    out_h = nb.denoise_tiled_host(img.pin_memory(), utnet, cs, ucs, ol)
+    assert float((out_h - out.cpu()).abs().max()) <= 1e-6
+
+
+def test_unet_cs512_multi_row_grid(unet):
+    """BASELINE configs[3] in shape: UNet at cs 512 / ucs 384 over a grid with several rows and columns."""
+    sd = on.randomize_bn_(on.init_state_dict("UNet", seed=0), seed=7)
+    W, H, cs, ucs, ol = 1000, 900, 512, 384, 6
+    img = np.random.default_rng(41).random((3, H, W), dtype=np.float32)
+    g = og.crop_grid(W, H, cs, ucs, ol)
+    assert g.nx >= 2 and g.ny >= 2
+    out = nb.denoise_tiled(torch.from_numpy(img).to(dev()), unet, cs, ucs, ol).cpu().numpy()
+    err, sigma = exclusive_region_errors(img, out, sd, "UNet", cs, ucs, ol, [0, g.nx - 1, g.size - 1, g.nx + 1])
+    print(f"UNet cs 512 {g.nx}x{g.ny} grid: max abs {err:.3e}, err/sigma {err / sigma:.3f}")
+    assert err <= MAX_ABS and err <= MAX_REL_SIGMA * sigma
+    # whole image against the oracle loop where seams are summed too (smaller image keeps the oracle quick)
+    W2, H2 = 700, 560
+    img2 = np.random.default_rng(42).random((3, H2, W2), dtype=np.float32)
+    out2 = nb.denoise_tiled(torch.from_numpy(img2).to(dev()), unet, cs, ucs, ol).cpu().numpy()
+    with torch.no_grad():
+        ref2 = og.denoise_tiled(img2, lambda c: on.unet_forward(sd, torch.from_numpy(c).unsqueeze(0))[0].numpy(),
+                                cs, ucs, ol)
+    check_pixels(out2, ref2, "tiled UNet cs 512, 700x560")
+
+
+def test_utnet_cs504_tiled_vs_oracle(utnet):
+    """The reference's own default tiling (cs 504 / ucs 480, denoise_image.py:41) on a two-by-two grid."""
+    sd = on.init_state_dict("UtNet", seed=0)
+    W, H, cs, ucs, ol = 900, 700, 504, 480, 6
+    img = np.random.default_rng(43).random((3, H, W), dtype=np.float32)
+    out = nb.denoise_tiled(torch.from_numpy(img).to(dev()), utnet, cs, ucs, ol).cpu().numpy()
+    with torch.no_grad():
+        ref = og.denoise_tiled(img, lambda c: on.utnet_forward(sd, torch.from_numpy(c).unsqueeze(0))[0].numpy(),
+                               cs, ucs, ol)
+    check_pixels(out, ref, "tiled UtNet cs 504, 900x700")
+
+
+def test_psnr_difference_against_a_clean_target(utnet):
+    """north_star: PSNR difference <= 0.05 dB versus the fp32 reference, measured against a CLEAN target: a smooth
+    synthetic image plus sigma = 0.05 Gaussian noise, clipped to 0..1.  The weights are the default init plus an
+    output-bias shift, so that the result lands in the image's range and PSNR-to-target is a meaningful number."""
+    sd = {k: v.clone() for k, v in on.init_state_dict("UtNet", seed=0).items()}
+    sd["tconvs4.4.bias"] = sd["tconvs4.4.bias"] + 0.6
+    m = nb.UtNet().to(dev()).eval()
+    m.load_state_dict(sd)
+    W, H, cs, ucs, ol = 520, 430, 248, 224, 6
+    yy, xx = np.meshgrid(np.linspace(0, 1, H), np.linspace(0, 1, W), indexing="ij")
+    clean = np.stack([0.5 + 0.35 * np.sin(6.0 * xx + 1.0) * np.cos(4.0 * yy),
+                      0.5 + 0.30 * np.sin(5.0 * yy + 0.5 * xx),
+                      0.45 + 0.25 * np.cos(7.0 * xx * yy)]).astype(np.float32)
+    noisy = np.clip(clean + np.random.default_rng(44).normal(0, 0.05, clean.shape), 0, 1).astype(np.float32)
+    out = nb.denoise_tiled(torch.from_numpy(noisy).to(dev()), m, cs, ucs, ol).cpu().numpy()
+    with torch.no_grad():
+        ref = og.denoise_tiled(noisy, lambda c: on.utnet_forward(sd, torch.from_numpy(c).unsqueeze(0))[0].numpy(),
+                               cs, ucs, ol)
+    check_pixels(out, ref, "tiled UtNet on a noisy smooth image")
+    d = abs(psnr(out, clean) - psnr(ref, clean))
+    print(f"PSNR vs clean target: b200 {psnr(out, clean):.3f} dB, fp32 oracle {psnr(ref, clean):.3f} dB, diff {d:.4f} dB")
+    assert d <= PSNR_DIFF
+
+
+# ------------------------------------------------------------------ round-2 entry points
+def test_denoise_batch_clamps_like_the_reference(utnet):
+    """Generator.denoise_batch = model(x).clip(0, 1) (nn_common.py:198-199); the clamp is fused into the head."""
+    sd = {k: v.clone() for k, v in on.init_state_dict("UtNet", seed=0).items()}
+    for k in sd:
+        if k.endswith(".weight") and sd[k].dim() == 4:
+            sd[k] = sd[k] * 1.35          # sigma_out ~ 0.2 around -0.1: values on both sides of 0
+    m = nb.UtNet().to(dev()).eval()
+    m.load_state_dict(sd)
+    torch.manual_seed(5)
+    x = torch.rand(2, 3, 120, 136)
+    with torch.no_grad():
+        ref = on.utnet_forward(sd, x)
+    y = m.denoise_batch(x.to(dev())).cpu()
+    assert float(y.min()) >= 0.0 and float(y.max()) <= 1.0
+    assert float((ref < 0).float().mean()) > 0.05 and float((ref > 0).float().mean()) > 0.05
+    err = float((y - ref.clip(0, 1)).abs().max())
+    assert err <= MAX_REL_SIGMA * float(ref.std())
+    assert torch.equal(y, m(x.to(dev())).cpu().clip(0, 1))   # identical arithmetic, clamp aside
+    # UNet: sigmoid output is inside (0, 1) already; the flag must be harmless
+    un = nb.UNet().to(dev()).eval()
+    un.load_state_dict(on.randomize_bn_(on.init_state_dict("UNet", seed=0), seed=7))
+    xu = torch.rand(1, 3, 64, 80, device=dev())
+    assert torch.equal(un.denoise_batch(xu), un(xu))
+
+
+def test_file_format_kernels_bit_exact():
+    """nind_image_to_chw_f32 / nind_chw_f32_to_image against the reference expressions
+    (np_imgops.py:19-28, pt_helpers.py:24-32)."""
+    from nind_denoise_b200 import cli
+    rng = np.random.default_rng(51)
+    h, w = 37, 53
+    for dtype, scale in ((np.uint8, 255), (np.uint16, 65535)):
+        bgr = rng.integers(0, scale + 1, (h, w, 3)).astype(dtype)
+        bgr[0, 0] = (0, scale, 1)
+        t = torch.from_numpy(bgr.view(np.int16) if dtype == np.uint16 else bgr).to(dev())
+        t = t.view(torch.uint16) if dtype == np.uint16 else t
+        got = cli.image_to_chw(t, bgr=True).cpu().numpy()
+        ref = bgr[:, :, ::-1].transpose(2, 0, 1).astype(np.single) / scale
+        assert np.array_equal(got, ref), dtype
+        got_rgb = cli.image_to_chw(t, bgr=False).cpu().numpy()
+        assert np.array_equal(got_rgb, bgr.transpose(2, 0, 1).astype(np.single) / scale)
+    f = rng.random((h, w, 3), dtype=np.float32) * 3 - 1     # stage-1 TIFFs keep highlights > 1 (denoise.py:417)
+    assert np.array_equal(cli.image_to_chw(torch.from_numpy(f).to(dev())).cpu().numpy(), f[:, :, ::-1].transpose(2, 0, 1))
+    x = torch.from_numpy((rng.random((3, h, w), dtype=np.float32) * 1.4 - 0.2))
+    x[0, 0, :4] = torch.tensor([0.5 / 65535, 1.5 / 65535, 2.5 / 65535, 1.0])     # round-half-even cases
+    q16 = cli.chw_to_image(x.to(dev()), torch.uint16).view(torch.int16).cpu().numpy().view(np.uint16)
+    ref16 = (x.clip(0, 1) * 65535).round().numpy().astype(np.uint16).transpose(1, 2, 0)[:, :, ::-1]
+    assert np.array_equal(q16, ref16)
+    q8 = cli.chw_to_image(x.to(dev()), torch.uint8).cpu().numpy()
+    ref8 = (x.clip(0, 1) * 255).add(0.5).clamp(0, 255).byte().numpy().transpose(1, 2, 0)[:, :, ::-1]
+    assert np.array_equal(q8, ref8)
+    qf = cli.chw_to_image(x.to(dev()), torch.float32).cpu().numpy()
+    assert np.array_equal(qf, x.numpy().transpose(1, 2, 0)[:, :, ::-1])
+
+
+def test_cli_model_directory_and_float_tiff(tmp_path, golden_networks):
+    """--model_path given as a directory (Model.complete_path, nn_common.py:75-114: best epoch from trainres.json)
+    and a float32 stage-1 TIFF in, float32 .tiff out (the production route of denoise.py:397-436)."""
+    import json
+
+    import cv2
+    from nind_denoise_b200 import cli
+
+    N = golden_networks
+    W, H, cs, ucs, ol = (int(v) for v in N["tiled_params"])
+    src = str(tmp_path / "in_s1.tif")
+    cv2.imwrite(src, cv2.cvtColor(N["tiled_img"].transpose(1, 2, 0), cv2.COLOR_RGB2BGR))      # 32-bit float TIFF
+    mdir = tmp_path / "models" / "run1"
+    mdir.mkdir(parents=True)
+    sd = on.init_state_dict("UtNet", seed=0)
+    torch.save(sd, str(mdir / "generator_12.pt"))
+    torch.save({k: v * 0 for k, v in sd.items()}, str(mdir / "generator_30.pt"))            # a worse, later epoch
+    json.dump({"best_epoch": {"validation_loss": 12}}, open(mdir / "trainres.json", "w"))
+    dst = str(tmp_path / "out.tiff")
+    rc = cli.main(["--network", "UtNet", "--model_path", "run1", "--models_dpath", str(tmp_path / "models"),
+                   "--input", src, "--output", dst, "--cs", str(cs), "--ucs", str(ucs), "--exif_method", "noexif"])
+    assert rc == 0
+    got = cv2.cvtColor(cv2.imread(dst, cv2.IMREAD_UNCHANGED), cv2.COLOR_BGR2RGB).transpose(2, 0, 1)
+    # models_dpath/name drops the keyword (nn_common.py:111): the highest-numbered file wins there ...
+    assert np.abs(got).max() <= 1e-6
+    # ... while the directory itself honours trainres.json's best epoch
+    rc = cli.main(["--network", "UtNet", "--model_path", str(mdir), "--input", src, "--output", dst, "--cs", str(cs),
+                   "--ucs", str(ucs), "--exif_method", "noexif"])
+    got = cv2.cvtColor(cv2.imread(dst, cv2.IMREAD_UNCHANGED), cv2.COLOR_BGR2RGB).transpose(2, 0, 1)
+    check_pixels(got, N["tiled_out"], "CLI, float TIFF in / out, model directory")
+
+
+def test_entry_points_on_different_streams_do_not_race(utnet):
+    """The entry points of one handle share scratch memory (plan arenas, crop outputs, origin table); calls
+    enqueued back to back on different streams — and on the library's own host-pipeline streams — are ordered by
+    the handle's last-use event."""
+    rng = np.random.default_rng(61)
+    cs, ucs, ol = 120, 96, 6
+    a = torch.from_numpy(rng.random((3, 500, 620), dtype=np.float32)).to(dev())
+    b = torch.from_numpy(rng.random((3, 500, 620), dtype=np.float32)).to(dev())
+    bh = b.cpu().pin_memory()
+    ref_a = nb.denoise_tiled(a, utnet, cs, ucs, ol, batch=20).clone()
+    ref_b = nb.denoise_tiled(b, utnet, cs, ucs, ol, batch=20).clone()
+    torch.cuda.synchronize()
+    s1, s2 = torch.cuda.Stream(), torch.cuda.Stream()
+    for _ in range(3):
+        with torch.cuda.stream(s1):
+            out_a = nb.denoise_tiled(a, utnet, cs, ucs, ol, batch=20)
+        with torch.cuda.stream(s2):
+            out_b = nb.denoise_tiled(b, utnet, cs, ucs, ol, batch=20)
+        out_bh = nb.denoise_tiled_host(bh, utnet, cs, ucs, ol, batch=20)      # library streams, synchronises itself
+        with torch.cuda.stream(s1):
+            out_a2 = nb.denoise_tiled(a, utnet, cs, ucs, ol, batch=20)
+        torch.cuda.synchronize()
+        assert torch.equal(out_a, ref_a) and torch.equal(out_b, ref_b) and torch.equal(out_a2, ref_a)
+        assert float((out_bh - ref_b.cpu()).abs().max()) <= 1e-6
+
+
+def test_module_moved_to_another_gpu():
+    """.to(another device) after the first forward: the native handle is rebuilt on the new device."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    sd = on.init_state_dict("UtNet", seed=0)
+    m = nb.UtNet().to("cuda:0").eval()
+    m.load_state_dict(sd)
+    x = torch.rand(1, 3, 120, 120)
+    y0 = m(x.to("cuda:0")).cpu()
+    m.to("cuda:1")
+    y1 = m(x.to("cuda:1")).cpu()
+    assert torch.equal(y0, y1)
+    m2 = nb.UtNet().to("cuda:0").eval()          # a second handle on another device of the same process
+    m2.load_state_dict(sd)
+    assert torch.equal(m2(x.to("cuda:0")).cpu(), y0) and torch.equal(m(x.to("cuda:1")).cpu(), y0)
+
+
+def _nccl_worker(rank, world, port, q):
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    d = torch.device("cuda", rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=d)
+    m = nb.UtNet().to(d).eval()
+    m.load_state_dict(on.init_state_dict("UtNet", seed=0))
+    W, H, cs, ucs, ol = 1210, 990, 120, 96, 6
+    img = torch.rand((3, H, W), generator=torch.Generator().manual_seed(3)).pin_memory()
+    out = nb.denoise_tiled_distributed(img.to(d), m, cs, ucs, ol)
+    sh = nb.SharedHostImage((3, H, W))
+    for _ in range(2):
+        out_h = nb.denoise_tiled_distributed_host(img, m, cs, ucs, ol, out=sh)
+    if rank == 0:
+        single = nb.denoise_tiled(img.to(d), m, cs, ucs, ol)
+        q.put((float((out - single).abs().max()), float((out_h - single.cpu()).abs().max())))
+    dist.barrier()
+    sh.close()
+    dist.destroy_process_group()
+
+
+def test_nccl_sharded_equals_single_gpu():
+    """BASELINE configs[2] under pytest: crops sharded over 2 NCCL ranks (device-resident gather to rank 0 and the
+    shared-host-image path) equal the single-GPU image.  Skipped on a one-GPU box (bench.py's `parity` block
+    makes the same comparison on every multi-GPU bench run)."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    import socket
+
+    import torch.multiprocessing as mp
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_nccl_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    d_dev, d_host = q.get(timeout=300)
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    assert d_dev <= 1e-6 and d_host <= 1e-6

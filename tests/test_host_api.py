@@ -155,3 +155,144 @@ def test_dir_cli_file_conventions(tmp_path):
     assert dir_cli.losses(a, a)["mse"] == 0.0
     l = dir_cli.losses(a, (a + 0.1))
     assert abs(l["psnr"] - (-10 * np.log10(l["mse"]))) < 1e-4
+
+
+# ------------------------------------------------------------------ round 2
+REF_SRC = "/root/reference/src/nind_denoise"
+
+
+def _import_reference_nn_common():
+    import sys
+    import types
+    if REF_SRC not in sys.path:
+        sys.path.insert(0, REF_SRC)
+    for missing in ("piqa",):
+        if missing not in sys.modules:
+            try:
+                __import__(missing)
+            except Exception:
+                sys.modules[missing] = types.ModuleType(missing)
+    if not hasattr(sys.modules["piqa"], "MS_SSIM"):
+        sys.modules["piqa"].MS_SSIM = type("MS_SSIM", (torch.nn.Module,), {})
+        sys.modules["piqa"].SSIM = type("SSIM", (torch.nn.Module,), {})
+    import nn_common
+    return nn_common
+
+
+@pytest.mark.skipif(not os.path.isdir(REF_SRC), reason="the reference tree is only present in the build container")
+def test_register_into_the_real_reference_factory(tmp_path):
+    """The drop-in claim, against the reference's own code: after register(), the unmodified
+    nn_common.Model.instantiate_model (nn_common.py:116-138) builds THESE classes — also 'UNet', which the fork's
+    factory cannot resolve on its own — and loads a state_dict checkpoint into them."""
+    nn_common = _import_reference_nn_common()
+    ref_utnet = nn_common.UtNet
+    try:
+        nb.register(nn_common)
+        m = nn_common.Model.instantiate_model(models_dpath=None, network="UtNet", device=None)
+        assert type(m) is nb.UtNet and len(m.state_dict()) == 64
+        m = nn_common.Model.instantiate_model(models_dpath=None, network="UNet", device=None)
+        assert type(m) is nb.UNet and len(m.state_dict()) == 136
+        # strparameters arrive as strings (nn_common.py:124)
+        m = nn_common.Model.instantiate_model(models_dpath=None, network="UtNet", device=None,
+                                              strparameters="funit=64,activation=Hardswish")
+        assert m._activation == "Hardswish" and len(m.state_dict()) == 46
+        # a .pt checkpoint written by the reference's own class loads strictly
+        torch.manual_seed(0)
+        ckpt = tmp_path / "generator_3.pt"
+        torch.save(ref_utnet().state_dict(), ckpt)
+        m = nn_common.Model.instantiate_model(models_dpath=None, model_path=str(ckpt), network="UtNet", device=None,
+                                              keyword="generator")
+        ref = on.init_state_dict("UtNet", seed=0)
+        assert type(m) is nb.UtNet and all(torch.equal(m.state_dict()[k], ref[k]) for k in ref)
+        with pytest.raises(RuntimeError, match="no CPU fallback"):   # built on the CPU it refuses to run
+            m(torch.rand(1, 3, 120, 120))
+    finally:
+        nn_common.UtNet = ref_utnet
+        if hasattr(nn_common, "UNet"):
+            del nn_common.UNet
+
+
+def test_complete_path_semantics(tmp_path):
+    """cli.complete_path == Model.complete_path (nn_common.py:75-114)."""
+    import json
+    from nind_denoise_b200 import cli
+    d = tmp_path / "models" / "runA"
+    d.mkdir(parents=True)
+    for n in ("generator_5.pt", "generator_40.pt", "discriminator_77.pt"):
+        (d / n).write_bytes(b"")
+    f = str(d / "generator_5.pt")
+    ref = _import_reference_nn_common().Model.complete_path if os.path.isdir(REF_SRC) else None
+    assert cli.complete_path(f, None, "generator") == f                                   # a file: as is
+    assert cli.complete_path(str(d), None, "generator") == str(d / "generator_40.pt")     # highest with the keyword
+    assert cli.complete_path(str(d), None, "discriminator") == str(d / "discriminator_77.pt")
+    # a name under models_dpath recurses WITHOUT the keyword (nn_common.py:111): highest file of any kind
+    assert cli.complete_path("runA", str(tmp_path / "models"), "generator") == str(d / "discriminator_77.pt")
+    if ref:   # same answers from the reference's own function
+        assert ref(f, None, "generator") == f
+        assert ref(str(d), None, "generator") == str(d / "generator_40.pt")
+        assert ref(str(d), None, "discriminator") == str(d / "discriminator_77.pt")
+        assert ref("runA", str(tmp_path / "models"), "generator") == str(d / "discriminator_77.pt")
+    json.dump({"best_epoch": {"validation_loss": 5}}, open(d / "trainres.json", "w"))
+    assert cli.complete_path(str(d), None, "generator") == str(d / "generator_5.pt")      # trainres.json wins
+    if ref:
+        assert ref(str(d), None, "generator") == str(d / "generator_5.pt")
+    # (with trainres.json present the reference's highest-number search raises on that file name; here files
+    # without a number are skipped)
+    assert cli.complete_path(str(d), None, "discriminator") == str(d / "discriminator_77.pt")
+    with pytest.raises(SystemExit):
+        cli.complete_path("nope", str(tmp_path / "models"), "generator")
+
+
+def test_scoring_matches_definitions():
+    """scoring.ssim / ms_ssim (piqa 1.3 defaults) against a direct, un-separated restatement of the formulas, and
+    the testres.json bookkeeping (json_saver.py)."""
+    import json
+    import tempfile
+    from scipy.signal import convolve2d
+    from nind_denoise_b200 import scoring
+    rng = np.random.default_rng(5)
+    a = rng.random((3, 40, 52)).astype(np.float32)
+    b = np.clip(a + rng.normal(0, 0.1, a.shape), 0, 1).astype(np.float32)
+    g = np.exp(-((np.arange(11) - 5.0) ** 2) / (2 * 1.5 ** 2))
+    g2 = np.outer(g / g.sum(), g / g.sum())
+    vals = []
+    for c in range(3):
+        f = lambda z: convolve2d(z.astype(np.float64), g2, mode="valid")
+        mx, my = f(a[c]), f(b[c])
+        sxx, syy, sxy = f(a[c] * a[c]) - mx * mx, f(b[c] * b[c]) - my * my, f(a[c] * b[c]) - mx * my
+        cs = (2 * sxy + 0.03 ** 2) / (sxx + syy + 0.03 ** 2)
+        vals.append(((2 * mx * my + 0.01 ** 2) / (mx * mx + my * my + 0.01 ** 2) * cs).mean())
+    got = float(scoring.ssim(torch.from_numpy(a)[None], torch.from_numpy(b)[None])[0])
+    assert abs(got - float(np.mean(vals))) < 1e-5
+    x = torch.rand(1, 3, 170, 180)
+    assert abs(float(scoring.ssim(x, x)[0]) - 1) < 1e-6 and abs(float(scoring.ms_ssim(x, x)[0]) - 1) < 1e-5
+    y = (x + 0.1 * torch.randn_like(x)).clip(0, 1)
+    m1, m2 = float(scoring.ms_ssim(x, y)[0]), float(scoring.ms_ssim(x, (x + 0.3 * torch.randn_like(x)).clip(0, 1))[0])
+    assert 0 < m2 < m1 < 1
+    with pytest.raises(RuntimeError):
+        scoring.ms_ssim(x[..., :100, :100], y[..., :100, :100])       # needs >= 162 px (pt_losses.py:20-29)
+    l = scoring.get_losses(x[0], y[0])
+    assert set(l) == {"mse", "ssim", "msssim"} and abs(l["msssim"] - (1 - m1)) < 1e-6
+    assert scoring.avg_listofdicts([{"mse": 1.0, "ssim": 0.5}, {"mse": 3.0, "ssim": 0.25}]) == {"mse": 2.0, "ssim": 0.375}
+    with tempfile.TemporaryDirectory() as td:
+        p = os.path.join(td, "testres.json")
+        scoring.add_test_results(p, 340, {"mse": 5.6e-4, "ssim": 0.1168, "msssim": 0.0397})
+        scoring.add_test_results(p, 141, {"mse": 5.5e-4, "ssim": 0.1146, "msssim": 0.0392})
+        scoring.add_test_results(p, 200, {"mse": 9.9e-4, "ssim": 0.2, "msssim": 0.1})
+        d = json.load(open(p))
+        assert d["best_epoch"] == {"test_mse": 141, "test_ssim": 141, "test_msssim": 141}
+        assert d["best_val"]["test_mse"] == 5.5e-4 and set(d) == {"best_val", "best_epoch", "340", "141", "200"}
+
+
+def test_baseline_file_selection():
+    """dir_cli.sort_isos / get_baseline_fpath == dataset_torch_3.sortISOs / get_baseline_fpath (:37-96)."""
+    import tempfile
+    from nind_denoise_b200 import dir_cli
+    assert dir_cli.sort_isos(["ISO6400", "ISO200", "ISOH1", "ISO800"]) == (["ISO200"], ["ISO800", "ISO6400", "ISOH1"])
+    assert dir_cli.sort_isos(["ISO200-2", "ISO200", "ISO3200"])[0] == ["ISO200", "ISO200-2"]
+    assert dir_cli.sort_isos(["GT1", "a", "b"]) == (["GT1"], ["a", "b"])
+    assert dir_cli.sort_isos(["b", "a", "c"]) == (["a"], ["b", "c"])
+    with tempfile.TemporaryDirectory() as td:
+        for n in ("NIND_x_ISO800.png", "NIND_x_ISO200.png", "NIND_x_ISOH2.png", "notes.txt"):
+            open(os.path.join(td, n), "w").close()
+        assert dir_cli.get_baseline_fpath(td) == os.path.join(td, "NIND_x_ISO200.png")

@@ -294,6 +294,7 @@ static int run_conv(int argc, char** argv) {
   const int flat = argc > 15 ? atoi(argv[15]) : -1;
   const int pair = argc > 16 ? atoi(argv[16]) : 0;   // pixel-pair mode (C_out = 64 layers)
   const int pool = argc > 17 ? atoi(argv[17]) : 0;   // fused 2x2 max-pool into a second buffer (EPI_STORE, even sizes)
+  const int dual = argc > 18 ? atoi(argv[18]) : -1;  // two MMA issuer warps (-1 default = on)
   const int tw = taps == 9 ? 3 : 1;
   const int Hv = Hs - (tw - 1), Wv = Ws - (tw - 1);
   const bool c8 = cin == 8;              // first-layer mode: 8-channel input, no-swizzle descriptors
@@ -354,7 +355,7 @@ static int run_conv(int argc, char** argv) {
   }
   s.in_coff = coff; s.cin = cin; s.taps = taps; s.w = c8 ? dw8 : (pair ? dwp : dw); s.n_total = n_total; s.bias = dbias;
   s.act = act; s.slope = slope; s.epi_mode = epi; (void)a_mode; (void)bo_mode;
-  s.n_tile = n_tile; s.force_ws = ws; s.max_ctas = ctas; s.cg = cg; s.flat = flat;
+  s.n_tile = n_tile; s.force_ws = ws; s.max_ctas = ctas; s.cg = cg; s.flat = flat; s.dual = dual;
   const int halo = 2, ocoff = 32;
   int Ho = 0, Wo = 0, Co = 0;
   const int unpad = 1;
