@@ -305,8 +305,9 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-parity", action="store_true", help="skip the oracle / distributed parity block")
     ap.add_argument("--parity-crops", type=int, default=0, help="crops checked against the oracle (0 = auto)")
-    ap.add_argument("--gather", default="rows", choices=["rows", "bands"],
-                    help="N>1: seam exchange + owned-row gather (default) or whole-band gather summed on rank 0")
+    ap.add_argument("--gather", default="peer", choices=["peer", "rows", "bands"],
+                    help="N>1: peer-memory DMA gather overlapped with compute (default), NCCL seam exchange + "
+                         "owned-row send/recv, or whole-band gather summed on rank 0")
     ap.add_argument("--images", type=int, default=6, help="throughput mode: images streamed per GPU")
     ap.add_argument("--sweep", action="store_true",
                     help="BASELINE configs[4]: throughput mode over cs {120,248,504,1016} x overlap {0,6,16,32}")
@@ -473,7 +474,7 @@ def main():
         if world > 1 and rank == 0:
             # sharded == single GPU: rank 0 runs the whole image alone and compares both sharded results with it
             single = nb.denoise_tiled(img, model, cs, ucs, ol, batch=default_batch(n, cs, nx))
-            dvs = {"device_path_max_abs": float((out - single).abs().max()),
+            dvs = {"device_path": args.gather, "device_path_max_abs": float((out - single).abs().max()),
                    "shared_host_path_max_abs": float((out_shared.tensor - single.cpu()).abs().max()),
                    "tolerance": 1e-6,
                    "note": "4-way seam corners may associate (a+b)+(c+d) instead of ((a+b)+c)+d across rank boundaries"}
@@ -570,7 +571,9 @@ def main():
             "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
             "config": {"workload": f"{NETWORK}(funit 64, random init) {W_IMG}x{H_IMG} synthetic image, cs {cs} ucs {ucs} overlap {ol} "
                                    f"-> {n} crops, batch {batch} crops/forward; crops sharded over {world} GPU(s)"
-                                   + (f", NCCL seam exchange between neighbours + send/recv gather of owned rows to rank 0 ({args.gather})"
+                                   + ((", owned rows copied to rank 0 by peer DMA over NVLink as they become final, NCCL for the "
+                                       "closing synchronisation (peer)" if args.gather == "peer" else
+                                       f", NCCL seam exchange between neighbours + send/recv gather of owned rows to rank 0 ({args.gather})")
                                       if world > 1 else ""),
                        "l2": "inputs larger than L2 (288 MB image, >1 GB activation arena per batch)",
                        "algorithmic_tflop_per_step": flops_image / 1e12},

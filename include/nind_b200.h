@@ -102,6 +102,35 @@ int nind_tiled_denoise(nind_net* net, const float* img_chw, float* out_band, int
 int nind_band_rows(int width, int height, int cs, int ucs, int ol, int crop_begin, int crop_end,
                    int* band_y0, int* band_y1);
 
+/* Step-wise form of nind_tiled_denoise for callers that overlap communication with compute (the multi-GPU gather
+ * of the stitched output): crops [step_begin, step_end) of the range [crop_begin, crop_end) go through one
+ * forward, and the band rows that become final with them, [*rows_begin, *rows_end), are stitched into out_img
+ * — a device image of FULL [3,height,width] layout.  Steps must be issued in raster order and cover the range
+ * (nind_plan_steps gives the boundaries the host pipeline uses: bounds[0..n_steps]). */
+int nind_tiled_denoise_step(nind_net* net, const float* img_chw, float* out_img, int height, int width, int cs,
+                            int ucs, int ol, int crop_begin, int crop_end, int step_begin, int step_end,
+                            int* rows_begin, int* rows_end, void* stream);
+int nind_plan_steps(nind_net* net, int width, int height, int cs, int ucs, int ol, int crop_begin, int crop_end,
+                    int batch, int* bounds, int max_bounds, int* n_steps);
+/* dst[p*dst_plane + i] = src[p*src_plane + i] for p < planes, i < count: asynchronous device-to-device copies on
+ * `stream` (copy engines, no SM).  dst may be peer memory opened with nind_peer_open: the bytes then go straight
+ * over NVLink. */
+int nind_copy_planes(float* dst, long long dst_plane, const float* src, long long src_plane, int planes,
+                     long long count, void* stream);
+/* Peer memory for the multi-GPU gather of the stitched output: nind_peer_alloc allocates device memory on the
+ * current device and returns its 64-byte CUDA IPC handle; another process of the node maps it on ITS current
+ * device with nind_peer_open (lazy peer access), after which copies and stores from that device reach it over
+ * NVLink.  The reference has no counterpart (single device). */
+int nind_peer_alloc(size_t bytes, void** ptr, unsigned char* handle64);
+int nind_peer_open(const unsigned char* handle64, void** ptr);
+int nind_peer_close(void* ptr);
+int nind_peer_free(void* ptr);
+/* dst[p*dst_plane + i] += src[p*src_plane + i] for p < planes, i < count (fp32 device pointers; vectorised when
+ * count, the plane strides and the pointers are multiples of 4 floats): the partial sums another rank computed
+ * for image rows are added to the rows' owner's, in rank = raster order. */
+int nind_add_rows(float* dst, long long dst_plane, const float* src, long long src_plane, int planes, long long count,
+                  void* stream);
+
 /* The two geometry halves of the loop as stand-alone ops (bit-exact copies / fp32 adds):
  *   nind_gather_crops  = OneImageDS.__getitem__ for crops [crop_begin, crop_end)
  *                        (denoise_image.py:129-174) -> crops_out [n,3,cs,cs] fp32 device;

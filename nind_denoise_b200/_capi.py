@@ -45,6 +45,16 @@ SIGNATURES = {
     "nind_crop_table": (C.c_int, [C.c_int] * 5 + [C.POINTER(NindCrop), C.POINTER(C.c_int)]),
     "nind_tiled_denoise": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p] + [C.c_int] * 8 +
                            [C.POINTER(C.c_int), C.POINTER(C.c_int), C.c_void_p]),
+    "nind_tiled_denoise_step": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p] + [C.c_int] * 9 +
+                                [C.POINTER(C.c_int), C.POINTER(C.c_int), C.c_void_p]),
+    "nind_plan_steps": (C.c_int, [C.c_void_p] + [C.c_int] * 8 + [C.POINTER(C.c_int), C.c_int, C.POINTER(C.c_int)]),
+    "nind_copy_planes": (C.c_int, [C.c_void_p, C.c_longlong, C.c_void_p, C.c_longlong, C.c_int, C.c_longlong,
+                                   C.c_void_p]),
+    "nind_peer_alloc": (C.c_int, [C.c_size_t, C.POINTER(C.c_void_p), C.c_char_p]),
+    "nind_peer_open": (C.c_int, [C.c_char_p, C.POINTER(C.c_void_p)]),
+    "nind_peer_close": (C.c_int, [C.c_void_p]),
+    "nind_peer_free": (C.c_int, [C.c_void_p]),
+    "nind_add_rows": (C.c_int, [C.c_void_p, C.c_longlong, C.c_void_p, C.c_longlong, C.c_int, C.c_longlong, C.c_void_p]),
     "nind_gather_crops": (C.c_int, [C.c_void_p, C.c_void_p] + [C.c_int] * 7 + [C.c_void_p, C.c_void_p]),
     "nind_stitch_crops": (C.c_int, [C.c_void_p] + [C.c_int] * 7 + [C.c_void_p, C.POINTER(C.c_int),
                                                                     C.POINTER(C.c_int), C.c_void_p]),

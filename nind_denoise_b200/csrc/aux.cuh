@@ -189,6 +189,32 @@ __global__ void __launch_bounds__(256) gather_crops_kernel(const CropGatherParam
   }
 }
 
+// ------------------------------------------------------------------ seam accumulation (multi-GPU)
+// dst[i] += src[i]: a rank adds the partial sums another rank computed for image rows it owns (the grid row two
+// crop ranges share, or the `ol` seam rows), in rank = raster order.
+template <bool VEC>
+__global__ void __launch_bounds__(256) add_rows_kernel(float* __restrict__ dst, long long dst_plane,
+                                                       const float* __restrict__ src, long long src_plane, int planes,
+                                                       long long count) {
+  if (VEC) {  // count, the plane strides (in floats) and both pointers are multiples of 4 floats
+    const long long n4 = count >> 2, total = n4 * planes;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+      const long long pl = i / n4, k = i - pl * n4;
+      float4* d = reinterpret_cast<float4*>(dst + pl * dst_plane) + k;
+      const float4 b = __ldg(reinterpret_cast<const float4*>(src + pl * src_plane) + k);
+      float4 a = *d;
+      a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
+      *d = a;
+    }
+  } else {
+    const long long total = count * planes;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+      const long long pl = i / count, k = i - pl * count;
+      dst[pl * dst_plane + k] += __ldg(src + pl * src_plane + k);
+    }
+  }
+}
+
 // ------------------------------------------------------------------ file formats either side of the path
 // image_to_chw_kernel = img_path_to_np_flt after the decode (common/libs/np_imgops.py:19-28): interleaved HWC
 // pixels as cv2 returns them (BGR when bgr = 1) of type u8 / u16 / f32 -> planar RGB fp32, x/255, x/65535 or

@@ -49,13 +49,15 @@ constexpr int IG_MAX_SETS = 4;         // epilogue warp sets (= TMEM accumulator
 constexpr int IG_EPI_BYTES = IG_MAX_SETS * 3072;  // per set: staged bias [2][256] fp32 (+ spare)
 // Store staging: NBUF buffers of 32 rows x 64 B per epilogue warp, used round-robin by the warp's TMA stores
 // (bulk groups retire in order, so "all but the newest NBUF-1 groups have read their source" frees the next
-// buffer).  One buffer made every 32-channel half wait ~1500 clk for the previous half's store — the TMA unit
-// also serves the activation loads — (profiles/r02_pipeline_trace_tma_store.log).
+// buffer).  Measured on B200 (profiles/r02_dual_issuer_staging_ab.log): 2 / 4 buffers do not shorten the
+// epilogue of a tile, and the 32 - 48 KB they take from the activation ring cost more (128->128 -5 %, 64->128
+// loses its resident weights) than they could give, so one buffer it is.
 #ifndef NIND_STG_BUFS
-#define NIND_STG_BUFS 0
+#define NIND_STG_BUFS 1
 #endif
 __host__ __device__ constexpr int ig_stg_bufs(int n_tile, bool pm = false) {
-  return NIND_STG_BUFS ? NIND_STG_BUFS : ((pm || n_tile == 64) ? 2 : 4);
+  (void)n_tile; (void)pm;
+  return NIND_STG_BUFS;
 }
 __host__ __device__ constexpr int ig_set_stage_bytes(int n_tile, bool pm = false) {
   return 4 * ig_stg_bufs(n_tile, pm) * 2048;  // per set: 4 warps x NBUF x 2 KB
@@ -223,6 +225,10 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
   tc_fence_after();
   uint32_t tmem_base;
   asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+  // Programmatic dependent launch: the next kernel of the stream may be scheduled from now on — its CTAs start on
+  // an SM as soon as this kernel's CTA there has exited, and run their prologue (and load their resident weights)
+  // while other SMs still finish this layer.
+  pdl_launch_dependents();
 
   // p.tiles_x / p.tiles_y / p.total_tiles count (super-)tiles: CG adjacent 16x8 pixel tiles each
   const int tiles_xy = p.tiles_x * p.tiles_y;
@@ -234,6 +240,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     if (lane == 0) {
       uint32_t s = 0, ph = 0;
       int tl = 0;
+      pdl_wait();  // the activations this layer reads are the previous kernel's output
       for (int tile = tile0; tile < p.total_tiles; tile += tstep, ++tl) {
         const int r = tile % tiles_xy;
         int yt = r / p.tiles_x, xt = r - yt * p.tiles_x;
@@ -371,6 +378,8 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
           umma_commit(a_empty + 8 * sa_i);
           umma_commit(t_full + 8 * acc);
         }
+        __syncwarp();  // the other lanes must not run ahead into the next tile's polling loops: they would take
+                       // issue slots from the lane that feeds the tensor pipe
       }
       if (PM) {
         constexpr uint32_t IDESC64 = umma_idesc_bf16(256, 64);
@@ -403,6 +412,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
             umma_commit_cg2(a_empty + 8 * sa_i);
             if (last) umma_commit_cg2(t_full + 8 * acc);
           }
+          __syncwarp();
           accum = 1;
           if (++sa_i == (uint32_t)p.sa) { sa_i = 0; pha ^= 1; }
         }
@@ -446,6 +456,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
               else umma_commit(t_full + 8 * acc);
             }
           }
+          __syncwarp();
           accum = 1;
           if (++sb_i == (uint32_t)p.sb) { sb_i = 0; phb ^= 1; }
           if (TPS == 3) {

@@ -55,6 +55,7 @@ struct IgemmLaunch {
   IgemmParams p;
   int n_tile = 0, tps = 1, cg = 1;
   bool c8 = false;  // first layer: 3x3 conv over an 8-channel (16 B/pixel) tensor, no-swizzle descriptors
+  bool pdl = true;  // programmatic dependent launch: overlap this kernel's prologue with its predecessor's tail
   bool pm = false;  // pixel-pair mode
   size_t smem = 0;
   int grid = 0;
@@ -423,13 +424,15 @@ inline cudaError_t igemm_launch_t(const IgemmLaunch& L, const IgemmParams& p, cu
   cfg.blockDim = dim3(ig_threads(N, PM));
   cfg.dynamicSmemBytes = L.smem;
   cfg.stream = st;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = CG;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;  // see pdl_wait() in the kernel
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = 1;
+  cfg.numAttrs = L.pdl ? 2 : 1;
   return cudaLaunchKernelEx(&cfg, igemm_kernel<N, T, CG, G, PM>, L.tmA, L.tmB, L.tmC4, L.tmC1, p);
 }
 

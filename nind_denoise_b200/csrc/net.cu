@@ -137,6 +137,9 @@ struct nind_net {
   int host_first = -1, host_last = -1;  // crops in the first / last pipeline step (-1: one grid row)
   // options
   int n_tile_deep = 256, max_ctas = 0, cg = 0, fuse_pool = 1, dual = -1;
+  // Programmatic dependent launch of the conv kernels: measured on B200 (profiles/r02_pdl_ab.log) +0.2 % at the
+  // default batch and -6 % with 28-crop forwards, so it is off; "pdl" = 1 switches it on.
+  int pdl = 0;
   // timing
   int timing = 0;
   std::vector<std::string> t_names;
@@ -708,6 +711,7 @@ int run_plan(nind_net* net, Plan* plan, const GatherParams& gsrc, float* head_ou
     } else {
       IgemmLaunch L = s.ig;
       if ((int)i == plan->head_step) { L.p.head_out = head_out; L.p.head_clamp = head_clamp; }
+      L.pdl = net->pdl && !net->timing;  // per-layer timing wants the launches serialised
 
       cudaError_t e = launch_igemm(L, net->err_flag, st);
       if (e != cudaSuccess) return fail(NIND_E_CUDA, s.name + ": " + cudaGetErrorString(e));
@@ -896,6 +900,9 @@ int nind_set_option(nind_net* net, const char* key, int value) {
     net->fuse_pool = value ? 1 : 0;
   } else if (k == "pair64") {  // pixel-pair mode for the C_out = 64 3x3 layers (0 | 1)
     net->pair64 = value ? 1 : 0;
+  } else if (k == "pdl") {  // programmatic dependent launch of the conv kernels (0 | 1)
+    net->pdl = value ? 1 : 0;
+    return 0;
   } else if (k == "dual_issuer") {  // two MMA issuer warps on alternate tiles (0 | 1)
     net->dual = value ? 1 : 0;
   } else if (k == "flat") {  // flat (1-D) tiles on narrow maps: -1 auto, 0 off, 1 wherever legal
@@ -1075,6 +1082,110 @@ int nind_tiled_denoise(nind_net* net, const float* img_chw, float* out_band, int
   return scratch_release(net, st);
 }
 
+// Band rows that are final once every crop with index < `upto` of the range [cb, ce) has been forwarded.
+static int rows_final(const GridGeom& g, int cb, int ce, int upto) {
+  int y0, y1;
+  band_of(g, cb, ce, &y0, &y1);
+  if (upto >= ce) return y1;
+  if (upto <= cb) return y0;
+  return std::min(y1, std::max(y0, g.stride * (upto / g.nx)));
+}
+
+int nind_tiled_denoise_step(nind_net* net, const float* img_chw, float* out_img, int height, int width, int cs,
+                            int ucs, int ol, int crop_begin, int crop_end, int step_begin, int step_end,
+                            int* rows_begin, int* rows_end, void* stream) {
+  if (!net || !img_chw || !out_img) return fail(NIND_E_INVALID, "null argument");
+  ENTER(net);
+  GridGeom g;
+  int rc;
+  if ((rc = check_range(width, height, cs, ucs, ol, crop_begin, crop_end, &g))) return rc;
+  if (step_begin < crop_begin || step_end > crop_end || step_begin >= step_end)
+    return fail(NIND_E_INVALID, "illegal step range");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int n = crop_end - crop_begin;
+  Plan* plan = nullptr;
+  if ((rc = get_plan(net, step_end - step_begin, cs, cs, &plan))) return rc;
+  if ((rc = scratch_acquire(net, st))) return rc;
+  if ((rc = ensure(reinterpret_cast<void**>(&net->crops_buf), &net->crops_cap, (size_t)n * 3 * cs * cs * sizeof(float))))
+    return rc;
+  if ((rc = upload_origins(net, g, crop_begin, n, st))) return rc;
+  GatherParams gp;
+  memset(&gp, 0, sizeof gp);
+  gp.src = img_chw; gp.src_img = 0; gp.src_plane = (long long)height * width; gp.src_w = width; gp.src_h = height;
+  gp.origin = net->origin_buf + (step_begin - crop_begin);
+  if ((rc = run_plan(net, plan, gp, net->crops_buf + (size_t)(step_begin - crop_begin) * 3 * cs * cs, st))) return rc;
+  const int r0 = rows_final(g, crop_begin, crop_end, step_begin), r1 = rows_final(g, crop_begin, crop_end, step_end);
+  if (rows_begin) *rows_begin = r0;
+  if (rows_end) *rows_end = r1;
+  if (r1 > r0 && (rc = launch_stitch(g, net->crops_buf, crop_begin, crop_end, out_img, r0, r1, true, st))) return rc;
+  return scratch_release(net, st);
+}
+
+int nind_copy_planes(float* dst, long long dst_plane, const float* src, long long src_plane, int planes,
+                     long long count, void* stream) {
+  if (!dst || !src || count < 0 || planes < 0) return fail(NIND_E_INVALID, "illegal argument");
+  if (count == 0 || planes == 0) return 0;
+  for (int p = 0; p < planes; ++p)
+    CUDA_TRY(cudaMemcpyAsync(dst + (size_t)p * dst_plane, src + (size_t)p * src_plane, (size_t)count * sizeof(float),
+                             cudaMemcpyDeviceToDevice, static_cast<cudaStream_t>(stream)));
+  return 0;
+}
+
+// Peer memory: a buffer of one process (rank) mapped into the others of the node through CUDA IPC.  The opener
+// maps it on ITS current device with lazy peer access, so plain device-to-device copies and kernel stores from
+// that device go straight over NVLink.
+int nind_peer_alloc(size_t bytes, void** ptr, unsigned char* handle64) {
+  if (!ptr || !handle64 || !bytes) return fail(NIND_E_INVALID, "illegal argument");
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+  CUDA_TRY(cudaMalloc(ptr, bytes));
+  cudaIpcMemHandle_t h;
+  cudaError_t e = cudaIpcGetMemHandle(&h, *ptr);
+  if (e != cudaSuccess) {
+    cudaFree(*ptr);
+    *ptr = nullptr;
+    return fail(NIND_E_CUDA, std::string("cudaIpcGetMemHandle: ") + cudaGetErrorString(e));
+  }
+  memcpy(handle64, &h, 64);
+  return 0;
+}
+
+int nind_peer_open(const unsigned char* handle64, void** ptr) {
+  if (!ptr || !handle64) return fail(NIND_E_INVALID, "null argument");
+  cudaIpcMemHandle_t h;
+  memcpy(&h, handle64, 64);
+  CUDA_TRY(cudaIpcOpenMemHandle(ptr, h, cudaIpcMemLazyEnablePeerAccess));
+  return 0;
+}
+
+int nind_peer_close(void* ptr) {
+  if (!ptr) return 0;
+  CUDA_TRY(cudaIpcCloseMemHandle(ptr));
+  return 0;
+}
+
+int nind_peer_free(void* ptr) {
+  if (!ptr) return 0;
+  CUDA_TRY(cudaFree(ptr));
+  return 0;
+}
+
+int nind_add_rows(float* dst, long long dst_plane, const float* src, long long src_plane, int planes, long long count,
+                  void* stream) {
+  if (!dst || !src || count < 0 || planes < 0) return fail(NIND_E_INVALID, "illegal argument");
+  if (count == 0 || planes == 0) return 0;
+  const bool vec = !((count | dst_plane | src_plane) & 3) &&
+                   !((reinterpret_cast<uintptr_t>(dst) | reinterpret_cast<uintptr_t>(src)) & 15);
+  if (vec)
+    add_rows_kernel<true><<<grid_for(planes * (count / 4)), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        dst, dst_plane, src, src_plane, planes, count);
+  else
+    add_rows_kernel<false><<<grid_for(planes * count), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        dst, dst_plane, src, src_plane, planes, count);
+  ++g_launches;
+  CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+
 // Pipeline steps of the host entry for crops [cb, ce): the first and the last step end / start at a grid-row
 // boundary (so that compute starts after one grid row of the image has been uploaded and only one grid row of
 // output is downloaded after the last forward), unless that would make them shorter than half a grid row — a
@@ -1103,6 +1214,24 @@ static void host_steps(const nind_net* net, const GridGeom& g, int cb, int ce, i
   if (first) steps->push_back({cb, cb + first});
   balanced_steps(cb + first, ce - last, batch, steps);
   if (last) steps->push_back({ce - last, ce});
+}
+
+int nind_plan_steps(nind_net* net, int width, int height, int cs, int ucs, int ol, int crop_begin, int crop_end,
+                    int batch, int* bounds, int max_bounds, int* n_steps) {
+  if (!net || !n_steps) return fail(NIND_E_INVALID, "null argument");
+  GridGeom g;
+  int rc;
+  if ((rc = check_range(width, height, cs, ucs, ol, crop_begin, crop_end, &g))) return rc;
+  if (batch <= 0) return fail(NIND_E_INVALID, "batch must be positive");
+  std::vector<std::pair<int, int>> steps;
+  host_steps(net, g, crop_begin, crop_end, batch, &steps);
+  *n_steps = (int)steps.size();
+  if (bounds) {
+    if (max_bounds < (int)steps.size() + 1) return fail(NIND_E_INVALID, "bounds array too small");
+    for (size_t i = 0; i < steps.size(); ++i) bounds[i] = steps[i].first;
+    bounds[steps.size()] = steps.back().second;
+  }
+  return 0;
 }
 
 // Enqueue crops [cb, ce) of one image on the three-stream host pipeline (no synchronisation).  Rows

@@ -53,7 +53,10 @@ class _NativeNet(nn.Module):
         self._packed_key = None
 
     def __del__(self):
-        self._drop_handle()
+        try:
+            self._drop_handle()
+        except Exception:  # interpreter shutdown: torch's module machinery may already be gone
+            pass
 
     def _state_key(self):
         # storage identity + in-place version counter of every parameter and buffer: changes on

@@ -73,6 +73,58 @@ def _band(model, img: torch.Tensor, cs, ucs, ol, crop_begin, crop_end, batch) ->
     return out, y0, y1
 
 
+def plan_steps(model, width: int, height: int, cs: int, ucs: int, ol: int, crop_begin: int, crop_end: int,
+               batch: int) -> List[Tuple[int, int]]:
+    """The forwards a crop range is split into when copies / communication overlap the compute (``nind_plan_steps``:
+    the first and last step end / start at a grid-row boundary, the rest are balanced forwards of <= batch crops)."""
+    n = C.c_int()
+    bounds = (C.c_int * 1026)()
+    _capi.check(_capi.lib().nind_plan_steps(model.native_handle(), width, height, cs, ucs, ol, crop_begin, crop_end, batch,
+                                            bounds, 1026, C.byref(n)))
+    return [(bounds[i], bounds[i + 1]) for i in range(n.value)]
+
+
+def tiled_step(model, img: torch.Tensor, out_img: torch.Tensor, cs: int, ucs: int, ol: int, crop_begin: int,
+               crop_end: int, step_begin: int, step_end: int) -> Tuple[int, int]:
+    """``nind_tiled_denoise_step``: one forward over crops [step_begin, step_end) of the range; the band rows that
+    become final, [r0, r1), are stitched into ``out_img`` (full [3,H,W] layout, same device).  Returns (r0, r1)."""
+    _, H, W = img.shape
+    r0, r1 = C.c_int(), C.c_int()
+    with torch.cuda.device(img.device):
+        stream = torch.cuda.current_stream().cuda_stream
+        _capi.check(_capi.lib().nind_tiled_denoise_step(model.native_handle(), img.data_ptr(), out_img.data_ptr(), H, W, cs,
+                                                        ucs, ol, crop_begin, crop_end, step_begin, step_end, C.byref(r0),
+                                                        C.byref(r1), C.c_void_p(stream)))
+    return r0.value, r1.value
+
+
+def add_rows(dst: torch.Tensor, src: torch.Tensor) -> None:
+    """dst += src for two [3, rows, W] fp32 CUDA views whose planes are contiguous (``nind_add_rows``)."""
+    assert dst.shape == src.shape and dst.dim() == 3 and dst.is_cuda and src.is_cuda
+    if dst.numel() == 0:
+        return
+    assert dst[0].is_contiguous() and src[0].is_contiguous()
+    count = dst.shape[1] * dst.shape[2]
+    with torch.cuda.device(dst.device):
+        _capi.check(_capi.lib().nind_add_rows(dst.data_ptr(), dst.stride(0), src.data_ptr(), src.stride(0), dst.shape[0], count,
+                                              C.c_void_p(torch.cuda.current_stream().cuda_stream)))
+
+
+def copy_planes(dst: torch.Tensor, src: torch.Tensor, stream=None) -> None:
+    """dst[...] = src[...] for two [3, rows, W] fp32 CUDA views with contiguous planes: ONE asynchronous 2-D copy on
+    the source device's current stream (``nind_copy_planes``).  ``dst`` may be peer memory — rank 0's output image
+    opened with ``nind_peer_open`` —: the copy is then a peer-to-peer DMA over NVLink."""
+    assert dst.shape == src.shape and dst.dim() == 3 and dst.is_cuda and src.is_cuda
+    if dst.numel() == 0:
+        return
+    assert dst[0].is_contiguous() and src[0].is_contiguous()
+    count = dst.shape[1] * dst.shape[2]
+    with torch.cuda.device(src.device):
+        st = (stream or torch.cuda.current_stream()).cuda_stream
+        _capi.check(_capi.lib().nind_copy_planes(dst.data_ptr(), dst.stride(0), src.data_ptr(), src.stride(0), dst.shape[0],
+                                                 count, C.c_void_p(st)))
+
+
 def denoise_tiled(img: torch.Tensor, model, cs: Optional[int] = None, ucs: Optional[int] = None,
                   ol: int = DEFAULT_OVERLAP, batch: Optional[int] = None) -> torch.Tensor:
     """[3,H,W] fp32 CUDA image -> [3,H,W] fp32 denoised image on the same device (no clamp, as the
@@ -174,21 +226,161 @@ def assemble_bands(bands: Sequence[Tuple[Optional[torch.Tensor], int, int]], hei
     return out
 
 
+class _DevicePtr:
+    """Zero-copy torch view of library-owned device memory (``__cuda_array_interface__``)."""
+
+    def __init__(self, ptr: int, shape):
+        self.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": "<f4", "data": (int(ptr), False),
+                                         "version": 2, "strides": None}
+
+
+class PeerGather:
+    """Rank ``dst``'s output image(s) and seam scratch, mapped into every rank of the node through CUDA IPC, so that
+    the gather of the stitched output is a set of peer-to-peer DMA copies over NVLink that each rank issues as
+    soon as rows are final — on its copy engines, overlapped with the forwards still running, no SM taken from
+    the persistent conv kernels (an NCCL send/recv kernel that waits for its peer would hold SMs the statically
+    scheduled conv CTAs need).  NCCL is only used for the closing synchronisation.
+
+    Two output images alternate between calls (a rank may start writing image k+1 while ``dst`` still finishes
+    image k).  ``seam[r]`` receives rank r's partial sums for rows later ranks own (the grid row two crop ranges
+    share, or the ``ol`` seam rows); ``dst`` adds them in rank = raster order.  Collective constructor."""
+
+    def __init__(self, height: int, width: int, max_seam_rows: int, device, group=None, dst: int = 0):
+        import torch.distributed as dist
+
+        self.group, self.dst = group, dst
+        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        self.shape = (3, height, width)
+        self.max_seam_rows = max(1, max_seam_rows)
+        n_out = 2 * 3 * height * width
+        n_seam = self.world * 3 * self.max_seam_rows * width
+        lib = _capi.lib()
+        ptr = C.c_void_p()
+        payload = [None]
+        self._owner = self.rank == dst
+        with torch.cuda.device(device):
+            if self._owner:
+                handle = C.create_string_buffer(64)
+                _capi.check(lib.nind_peer_alloc((n_out + n_seam) * 4, C.byref(ptr), handle))
+                payload[0] = handle.raw
+            src = dist.get_global_rank(group, dst) if group is not None else dst
+            dist.broadcast_object_list(payload, src=src, group=group)
+            if not self._owner:  # map rank dst's buffer on THIS rank's device (lazy peer access over NVLink)
+                _capi.check(lib.nind_peer_open(payload[0], C.byref(ptr)))
+        self._ptr = ptr.value
+        base = torch.as_tensor(_DevicePtr(self._ptr, (n_out + n_seam,)), device=device)
+        self.outs = base[:n_out].view(2, 3, height, width)
+        self.seam = base[n_out:].view(self.world, 3, self.max_seam_rows, width)
+        self.calls = 0
+        dist.barrier(group)
+
+    def close(self):
+        if getattr(self, "_ptr", None):
+            lib = _capi.lib()
+            (lib.nind_peer_free if self._owner else lib.nind_peer_close)(C.c_void_p(self._ptr))
+            self._ptr = None
+
+    def out(self) -> torch.Tensor:
+        return self.outs[self.calls & 1]
+
+
+_peer_cache = {}
+
+
+def _peer_gather(height, width, max_seam_rows, device, group, dst) -> PeerGather:
+    key = (height, width, str(device), id(group), dst)
+    pg = _peer_cache.get(key)
+    if pg is None or pg.max_seam_rows < max_seam_rows:
+        pg = PeerGather(height, width, max_seam_rows, device, group, dst)
+        _peer_cache[key] = pg
+    return pg
+
+
+def _denoise_tiled_distributed_peer(img, model, cs, ucs, ol, batch, group, dst):
+    """mode="peer" of ``denoise_tiled_distributed`` (see there)."""
+    import torch.distributed as dist
+
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    _, H, W = img.shape
+    n = n_crops(W, H, cs, ucs, ol)
+    ranges = shard_ranges(n, world)
+    cb, ce = ranges[rank]
+    extents = band_extents(W, H, cs, ucs, ol, ranges)
+    own = owned_rows(extents, H)
+    max_seam = max([max(0, e[1] - o[1]) for e, o in zip(extents, own)] + [1])
+    pg = _peer_gather(H, W, max_seam, img.device, group, dst)
+    out = pg.out()
+    dev = img.device
+    key = ("full", H, W, str(dev))
+    full = _peer_cache.get(key)
+    if full is None:
+        full = _peer_cache[key] = torch.empty((3, H, W), dtype=torch.float32, device=dev)
+    if ("side", str(dev)) not in _peer_cache:
+        _peer_cache[("side", str(dev))] = torch.cuda.Stream(device=dev)
+        _peer_cache[("token", str(dev))] = torch.zeros(1, device=dev)
+    side = _peer_cache[("side", str(dev))]
+    main = torch.cuda.current_stream(dev)
+    if ce > cb:
+        if batch is None:
+            batch = default_batch(ce - cb, cs, _nx(W, ucs, ol))
+        y0, y1 = extents[rank]
+        o0, o1 = own[rank]
+        # at least two balanced forwards, so that half of the copies overlap compute; small forwards are
+        # inefficient (per-launch prologues, wave quantisation), so no finer than the batch asks for
+        ncr = ce - cb
+        k = max(2 if ncr >= 32 else 1, -(-ncr // batch))
+        for i in range(k):
+            a, b = cb + ncr * i // k, cb + ncr * (i + 1) // k
+            r0, r1 = tiled_step(model, img, full, cs, ucs, ol, cb, ce, a, b)
+            if r1 <= r0:
+                continue
+            ev = torch.cuda.Event()
+            ev.record(main)
+            side.wait_event(ev)
+            a0, a1 = max(r0, o0), min(r1, o1)          # rows this rank owns: straight into the output image
+            if a1 > a0:
+                copy_planes(out[:, a0:a1], full[:, a0:a1], side)
+            s0, s1 = max(r0, o1), min(r1, y1)          # rows later ranks own: partial sums -> seam scratch
+            if s1 > s0:
+                copy_planes(pg.seam[rank, :, s0 - o1:s1 - o1], full[:, s0:s1], side)
+        main.wait_stream(side)
+    # closing synchronisation: every rank's copies are ordered before its contribution to this all-reduce
+    token = _peer_cache[("token", str(dev))]
+    dist.all_reduce(token, group=group)
+    pg.calls += 1
+    if rank != dst:
+        return None
+    for r in range(world):          # partial sums for rows later ranks own, in rank (= raster) order
+        rows = extents[r][1] - own[r][1]
+        if extents[r][1] > extents[r][0] and rows > 0:
+            add_rows(out[:, own[r][1]:extents[r][1]], pg.seam[r, :, :rows])
+    return out
+
+
 def denoise_tiled_distributed(img: torch.Tensor, model, cs: int, ucs: int, ol: int = DEFAULT_OVERLAP,
                               batch: Optional[int] = None, group=None, dst: int = 0,
                               band_fn: Optional[Callable] = None, mode: str = "rows") -> Optional[torch.Tensor]:
     """Every rank holds the same ``img`` (read-only) and a replica of ``model``; rank ``dst`` returns the
     stitched image, the others return None.
 
+    ``mode="peer"``: every rank copies the rows it owns straight into ``dst``'s output image, which is mapped
+    into every rank through CUDA IPC (``PeerGather``), step by step as they become final — peer DMA over NVLink
+    overlapped with the remaining forwards; partial sums for rows later ranks own go to a scratch area that
+    ``dst`` adds at the end; the only collective is the closing synchronisation.  The returned image is one of two
+    buffers that alternate between calls.
     ``mode="rows"`` (default): neighbours first exchange the seam rows they share (``exchange_seams``),
     then every rank sends only the rows it owns and ``dst`` receives them straight into the output image —
-    each output byte crosses NVLink once and nothing is summed on ``dst``.
+    each output byte crosses NVLink once and nothing is summed on ``dst`` (NCCL send / recv).
     ``mode="bands"``: whole overlapping bands are gathered and summed on ``dst`` (kept for comparison).
 
     ``band_fn(img, crop_begin, crop_end) -> (band, y0, y1)`` replaces the GPU band computation in CPU
     (gloo) tests of the sharding/gather logic."""
     import torch.distributed as dist
 
+    if mode == "peer":
+        if band_fn is not None:
+            raise ValueError("mode='peer' runs on GPUs only (CUDA IPC)")
+        return _denoise_tiled_distributed_peer(img, model, cs, ucs, ol, batch, group, dst)
     world = dist.get_world_size(group)
     rank = dist.get_rank(group)
     _, H, W = img.shape
@@ -318,14 +510,6 @@ def exchange_seams(band: Optional[torch.Tensor], extents, own, rank: int, group=
         band[:, a - y0:b - y0, :] += buf
 
 
-class _DevicePtr:
-    """Zero-copy torch view of library-owned device memory (``__cuda_array_interface__``)."""
-
-    def __init__(self, ptr: int, shape):
-        self.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": "<f4", "data": (int(ptr), False),
-                                         "version": 2, "strides": None}
-
-
 def host_range(model, img_host: torch.Tensor, out_host: torch.Tensor, cs: int, ucs: int, ol: int, batch: int,
                crop_begin: int, crop_end: int, d2h_y0: int, d2h_y1: int) -> torch.Tensor:
     """``nind_tiled_denoise_host_range`` + ``nind_host_join``: enqueue one rank's crops on the library's
@@ -348,7 +532,13 @@ class SharedHostImage:
     """A [3,H,W] fp32 host image in ONE shared-memory segment mapped by every rank of ``group`` (ranks of a
     node), page-locked on each rank: the multi-GPU host entry lets every GPU copy the rows it owns straight
     into it over its own PCIe link instead of funnelling the whole image through rank ``src``'s.
-    Collective constructor.  ``tensor`` is the CPU view (all ranks see the same bytes)."""
+    Collective constructor.  ``tensor`` is the CPU view (all ranks see the same bytes).
+
+    The segment also carries one 64-bit arrival counter per rank (``arrive`` / ``wait_all``): the closing
+    synchronisation of an image — "every rank's rows have landed" — is a store by each rank and a spin over
+    ``world`` cache lines by the reader, instead of an NCCL barrier (a kernel launch and a stream sync per rank)."""
+
+    _FLAG_STRIDE = 16  # int64s per rank: one 128-byte line each, no false sharing
 
     def __init__(self, shape, group=None, src: int = 0, pin: bool = True):
         import os
@@ -358,16 +548,26 @@ class SharedHostImage:
         self.shape = tuple(int(v) for v in shape)
         numel = math.prod(self.shape)
         self._fd = None
+        self._group = group
         rank = dist.get_rank(group)
+        self._rank, self._world = rank, dist.get_world_size(group)
+        flag_bytes = self._world * self._FLAG_STRIDE * 8
+        data_bytes = (numel * 4 + 4095) // 4096 * 4096
         path = [None]
         if rank == src:
             # anonymous memory file, reachable by the other ranks through /proc (no /dev/shm size limit)
             self._fd = os.memfd_create("nind_b200_out")
-            os.ftruncate(self._fd, numel * 4)
+            os.ftruncate(self._fd, data_bytes + flag_bytes)
             path[0] = f"/proc/{os.getpid()}/fd/{self._fd}"
         dist.broadcast_object_list(path, src=dist.get_global_rank(group, src) if group is not None else src,
                                    group=group)
-        self.tensor = torch.from_file(path[0], shared=True, size=numel, dtype=torch.float32).view(self.shape)
+        whole = torch.from_file(path[0], shared=True, size=data_bytes + flag_bytes, dtype=torch.uint8)
+        self._whole = whole
+        self.tensor = whole[:numel * 4].view(torch.float32).view(self.shape)
+        self._flags = whole[data_bytes:].view(torch.int64)
+        if rank == src:
+            self._flags.zero_()
+        self._seq = 0
         self.pinned = False
         if pin and torch.cuda.is_available():
             _capi.check(_capi.lib().nind_host_register(self.tensor.data_ptr(), numel * 4))
@@ -376,6 +576,22 @@ class SharedHostImage:
         if self._fd is not None:
             os.close(self._fd)
             self._fd = None
+
+    def arrive(self) -> int:
+        """This rank's rows of the current image are in the segment (call after the copies were synchronised)."""
+        self._seq += 1
+        self._flags[self._rank * self._FLAG_STRIDE] = self._seq
+        return self._seq
+
+    def wait_all(self, timeout: float = 60.0) -> None:
+        """Spin until every rank has arrived at this rank's current sequence number."""
+        import time
+
+        view = self._flags[::self._FLAG_STRIDE][:self._world]
+        t0 = time.perf_counter()
+        while int(view.min()) < self._seq:
+            if time.perf_counter() - t0 > timeout:
+                raise RuntimeError("SharedHostImage.wait_all: a rank did not arrive within the time-out")
 
     def close(self):
         if self.pinned:
@@ -438,7 +654,11 @@ def denoise_tiled_distributed_host(img_host: torch.Tensor, model, cs: int, ucs: 
         if band_fn is None and ce > cb:
             _capi.check(_capi.lib().nind_host_sync(model.native_handle()))
             torch.cuda.current_stream(model._device).synchronize()
-        dist.barrier(group)  # every rank's rows have landed in the shared image
+        # every rank's rows have landed in the shared image: arrival counters in the segment itself (no NCCL
+        # barrier); only the rank that returns the image waits
+        out.arrive()
+        if rank == dst:
+            out.wait_all()
         return out.tensor if rank == dst else None
     if band_fn is None:
         dev = model._device if getattr(model, "_handle", None) else next(model.parameters()).device

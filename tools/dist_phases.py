@@ -55,11 +55,30 @@ def band_exchange():
     nb.exchange_seams(band, ext, own, rank)
 
 
+def steps_only():
+    from nind_denoise_b200.tiler import _peer_cache
+    full = _peer_cache.setdefault(("dbg_full",), torch.empty((3, H, W), device=dev))
+    for (a, b) in nb.plan_steps(model, W, H, cs, ucs, ol, cb, ce, batch):
+        nb.tiled_step(model, img, full, cs, ucs, ol, cb, ce, a, b)
+
+
+def peer_copy_only():
+    from nind_denoise_b200.tiler import _peer_cache, _peer_gather, copy_planes
+    pg = _peer_gather(H, W, 512, dev, None, 0)
+    full = _peer_cache.setdefault(("dbg_full",), torch.empty((3, H, W), device=dev))
+    o0, o1 = own[rank]
+    copy_planes(pg.out()[:, o0:o1], full[:, o0:o1])
+
+
 if rank == 0:
-    print(f"world {world} cs {cs}: {n} crops, {ce - cb} per rank, batch {batch}", flush=True)
+    print(f"world {world} cs {cs}: {n} crops, {ce - cb} per rank, batch {batch}; steps "
+          f"{nb.plan_steps(model, W, H, cs, ucs, ol, cb, ce, batch)}", flush=True)
 timed("band only (no communication)", band_only)
+timed("steps only (forward + stitch per step)", steps_only)
+timed("peer copy of the owned rows only", peer_copy_only)
+timed("device path, peer mode", lambda: nb.denoise_tiled_distributed(img, model, cs, ucs, ol, batch=batch, mode="peer"))
 timed("band + seam exchange", band_exchange)
-timed("device path, rows mode", lambda: nb.denoise_tiled_distributed(img, model, cs, ucs, ol, batch=batch))
+timed("device path, rows mode", lambda: nb.denoise_tiled_distributed(img, model, cs, ucs, ol, batch=batch, mode="rows"))
 timed("device path, bands mode", lambda: nb.denoise_tiled_distributed(img, model, cs, ucs, ol, batch=batch, mode="bands"))
 timed("host path, shared host image (pipelined)", lambda: nb.denoise_tiled_distributed_host(img_host, model, cs, ucs, ol, batch=batch, out=shared))
 timed("host path, gather to rank 0 + one D2H", lambda: nb.denoise_tiled_distributed_host(img_host, model, cs, ucs, ol, batch=batch, out=plain))

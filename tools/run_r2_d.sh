@@ -28,6 +28,8 @@ run conv 1 1024 2048 2 28 28 0 0 1 0 -1 0 0 0
 run conv 9 8 64 2 40 40 0 0 0
 run conv 9 8 64 3 41 37 0 0 0
 run conv 9 64 64 1 24 24 0 0 0
+run conv 9 64 128 1 60 60 0 0 0
+run conv 9 64 128 2 62 62 0 0 0 0 -1 0 1 1
 run conv 9 8 64 1 20 20 0 0 0
 echo "=== timing (B = 32): dual issuer off / on"
 for d in 0 1; do
@@ -58,3 +60,5 @@ echo "=== bench (default / dual off / pair off)"
 python bench.py --steps 5 --no-cpu-baseline --layers 2> gpurun_out/r2d_layers.txt | cut -c1-260
 python bench.py --steps 5 --no-cpu-baseline --layers --opt dual_issuer=0 2> gpurun_out/r2d_layers_dual0.txt | cut -c1-260
 python bench.py --steps 5 --no-cpu-baseline --layers --opt pair64=0 2> gpurun_out/r2d_layers_pair0.txt | cut -c1-260
+python bench.py --steps 5 --no-cpu-baseline --cs 504 --no-parity | cut -c1-260
+python bench.py --steps 3 --no-cpu-baseline --network UNet --no-parity | cut -c1-260
