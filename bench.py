@@ -430,11 +430,13 @@ def main():
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     sync_all()
     t_start = time.time()
+    torch.cuda.profiler.start()  # no-op unless run under `ncu --profile-from-start off` (tools/run_ncu_r2.sh)
     e0.record()
     for _ in range(args.steps):
         out = step()
     e1.record()
     sync_all()
+    torch.cuda.profiler.stop()
     t_end = time.time()
     ms = max_over_ranks(e0.elapsed_time(e1))
     launches = lib.nind_kernel_launches() - l0

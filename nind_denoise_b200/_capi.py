@@ -82,7 +82,10 @@ def lib() -> C.CDLL:
     global _lib
     if _lib is None:
         path = _build.LIB_PATH
-        if _build.is_stale():
+        alt = os.environ.get("NIND_LIB")  # development A/B runs: another build of the same ABI (tools/build_base.sh)
+        if alt:
+            path = alt
+        elif _build.is_stale():
             try:
                 _build.build()
             except Exception as e:  # no nvcc on this machine: use the prebuilt library if there is one

@@ -59,8 +59,9 @@ __host__ __device__ constexpr int ig_stg_bufs(int n_tile, bool pm = false) {
   (void)n_tile; (void)pm;
   return NIND_STG_BUFS;
 }
-__host__ __device__ constexpr int ig_set_stage_bytes(int n_tile, bool pm = false) {
-  return 4 * ig_stg_bufs(n_tile, pm) * 2048;  // per set: 4 warps x NBUF x 2 KB
+// wide: 128-byte staging rows (all 64 channels of a pixel per TMA store) instead of two 64-byte halves: 4 KB per warp
+__host__ __device__ constexpr int ig_set_stage_bytes(int n_tile, bool pm = false, bool wide = false) {
+  return 4 * ig_stg_bufs(n_tile, pm) * (wide ? 4096 : 2048);  // per set: 4 warps x NBUF x 2 (4) KB
 }
 // Epilogue sets per kernel: N_TILE = 64 layers are epilogue-bound with two sets (their MMA phase per tile
 // is short), and their accumulators are small, so they get four (B200 A/B, same box: 64->64 572 / 651 / 680 TFLOP/s with 2 / 3 / 4 sets).
@@ -99,6 +100,8 @@ struct IgemmParams {
   long long o_img, o_row;  // element strides
   int o_pix;
   int d2s_cout;            // EPI_D2S: channels per sub-pixel
+  int wide;                // TMA-store modes: 128-byte staging rows, one store per 64 channels (see the epilogue)
+  int d2s_hs2;             // EPI_D2S: stored destination rows per image / 2 (image stride of tmC4's folded row dimension)
   // Flat mode (narrow maps): tiles are 128 consecutive pixels of the row-major (b, y, x) index space of the
   // INPUT buffer (pitch = its width), the A box is a 2-D slab of 128 + 2*pitch + 2 pixel rows, and tap
   // (ky, kx) starts (ky*pitch + kx) rows into it.  No 8-pixel column quantisation; the only waste is the
@@ -125,17 +128,26 @@ struct IgemmParams {
 
 // pipeline trace events (CTA 0 only, first 64 tiles): see tools/probe.cu "trace"
 enum { TR_A_ISSUE = 0, TR_MMA_TEMPTY = 1, TR_MMA_AFULL = 2, TR_MMA_DONE = 3, TR_EPI_TFULL = 4, TR_EPI_TMEM = 5,
-       TR_EPI_DONE = 6 };
+       TR_EPI_DONE = 6,
+       // fine-grained epilogue stamps of the tile's first 32-channel half (-DNIND_TRACE_FINE=1 builds only)
+       TR_F_LD0 = 7, TR_F_STAGED = 8, TR_F_FENCED = 9, TR_F_STORED = 10, TR_F_BUF1 = 11, TR_F_LD1 = 12 };
+#ifndef NIND_TRACE_FINE
+#define NIND_TRACE_FINE 0
+#endif
 #define NIND_TRACE(tl, ev)                                                                  \
   do {                                                                                      \
-    if (p.trace && blockIdx.x == 0 && (tl) < 64 && lane == 0) p.trace[(tl) * 8 + (ev)] = clock64(); \
+    if (p.trace && blockIdx.x == 0 && (tl) < 64 && lane == 0) p.trace[(tl) * 16 + (ev)] = clock64(); \
+  } while (0)
+#define NIND_TRACE_F(cond, tl, ev)                                   \
+  do {                                                               \
+    if (NIND_TRACE_FINE && quarter == 0 && (cond)) NIND_TRACE(tl, ev); \
   } while (0)
 #define NIND_MBW(bar, parity, code) mbar_wait((bar), (parity), p.err, (code), p.wait_cycles)
 
 __host__ __device__ inline size_t igemm_smem_bytes(int n_tile, int tps, int cg, int sa, uint32_t a_stage_bytes,
-                                                   int sb, bool pm = false) {
+                                                   int sb, bool pm = false, bool wide = false) {
   return 1024 + (size_t)sa * a_stage_bytes + (size_t)sb * tps * (n_tile / cg) * 128 + IG_BAR_BYTES +
-         IG_EPI_BYTES + (size_t)ig_sets(n_tile, pm) * ig_set_stage_bytes(n_tile, pm);
+         IG_EPI_BYTES + (size_t)ig_sets(n_tile, pm) * ig_set_stage_bytes(n_tile, pm, wide);
 }
 
 // N_TILE: GEMM N per tile (64/128/256).  TPS: taps per weight pipeline stage (1 or 3).
@@ -177,7 +189,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
   const uint32_t b_base = a_base + (uint32_t)p.sa * p.a_stage_bytes;
   const uint32_t stg_base = b_base + (uint32_t)p.sb * B_BYTES;  // 1024-aligned
   constexpr int NBUF = ig_stg_bufs(N_TILE, PM);
-  const uint32_t bar_base = stg_base + ES * ig_set_stage_bytes(N_TILE, PM);
+  const uint32_t bar_base = stg_base + ES * ig_set_stage_bytes(N_TILE, PM, p.wide != 0);
   const uint32_t a_full = bar_base;
   const uint32_t a_empty = bar_base + 8 * IG_MAX_STAGES;
   const uint32_t b_full = bar_base + 16 * IG_MAX_STAGES;
@@ -188,7 +200,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
   const uint32_t go_bar = t_full + 80;  // two "go" batons of the dual MMA issuers
   const uint32_t epi_base = bar_base + IG_BAR_BYTES;
 
-  const int warp = threadIdx.x >> 5;
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);  // warp-uniform for the compiler: role / tile geometry in uniform registers
   const int lane = threadIdx.x & 31;
 
   if (warp == 0 && lane == 0) {
@@ -479,7 +491,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     const int etid = threadIdx.x - 128 - eset * 128;  // 0..127 inside the set
     uint8_t* smem_gen = smem_raw + (sbase - smem_u32(smem_raw));
     float* bias_s = reinterpret_cast<float*>(smem_gen + (epi_base - sbase) + eset * 3072);  // [2][256] per set
-    const uint32_t stg_off = (stg_base - sbase) + (eset * 4 + quarter) * (NBUF * 2048);
+    const uint32_t stg_off = (stg_base - sbase) + (eset * 4 + quarter) * (NBUF * (p.wide ? 4096 : 2048));
     uint8_t* const stg0 = smem_gen + stg_off;  // this warp's NBUF staging buffers: 32 rows x 64 B, rows = (tile row, pixel)
     const uint32_t stg_s0 = sbase + stg_off;   // same, shared-space address (TMA source)
     uint32_t bufi = 0;                         // staging buffer of the next 32-channel half
@@ -504,10 +516,18 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     // MODE 0 store, 1 store + fused max-pool, 2 depth-to-space (all three: TMA stores), 3 fused 1x1 head,
     //      4 flat-tile store, 5 flat-tile depth-to-space (per-pixel 16-byte stores);
     // ACT 0 none, 1 PReLU/ReLU with 0 <= slope <= 1 (max(x, a*x)), 2 anything else.
+    // MODE 6 / 7 = MODE 0 / 2 with WIDE staging: rows of 128 B (the tile's 64-channel group per pixel, 128B-swizzled)
+    // and ONE TMA store per group instead of one per 32-channel half.  The TMA unit works per box row, and the
+    // store-bound kernels (first layer, 2x2/s2 up-convs: ~1000 clk of MMA per 16 - 64 KB of output) ran at one
+    // 64-byte row per ~4 clk and SM — 3.2 TB/s of writes whatever the store mechanism (profiles/r02_pipeline_trace_fine.log).
     auto run = [&](auto mode_c, auto act_c) {
-      constexpr int MODE = decltype(mode_c)::value;
+      constexpr int MODE_ = decltype(mode_c)::value;
+      constexpr bool WIDE = MODE_ >= 6;
+      constexpr int MODE = MODE_ == 6 ? 0 : (MODE_ == 7 ? 2 : MODE_);
       constexpr int ACT = decltype(act_c)::value;
       constexpr bool HEAD = MODE == 3, TMA = MODE < 3, D2S = MODE == 2 || MODE == 5, POOL = MODE == 1;
+      constexpr uint32_t STG_BYTES = WIDE ? 4096 : 2048;
+      const uint32_t off_ww = lane * 128;  // WIDE: this thread's staging row
       int prev_nt = -1, bsel = 1;
       uint32_t aph = 0;
       int tl = eset;
@@ -555,7 +575,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         } else if (TMA) {
           tb = yf0 / p.hs_in;
           ty = yf0 - tb * p.hs_in;
-          one_box = !D2S && (ty + 3 < p.hs_in);
+          one_box = D2S ? (p.d2s_hs2 > 0 && ty + 3 < p.h_valid) : (ty + 3 < p.hs_in);
           if (POOL) {
             // pooled pixel of this lane: tile origins and map sizes are even, so the validity of the top-left
             // source pixel covers all four
@@ -622,11 +642,11 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
           }
 #pragma unroll
           for (int half = 0; half < 2; ++half) {
-            uint8_t* const stg = stg0 + bufi * 2048;  // staging buffer of this half
-            uint8_t* const stg_w = stg + off_w;
+            uint8_t* const stg = stg0 + bufi * STG_BYTES;  // staging buffer of this half (WIDE: of both halves)
+            uint8_t* const stg_w = stg + (WIDE ? off_ww : off_w);
             const uint8_t* const stg_r = stg + off_r;
             const uint8_t* const stg_p = stg + off_p;
-            const uint32_t stg_s = stg_s0 + bufi * 2048;
+            const uint32_t stg_s = stg_s0 + bufi * STG_BYTES;
             // CW accumulator columns at a time (16 for the 640-thread kernels, whose 96-register
             // budget a 32-wide chunk overflows)
 #pragma unroll
@@ -634,6 +654,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
               uint32_t v[CW];
               tmem_ld_32x32(taddr + c64 * 64 + half * 32 + q * CW, v);
               tmem_wait_ld();
+              NIND_TRACE_F(c64 == 0 && q == 0, tl, half == 0 ? TR_F_LD0 : TR_F_LD1);
               if (half == 1 && q == 32 / CW - 1 && c64 == live - 1) {  // accumulator fully read: back to the MMA warp
                 tc_fence_before();
                 __syncwarp();
@@ -688,9 +709,10 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
                   h2 = fmaf(f[j], p.head_c[128 + half * 32 + q * CW + j], h2);
                 }
               } else {
-                if (TMA && q == 0) {  // the TMA store that last used this staging buffer has finished reading it
+                if (TMA && q == 0 && (!WIDE || half == 0)) {  // the TMA store that last used this staging buffer has finished reading it
                   if (lane == 0) bulk_wait_group_read<NBUF - 1>();
                   __syncwarp();
+                  NIND_TRACE_F(c64 == 0 && half == 1, tl, TR_F_BUF1);
                 }
                 // this thread's channels -> staging row (64 B per half), 16-byte chunks XOR-swizzled
 #pragma unroll
@@ -700,13 +722,18 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
                   o.y = pack_bf16x2(f[8 * j + 2], f[8 * j + 3]);
                   o.z = pack_bf16x2(f[8 * j + 4], f[8 * j + 5]);
                   o.w = pack_bf16x2(f[8 * j + 6], f[8 * j + 7]);
-                  *reinterpret_cast<uint4*>(stg_w + (((q * (CW / 8) + j) ^ sw_w) << 4)) = o;
+                  if (WIDE)  // 128B swizzle: 16-byte chunk index XOR (row & 7)
+                    *reinterpret_cast<uint4*>(stg_w + (((half * 4 + q * (CW / 8) + j) ^ (lane & 7)) << 4)) = o;
+                  else
+                    *reinterpret_cast<uint4*>(stg_w + (((q * (CW / 8) + j) ^ sw_w) << 4)) = o;
                 }
               }
             }
-            if (TMA) {
+            if (TMA && (!WIDE || half == 1)) {
+              NIND_TRACE_F(c64 == 0 && half == 0, tl, TR_F_STAGED);
               fence_proxy_async_smem();
               __syncwarp();
+              NIND_TRACE_F(c64 == 0 && half == 0, tl, TR_F_FENCED);
               if (POOL && PM) {
                 // fused 2x2 max-pool across the two column groups (= the two pixels of a pair): rows (0,1) and
                 // (2,3) of this lane's pair column reduce in registers; group 0 is kept until group 1 arrives
@@ -743,18 +770,20 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
                 if (pvmask) *reinterpret_cast<uint4*>(p.pool_out + (pdst + n + half * 32)) = m;
               }
               if (lane == 0) {
-                const int cc = c_chan + half * 32, x0 = xt * IG_TILE_W;
+                const int cc = WIDE ? c_chan : c_chan + half * 32, x0 = xt * IG_TILE_W;
                 if (one_box) {
-                  tma_store_5d(&tmC4, stg_s, cc, c_sx, x0, ty, tb);
+                  if (D2S) tma_store_5d(&tmC4, stg_s, cc, c_sx, x0, c_dy, tb * p.d2s_hs2 + ty);
+                  else tma_store_5d(&tmC4, stg_s, cc, c_sx, x0, ty, tb);
                 } else {
                   int b = tb, y = ty;
 #pragma unroll
                   for (int it = 0; it < 4; ++it) {
-                    tma_store_5d(&tmC1, stg_s + it * 512, cc, c_sx, x0, D2S ? 2 * y + c_dy : y, b);
+                    tma_store_5d(&tmC1, stg_s + it * (STG_BYTES / 4), cc, c_sx, x0, D2S ? 2 * y + c_dy : y, b);
                     if (++y == p.hs_in) { y = 0; ++b; }
                   }
                 }
                 bulk_commit_group();
+                NIND_TRACE_F(c64 == 0 && half == 0, tl, TR_F_STORED);
               }
               bufi = bufi + 1 == NBUF ? 0 : bufi + 1;
             } else if (!HEAD) {
@@ -833,10 +862,26 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         default: run(I3{}, I2{}); break;
       }
     } else if (C8) {  // first layer: plain store
-      switch (actk) {
+      using I6 = std::integral_constant<int, 6>;
+      switch (actk + (p.wide ? 3 : 0)) {
         case 0: run(I0{}, I0{}); break;
         case 1: run(I0{}, I1{}); break;
-        default: run(I0{}, I2{}); break;
+        case 2: run(I0{}, I2{}); break;
+        case 3: run(I6{}, I0{}); break;
+        case 4: run(I6{}, I1{}); break;
+        default: run(I6{}, I2{}); break;
+      }
+    } else if (p.wide) {  // plain store / depth-to-space with 128-byte staging rows
+      using I6 = std::integral_constant<int, 6>;
+      using I7 = std::integral_constant<int, 7>;
+      if (mode == 2) {
+        if (actk == 0) run(I7{}, I0{}); else run(I7{}, I2{});
+      } else {
+        switch (actk) {
+          case 0: run(I6{}, I0{}); break;
+          case 1: run(I6{}, I1{}); break;
+          default: run(I6{}, I2{}); break;
+        }
       }
     } else {
       switch (mode * 3 + actk) {

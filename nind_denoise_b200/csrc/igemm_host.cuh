@@ -46,6 +46,7 @@ struct ConvSpec {
   bool c8 = false;    // first layer over the 8-channel padded-crop tensor (C_in = 3 as hi/lo bf16)
   int force_ws = -1;  // -1 = auto
   int dual = -1;      // two MMA issuer warps: -1 auto (on), 0 off, 1 on
+  int wide = -1;      // 128-byte staging rows / one TMA store per 64 channels: -1 auto, 0 off, 1 on (where legal)
   int max_ctas = 0;   // 0 = number of SMs
 };
 
@@ -258,17 +259,23 @@ inline bool build_igemm(const ConvSpec& s, IgemmLaunch* L, std::string* why) {
 
   if (!flat) p.tap_pitch16 = p.a_sbo >> 4;
 
+  // Store-bound layers (first layer, 2x2/s2 up-convs) hand the TMA unit 128-byte rows; the MMA-bound ones keep
+  // the 64-byte halves, whose staging is half the size (the activation ring needs the shared memory more).
+  const bool wide_ok = !flat && !s.pair && s.epi_mode != EPI_HEAD && !s.pool.ptr;
+  const bool wide = wide_ok && (s.wide == 1 || (s.wide == -1 && (s.taps == 1 || s.c8)));
+  p.wide = wide ? 1 : 0;
+
   // pipeline depth / weights-stationary decision
   const int tps = (s.c8 || s.pair) ? 1 : ((s.taps == 9 && n_tile <= 128) ? 3 : 1);  // taps per weight stage
   L->tps = tps;
   const int kt = s.c8 ? 2 : p.kchunks * (p.taps / tps);  // c8: 10 KB of weights in two 8 KB "stages"
   bool ws = false;
   if (s.force_ws != 0 && p.tiles_n == 1 && kt <= IG_MAX_STAGES &&
-      igemm_smem_bytes(n_tile, tps, cg, 2, p.a_stage_bytes, kt, s.pair) <= IG_SMEM_LIMIT)
+      igemm_smem_bytes(n_tile, tps, cg, 2, p.a_stage_bytes, kt, s.pair, wide) <= IG_SMEM_LIMIT)
     ws = true;
   if (s.force_ws == 1 && !ws) return fail("weights do not fit in shared memory");
   auto fits = [&](int sa, int sb) {
-    return igemm_smem_bytes(n_tile, tps, cg, sa, p.a_stage_bytes, sb, s.pair) <= IG_SMEM_LIMIT;
+    return igemm_smem_bytes(n_tile, tps, cg, sa, p.a_stage_bytes, sb, s.pair, wide) <= IG_SMEM_LIMIT;
   };
   if (s.pair) {  // resident weights: 36 KB per (e, 64-channel block) per CTA, counted in 8 KB "stages"
     ws = true;
@@ -279,7 +286,12 @@ inline bool build_igemm(const ConvSpec& s, IgemmLaunch* L, std::string* why) {
   } else if (ws) {
     p.sb = kt;
     p.sa = 2;
-    while (p.sa < 6 && fits(p.sa + 1, p.sb)) ++p.sa;
+    // The first layer's patches are 3 KB and its MMA phase per tile is ~200 clk, so the ring must cover the LOAD
+    // LATENCY, not the consumption rate: with the HBM interface busy writing the 8x larger output, a patch arrives
+    // ~5700 clk after its TMA is issued (profiles/r02_pipeline_trace_fine.log) — 6 stages capped the kernel at one
+    // tile per ~950 clk.
+    const int sa_max = s.c8 ? 24 : 6;
+    while (p.sa < sa_max && fits(p.sa + 1, p.sb)) ++p.sa;
   } else {
     p.sb = 2;
     p.sa = 2;
@@ -292,7 +304,7 @@ inline bool build_igemm(const ConvSpec& s, IgemmLaunch* L, std::string* why) {
   }
   p.ws = ws ? 1 : 0;
   p.dual = s.dual != 0 ? 1 : 0;
-  L->smem = igemm_smem_bytes(n_tile, tps, cg, p.sa, p.a_stage_bytes, p.sb, s.pair);
+  L->smem = igemm_smem_bytes(n_tile, tps, cg, p.sa, p.a_stage_bytes, p.sb, s.pair, wide);
 
   // tensor maps
   {
@@ -374,10 +386,27 @@ inline bool build_igemm(const ConvSpec& s, IgemmLaunch* L, std::string* why) {
       const uint64_t dimsC[5] = {(uint64_t)s.out.c, (uint64_t)sx, wv, hv, (uint64_t)s.out.b};
       const uint64_t stridesC[4] = {(uint64_t)p.o_pix * 2, (uint64_t)p.o_pix * 2 * sx, (uint64_t)p.o_row * 2,
                                     (uint64_t)p.o_img * 2};
-      const uint32_t box4[5] = {32, 1, 8, 4, 1}, box1[5] = {32, 1, 8, 1, 1};
+      const uint32_t bc = wide ? 64 : 32;  // channels per box row
+      const int sw = wide ? 128 : 64;
+      const uint32_t box4[5] = {bc, 1, 8, 4, 1}, box1[5] = {bc, 1, 8, 1, 1};
       const __nv_bfloat16* baseC = s.out.ptr + (long long)s.out_halo * p.o_row + (long long)s.out_halo * p.o_pix;
-      if (!encode_tmap_bf16(&L->tmC4, baseC, 5, dimsC, stridesC, box4, why, 64)) return false;
-      if (!encode_tmap_bf16(&L->tmC1, baseC, 5, dimsC, stridesC, box1, why, 64)) return false;
+      if (s.epi_mode == EPI_D2S && !(s.out.hs & 1)) {
+        // Four input rows of one sub-pixel row dy are four output rows 2 apart: a single box needs
+        // [channel][dx][x][dy][input row], and the image index is folded into the last dimension (stored rows per
+        // image are even, so image b starts hs/2 row pairs after image b-1).  The folded dimension also covers the
+        // halo rows between images, which the kernel never addresses: it only uses this map for warps whose four
+        // rows are valid rows of ONE image, everything else goes row by row through tmC1.  (An odd number of stored
+        // rows — UNet levels whose skip tensor has an odd size — keeps d2s_hs2 = 0: row-by-row stores only.)
+        p.d2s_hs2 = s.out.hs / 2;
+        const uint64_t dimsD[5] = {(uint64_t)s.out.c, 2, wv, 2, (uint64_t)s.out.b * p.d2s_hs2};
+        const uint64_t stridesD[4] = {(uint64_t)p.o_pix * 2, (uint64_t)p.o_pix * 4, (uint64_t)p.o_row * 2,
+                                      (uint64_t)p.o_row * 4};
+        const uint32_t boxD[5] = {bc, 1, 8, 1, 4};
+        if (!encode_tmap_bf16(&L->tmC4, baseC, 5, dimsD, stridesD, boxD, why, sw)) return false;
+      } else if (!encode_tmap_bf16(&L->tmC4, baseC, 5, dimsC, stridesC, box4, why, sw)) {
+        return false;
+      }
+      if (!encode_tmap_bf16(&L->tmC1, baseC, 5, dimsC, stridesC, box1, why, sw)) return false;
     }
     if (s.pool.ptr) {
       if (s.epi_mode != EPI_STORE) return fail("fused pooling needs a plain store epilogue");

@@ -3,6 +3,7 @@
 // convolution.  Each invocation runs ONE test so that a trap in one cannot mask the others.
 //
 //   probe desc <r0> <sbo_bytes> <bo_mode>
+//   probe hbm [GiB]                          read / write / copy ceilings of plain kernels
 //   probe conv <taps> <cin> <n_total> <B> <Hs> <Ws> <a_mode> <bo_mode> <epi> [n_tile] [ws] [ctas]
 //
 // Build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -o tools/probe tools/probe.cu
@@ -295,6 +296,7 @@ static int run_conv(int argc, char** argv) {
   const int pair = argc > 16 ? atoi(argv[16]) : 0;   // pixel-pair mode (C_out = 64 layers)
   const int pool = argc > 17 ? atoi(argv[17]) : 0;   // fused 2x2 max-pool into a second buffer (EPI_STORE, even sizes)
   const int dual = argc > 18 ? atoi(argv[18]) : -1;  // two MMA issuer warps (-1 default = on)
+  const int wide = argc > 19 ? atoi(argv[19]) : -1;  // 128-byte staging rows (-1 auto, 0 off, 1 on)
   const int tw = taps == 9 ? 3 : 1;
   const int Hv = Hs - (tw - 1), Wv = Ws - (tw - 1);
   const bool c8 = cin == 8;              // first-layer mode: 8-channel input, no-swizzle descriptors
@@ -355,7 +357,7 @@ static int run_conv(int argc, char** argv) {
   }
   s.in_coff = coff; s.cin = cin; s.taps = taps; s.w = c8 ? dw8 : (pair ? dwp : dw); s.n_total = n_total; s.bias = dbias;
   s.act = act; s.slope = slope; s.epi_mode = epi; (void)a_mode; (void)bo_mode;
-  s.n_tile = n_tile; s.force_ws = ws; s.max_ctas = ctas; s.cg = cg; s.flat = flat; s.dual = dual;
+  s.n_tile = n_tile; s.force_ws = ws; s.max_ctas = ctas; s.cg = cg; s.flat = flat; s.dual = dual; s.wide = wide;
   const int halo = 2, ocoff = 32;
   int Ho = 0, Wo = 0, Co = 0;
   const int unpad = 1;
@@ -399,7 +401,7 @@ static int run_conv(int argc, char** argv) {
   if (!build_igemm(s, &L, &why)) { printf("build_igemm failed: %s\n", why.c_str()); return 2; }
   printf("CONV taps=%d cin=%d N=%d B=%d %dx%d a_mode=%d bo=%d epi=%d | n_tile=%d tiles=%d (x%d y%d n%d) grid=%d sa=%d sb=%d ws=%d smem=%zu\n",
          taps, cin, n_total, B, Hs, Ws, a_mode, bo_mode, epi, L.n_tile, L.p.total_tiles, L.p.tiles_x,
-         L.p.tiles_y, L.p.tiles_n, L.grid, L.p.sa, L.p.sb, L.p.ws, L.smem); printf("  tps=%d cg=%d flat=%d\n", L.tps, L.cg, L.p.flat);
+         L.p.tiles_y, L.p.tiles_n, L.grid, L.p.sa, L.p.sb, L.p.ws, L.smem); printf("  tps=%d cg=%d flat=%d wide=%d\n", L.tps, L.cg, L.p.flat, L.p.wide);
 
   naive_conv_kernel<<<1024, 256>>>(din, B, Hs, Ws, Cbuf, coff, cin, dw, taps, n_total, dbias, act, slope, dref);
   CK(cudaGetLastError());
@@ -427,17 +429,18 @@ static int run_conv(int argc, char** argv) {
   printf("  time %.3f ms  -> %.1f TFLOP/s (useful)\n", ms, L.flops / ms * 1e-9);
   if (getenv("NIND_TRACE")) {
     long long* dtr;
-    CK(cudaMalloc(&dtr, 64 * 8 * sizeof(long long)));
-    CK(cudaMemset(dtr, 0, 64 * 8 * sizeof(long long)));
+    CK(cudaMalloc(&dtr, 64 * 16 * sizeof(long long)));
+    CK(cudaMemset(dtr, 0, 64 * 16 * sizeof(long long)));
     CK(launch_igemm(L, derr, 0, dtr));
     CK(cudaDeviceSynchronize());
-    std::vector<long long> tr(64 * 8);
+    std::vector<long long> tr(64 * 16);
     CK(cudaMemcpy(tr.data(), dtr, tr.size() * 8, cudaMemcpyDeviceToHost));
     const long long t0 = tr[0];
-    printf("  trace (CTA 0, clk rel. to first A issue): tile | A_issue MMA_tempty MMA_afull MMA_done EPI_tfull EPI_tmem EPI_done\n");
+    printf("  trace (CTA 0, clk rel. to first A issue): tile | A_issue MMA_tempty MMA_afull MMA_done EPI_tfull EPI_tmem EPI_done"
+           " | first half: ld0 staged fenced stored | second half: buf_free ld\n");
     for (int t = 0; t < 16; ++t) {
       printf("   %2d |", t);
-      for (int e = 0; e < 7; ++e) printf(" %8lld", tr[t * 8 + e] ? tr[t * 8 + e] - t0 : -1);
+      for (int e = 0; e < 13; ++e) printf(" %8lld", tr[t * 16 + e] ? tr[t * 16 + e] - t0 : -1);
       printf("\n");
     }
   }
@@ -521,6 +524,106 @@ static int run_conv(int argc, char** argv) {
   return bad ? 1 : 0;
 }
 
+// ------------------------------------------------------------------ HBM ceilings (probe hbm [GiB])
+// What a plain CUDA-core kernel reaches on this GPU for read-only, write-only, copy and the store patterns of the
+// conv epilogues (64-byte halves of a 128-byte pixel written by different instructions; 128 of every 256 bytes =
+// one channel half of a concat buffer).  MODE: 0 read, 1 write, 2 copy, 3 write in 64 B halves, 4 write 128 of 256 B,
+// 5 read 1 : write 2 (the 2x2/s2 up-convs' mix).
+template <int MODE>
+__global__ void __launch_bounds__(256) hbm_kernel(const uint4* __restrict__ src, uint4* __restrict__ dst, size_t n16,
+                                                  uint32_t* sink) {
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  uint4 acc = make_uint4(0, 0, 0, 0);
+  const uint4 val = make_uint4(threadIdx.x, blockIdx.x, 3, 4);
+  if (MODE == 0) {
+    for (; i < n16; i += stride) { const uint4 v = __ldg(src + i); acc.x ^= v.x; acc.y ^= v.y; acc.z ^= v.z; acc.w ^= v.w; }
+    if ((acc.x ^ acc.y ^ acc.z ^ acc.w) == 0x12345678u) *sink = 1;
+  } else if (MODE == 1) {
+    for (; i < n16; i += stride) dst[i] = val;
+  } else if (MODE == 2) {
+    for (; i < n16; i += stride) dst[i] = __ldg(src + i);
+  } else if (MODE == 3) {
+    // a warp covers 8 pixels x 128 B in two instructions: lanes (pixel = lane / 4, chunk = lane % 4), halves 0 then 1
+    const size_t warps = stride / 32, w0 = i / 32;
+    const int lane = threadIdx.x & 31;
+    for (size_t w = w0; w * 64 + 63 < n16; w += warps) {
+      uint4* base = dst + w * 64 + (size_t)(lane >> 2) * 8 + (lane & 3);
+      base[0] = val;
+      base[4] = val;
+    }
+  } else if (MODE == 4) {
+    // 128 contiguous bytes of every 256: 16-byte chunk c of the dense index -> chunk (c / 8) * 16 + c % 8
+    for (; i < n16 / 2; i += stride) dst[(i >> 3) * 16 + (i & 7)] = val;
+  } else {
+    for (; i < n16 / 2; i += stride) {
+      const uint4 v = __ldg(src + i);
+      dst[2 * i] = v;
+      dst[2 * i + 1] = val;
+    }
+  }
+}
+
+static int run_hbm(double gib) {
+  const size_t bytes = (size_t)(gib * (1ull << 30)), n16 = bytes / 16;
+  uint4 *a, *b;
+  uint32_t* sink;
+  CK(cudaMalloc(&a, bytes));
+  CK(cudaMalloc(&b, bytes));
+  CK(cudaMalloc(&sink, 4));
+  CK(cudaMemset(a, 1, bytes));
+  CK(cudaMemset(b, 2, bytes));
+  int sms = 0;
+  CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0));
+  cudaEvent_t e0, e1;
+  CK(cudaEventCreate(&e0));
+  CK(cudaEventCreate(&e1));
+  const char* names[6] = {"read only", "write only", "copy (read + write)", "write, 64 B halves of a 128 B pixel",
+                          "write 128 of every 256 B", "read 1 : write 2"};
+  for (int mode = 0; mode < 6; ++mode) {
+    for (int per_sm : {4, 8}) {
+      const int grid = sms * per_sm;
+      float best = 1e30f;
+      for (int it = 0; it < 6; ++it) {
+        CK(cudaEventRecord(e0));
+        switch (mode) {
+          case 0: hbm_kernel<0><<<grid, 256>>>(a, b, n16, sink); break;
+          case 1: hbm_kernel<1><<<grid, 256>>>(a, b, n16, sink); break;
+          case 2: hbm_kernel<2><<<grid, 256>>>(a, b, n16, sink); break;
+          case 3: hbm_kernel<3><<<grid, 256>>>(a, b, n16, sink); break;
+          case 4: hbm_kernel<4><<<grid, 256>>>(a, b, n16, sink); break;
+          default: hbm_kernel<5><<<grid, 256>>>(a, b, n16, sink); break;
+        }
+        CK(cudaEventRecord(e1));
+        CK(cudaEventSynchronize(e1));
+        float ms;
+        CK(cudaEventElapsedTime(&ms, e0, e1));
+        if (it > 0 && ms < best) best = ms;
+      }
+      // bytes that cross the HBM interface
+      const double moved = mode == 2 ? 2.0 * bytes : (mode == 4 ? 0.5 * bytes : (mode == 5 ? 1.5 * bytes : 1.0 * bytes));
+      printf("hbm %-38s %d CTAs/SM  %7.3f ms  %7.1f GB/s\n", names[mode], per_sm, best, moved / best / 1e6);
+    }
+  }
+  // cudaMemsetAsync / cudaMemcpyAsync D2D for comparison (the driver's own kernels / copy engines)
+  for (int k = 0; k < 2; ++k) {
+    float best = 1e30f;
+    for (int it = 0; it < 4; ++it) {
+      CK(cudaEventRecord(e0));
+      if (k == 0) CK(cudaMemsetAsync(b, 0, bytes));
+      else CK(cudaMemcpyAsync(b, a, bytes, cudaMemcpyDeviceToDevice));
+      CK(cudaEventRecord(e1));
+      CK(cudaEventSynchronize(e1));
+      float ms;
+      CK(cudaEventElapsedTime(&ms, e0, e1));
+      if (it > 0 && ms < best) best = ms;
+    }
+    printf("hbm %-38s            %7.3f ms  %7.1f GB/s\n", k == 0 ? "cudaMemsetAsync" : "cudaMemcpyAsync D2D", best,
+           (k == 0 ? 1.0 : 2.0) * bytes / best / 1e6);
+  }
+  return 0;
+}
+
 int main(int argc, char** argv) {
   if (argc < 2) { printf("usage: probe desc|conv ...\n"); return 2; }
   if (!strcmp(argv[1], "desc")) {
@@ -532,5 +635,6 @@ int main(int argc, char** argv) {
     return run_desc0(atoi(argv[2]), atoi(argv[3]), atoi(argv[4]), atoi(argv[5]));
   }
   if (!strcmp(argv[1], "conv")) return run_conv(argc, argv);
+  if (!strcmp(argv[1], "hbm")) return run_hbm(argc > 2 ? atof(argv[2]) : 4.0);
   return 2;
 }

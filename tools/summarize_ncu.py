@@ -22,7 +22,7 @@ out = [f"# ncu evidence ({prefix}; B200; `python bench.py --steps 2 --warmup 3 -
        f"cs 248, 4 forwards of 133 crops per image)\n",
        f"Kernel sources: `{_build.build_key()[:16]}` (nind_denoise_b200/_build.py:build_key).  Captured by "
        "tools/run_ncu_r2.sh after the same command exited 0 without ncu.\n",
-       "## Launch list of the two timed steps (`--metrics gpu__time_duration.sum --clock-control none -s 279 -c 186`)\n"]
+       "## Launch list of the two timed steps (`--metrics gpu__time_duration.sum --clock-control none --profile-from-start off`)\n"]
 rows = [r for r in csv.reader(open(lpath)) if len(r) > 5]
 hdr, data = rows[0], rows[1:]
 ik, iv, iu = hdr.index("Kernel Name"), hdr.index("Metric Value"), hdr.index("Metric Unit")
@@ -54,7 +54,7 @@ want = [("gpu__time_duration.sum", "ms", "time"), ("sm__cycles_elapsed.avg.per_s
         ("launch__registers_per_thread", "", "regs"), ("launch__block_size", "", "threads"),
         ("launch__shared_mem_per_block_dynamic", "KB", "smem")]
 scale = {"Gbyte": 1e3, "Mbyte": 1.0, "Kbyte": 1e-3, "byte": 1e-6, "us": 1e-3, "ms": 1.0, "ns": 1e-6, "Ghz": 1.0, "Mhz": 1e-3}
-out.append("## `--set full` capture of the 22 conv launches of the first timed forward (133 crops; `-k regex:igemm -s 264 -c 22`)\n")
+out.append("## `--set full` capture of the 22 conv launches of the first timed forward (133 crops; `--profile-from-start off -k regex:igemm -c 22`)\n")
 out.append("| layer | kernel | " + " | ".join(f"{lab} ({u})" if u else lab for _, u, lab in want) + " |")
 out.append("|---|---|" + "---|" * len(want))
 traffic = {}
