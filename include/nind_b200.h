@@ -163,6 +163,11 @@ int nind_tiled_denoise_host_range(nind_net* net, const float* img_chw_host, floa
                                   int width, int cs, int ucs, int ol, int batch, int crop_begin, int crop_end,
                                   int d2h_y0, int d2h_y1, float** d_out);
 int nind_host_join(nind_net* net, void* stream);
+/* Same, but only after the step of the LAST nind_tiled_denoise_host_range call that makes band rows [band start, y)
+ * final: lets a rank hand the rows a neighbour owns to that neighbour while its remaining crops still run. */
+int nind_host_join_rows(nind_net* net, int y, void* stream);
+/* rows[k] = first band row that is NOT final after step k of the last nind_tiled_denoise_host_range call. */
+int nind_host_rows_done(nind_net* net, int* rows, int max_rows, int* n);
 
 /* Page-lock an existing host range (e.g. a shared-memory mapping every rank of a multi-GPU job writes
  * its output rows into) so that copies to/from it are true asynchronous DMA.  The reference has no

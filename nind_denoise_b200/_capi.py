@@ -65,6 +65,8 @@ SIGNATURES = {
     "nind_tiled_denoise_host_range": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p] + [C.c_int] * 10
                                       + [C.POINTER(C.c_void_p)]),
     "nind_host_join": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "nind_host_join_rows": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p]),
+    "nind_host_rows_done": (C.c_int, [C.c_void_p, C.POINTER(C.c_int), C.c_int, C.POINTER(C.c_int)]),
     "nind_host_register": (C.c_int, [C.c_void_p, C.c_size_t]),
     "nind_host_unregister": (C.c_int, [C.c_void_p]),
     "nind_kernel_launches": (C.c_int64, []),

@@ -131,6 +131,8 @@ struct nind_net {
   unsigned host_seq = 0;
   cudaStream_t s_in = nullptr, s_comp = nullptr, s_out = nullptr;
   std::vector<cudaEvent_t> ev_in, ev_done;
+  std::vector<cudaEvent_t> ev_rows;   // host-range pipeline: recorded on s_comp after each step's stitch
+  std::vector<int> rows_done;         // band rows [y0, rows_done[k]) are final after step k (last enqueue)
   cudaEvent_t ev_join = nullptr;
   int flat = -1;
   int pair64 = 1;  // pixel-pair mode for the C_out = 64 3x3 layers (validated on B200, profiles/r02_pair_mode_first_light.log)
@@ -172,6 +174,7 @@ struct nind_net {
     }
     for (auto e : ev_in) cudaEventDestroy(e);
     for (auto e : ev_done) cudaEventDestroy(e);
+    for (auto e : ev_rows) cudaEventDestroy(e);
     if (s_in) { cudaStreamDestroy(s_in); cudaStreamDestroy(s_comp); cudaStreamDestroy(s_out); }
   }
 };
@@ -1273,6 +1276,12 @@ static int enqueue_host_range_impl(nind_net* net, const float* img_chw_host, flo
     net->ev_in.push_back(a);
     net->ev_done.push_back(b);
   }
+  while (net->ev_rows.size() < steps.size()) {
+    cudaEvent_t a;
+    CUDA_TRY(cudaEventCreateWithFlags(&a, cudaEventDisableTiming));
+    net->ev_rows.push_back(a);
+  }
+  net->rows_done.clear();
   // plans first: building one allocates (and zero-fills) its arena, which must not happen between enqueues
   std::vector<Plan*> plans(steps.size(), nullptr);
   for (size_t k = 0; k < steps.size(); ++k)
@@ -1335,6 +1344,8 @@ static int enqueue_host_range_impl(nind_net* net, const float* img_chw_host, flo
                                    (size_t)(c1 - c0) * width * sizeof(float), 3, cudaMemcpyDeviceToHost, net->s_out));
       }
     }
+    CUDA_TRY(cudaEventRecord(net->ev_rows[k], net->s_comp));
+    net->rows_done.push_back(done);
   }
   if ((rc = scratch_release(net, net->s_comp))) return rc;
   CUDA_TRY(cudaEventRecord(S.out_free, net->s_out));
@@ -1397,6 +1408,27 @@ int nind_host_join(nind_net* net, void* stream) {
   if (!net->ev_join) CUDA_TRY(cudaEventCreateWithFlags(&net->ev_join, cudaEventDisableTiming));
   CUDA_TRY(cudaEventRecord(net->ev_join, net->s_comp));
   CUDA_TRY(cudaStreamWaitEvent(static_cast<cudaStream_t>(stream), net->ev_join, 0));
+  return 0;
+}
+
+int nind_host_join_rows(nind_net* net, int y, void* stream) {
+  if (!net) return fail(NIND_E_INVALID, "null handle");
+  ENTER(net);
+  for (size_t k = 0; k < net->rows_done.size(); ++k)
+    if (net->rows_done[k] >= y) {
+      CUDA_TRY(cudaStreamWaitEvent(static_cast<cudaStream_t>(stream), net->ev_rows[k], 0));
+      return 0;
+    }
+  return fail(NIND_E_INVALID, "nind_host_join_rows: the last host-range call does not complete that row");
+}
+
+int nind_host_rows_done(nind_net* net, int* rows, int max_rows, int* n) {
+  if (!net || !n) return fail(NIND_E_INVALID, "null argument");
+  *n = (int)net->rows_done.size();
+  if (rows) {
+    if (max_rows < *n) return fail(NIND_E_INVALID, "rows array too small");
+    for (int k = 0; k < *n; ++k) rows[k] = net->rows_done[k];
+  }
   return 0;
 }
 

@@ -296,6 +296,15 @@ def _peer_gather(height, width, max_seam_rows, device, group, dst) -> PeerGather
     return pg
 
 
+def _peer_seams(width, max_rows, device, group) -> "PeerSeams":
+    key = ("seams", width, str(device), id(group))
+    ps = _peer_cache.get(key)
+    if ps is None or ps.max_rows < max_rows:
+        ps = PeerSeams(width, max_rows, device, group)
+        _peer_cache[key] = ps
+    return ps
+
+
 def _denoise_tiled_distributed_peer(img, model, cs, ucs, ol, batch, group, dst):
     """mode="peer" of ``denoise_tiled_distributed`` (see there)."""
     import torch.distributed as dist
@@ -510,6 +519,109 @@ def exchange_seams(band: Optional[torch.Tensor], extents, own, rank: int, group=
         band[:, a - y0:b - y0, :] += buf
 
 
+def owned_rows_up(extents: Sequence[Tuple[int, int]], height: int) -> List[Tuple[int, int]]:
+    """Row ownership of the host-buffer entry: a non-empty rank owns the rows from the END of the previous
+    non-empty band up to the end of its own band (the last one up to ``height``).  The grid row two crop ranges
+    share therefore belongs to the EARLIER rank — the later rank computes its part of that row first (raster
+    order) and can hand it over while both still run, whereas the earlier rank finishes its part last."""
+    own = [(0, 0)] * len(extents)
+    live = [r for r, (y0, y1) in enumerate(extents) if y1 > y0]
+    prev_end = 0
+    for i, r in enumerate(live):
+        end = max(prev_end, extents[r][1] if i + 1 < len(live) else height)
+        own[r] = (prev_end, end)
+        prev_end = end
+    return own
+
+
+def seam_plan(extents, own, rank: int):
+    """(sends, recvs) of ``rank`` for an ownership table: sends = [(owner, a, b)] rows [a, b) of this rank's band that
+    another rank owns; recvs = [(sender, a, b)] rows of this rank's own range that rank ``sender``'s band also
+    touches — in increasing rank order, which is the order the partial sums are added in."""
+    y0, y1 = extents[rank]
+    o0, o1 = own[rank]
+    sends, recvs = [], []
+    for r in range(len(extents)):
+        if r == rank:
+            continue
+        a, b = max(y0, own[r][0]), min(y1, own[r][1])
+        if y1 > y0 and b > a:
+            sends.append((r, a, b))
+        a, b = max(extents[r][0], o0), min(extents[r][1], o1)
+        if extents[r][1] > extents[r][0] and b > a:
+            recvs.append((r, a, b))
+    return sends, recvs
+
+
+def exchange_seams_up(band: Optional[torch.Tensor], extents, own, rank: int, group=None) -> None:
+    """Blocking form of the seam hand-over for any ownership table (CPU / gloo tests; the GPU path uses
+    ``PeerSeams``): one batched P2P group, partial sums added in rank order."""
+    import torch.distributed as dist
+
+    if band is None:
+        return
+    y0 = extents[rank][0]
+    sends, recvs = seam_plan(extents, own, rank)
+    ops, keep, bufs = [], [], []
+    for r, a, b in sends:
+        keep.append(band[:, a - y0:b - y0, :].contiguous())
+        ops.append(dist.P2POp(dist.isend, keep[-1], r, group))
+    for r, a, b in recvs:
+        bufs.append(torch.empty((3, b - a, band.shape[2]), dtype=band.dtype, device=band.device))
+        ops.append(dist.P2POp(dist.irecv, bufs[-1], r, group))
+    if ops:
+        for req in dist.batch_isend_irecv(ops):
+            req.wait()
+    for (r, a, b), buf in zip(recvs, bufs):
+        band[:, a - y0:b - y0, :] += buf
+
+
+class PeerSeams:
+    """Every rank's seam receive area ([2 images][world senders][3, max_rows, W] fp32), mapped into the ranks that
+    send to it through CUDA IPC: a rank hands the rows a neighbour owns to that neighbour with ONE peer-to-peer DMA
+    over NVLink as soon as its own crops are done with them (copy engines; no NCCL kernel that would take SMs from
+    the persistent conv kernels and wait for its peer).  Completion is signalled through ``SharedHostImage``'s
+    flags.  Collective constructor."""
+
+    def __init__(self, width: int, max_rows: int, device, group=None):
+        import torch.distributed as dist
+
+        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        self.width, self.max_rows, self.device = width, max(1, max_rows), device
+        self.slot = 3 * self.max_rows * width
+        lib = _capi.lib()
+        ptr = C.c_void_p()
+        handle = C.create_string_buffer(64)
+        with torch.cuda.device(device):
+            _capi.check(lib.nind_peer_alloc(2 * self.world * self.slot * 4, C.byref(ptr), handle))
+        handles = [None] * self.world
+        dist.all_gather_object(handles, handle.raw, group=group)
+        self._handles = handles
+        self._ptrs = {self.rank: ptr.value}
+        dist.barrier(group)
+
+    def _base(self, owner: int) -> int:
+        if owner not in self._ptrs:  # map the owner's area on THIS rank's device (lazy peer access over NVLink)
+            ptr = C.c_void_p()
+            with torch.cuda.device(self.device):
+                _capi.check(_capi.lib().nind_peer_open(self._handles[owner], C.byref(ptr)))
+            self._ptrs[owner] = ptr.value
+        return self._ptrs[owner]
+
+    def view(self, owner: int, parity: int, sender: int, rows: int) -> torch.Tensor:
+        """[3, rows, W] view of rank ``owner``'s slot for ``sender`` (image parity 0 | 1), on this rank's device."""
+        assert rows <= self.max_rows
+        off = ((parity & 1) * self.world + sender) * self.slot * 4
+        t = torch.as_tensor(_DevicePtr(self._base(owner) + off, (3, self.max_rows, self.width)), device=self.device)
+        return t[:, :rows]
+
+    def close(self):
+        lib = _capi.lib()
+        for owner, ptr in list(getattr(self, "_ptrs", {}).items()):
+            (lib.nind_peer_free if owner == self.rank else lib.nind_peer_close)(C.c_void_p(ptr))
+        self._ptrs = {}
+
+
 def host_range(model, img_host: torch.Tensor, out_host: torch.Tensor, cs: int, ucs: int, ol: int, batch: int,
                crop_begin: int, crop_end: int, d2h_y0: int, d2h_y1: int) -> torch.Tensor:
     """``nind_tiled_denoise_host_range`` + ``nind_host_join``: enqueue one rank's crops on the library's
@@ -583,6 +695,25 @@ class SharedHostImage:
         self._flags[self._rank * self._FLAG_STRIDE] = self._seq
         return self._seq
 
+    def seam_rows_sent(self, seq: int, rows: int) -> None:
+        """``rows`` of the rows this rank hands over for image ``seq`` have landed in their owners' receive areas."""
+        self._flags[self._rank * self._FLAG_STRIDE + 1] = (seq << 32) | rows
+
+    def seam_rows_of(self, rank: int, seq: int) -> int:
+        """How many of rank ``rank``'s hand-over rows of image ``seq`` have landed (all of them once it is past it)."""
+        v = int(self._flags[rank * self._FLAG_STRIDE + 1])
+        return (v & 0xFFFFFFFF) if (v >> 32) == seq else (1 << 31 if (v >> 32) > seq else 0)
+
+    def wait_flag(self, rank: int, slot: int, seq: int, timeout: float = 60.0) -> None:
+        """Spin until rank ``rank``'s counter ``slot`` (0 arrival, 1 seam rows sent) has reached ``seq``."""
+        import time
+
+        view = self._flags[rank * self._FLAG_STRIDE + slot]
+        t0 = time.perf_counter()
+        while int(view) < seq:
+            if time.perf_counter() - t0 > timeout:
+                raise RuntimeError(f"SharedHostImage: rank {rank} did not reach image {seq} within the time-out")
+
     def wait_all(self, timeout: float = 60.0) -> None:
         """Spin until every rank has arrived at this rank's current sequence number."""
         import time
@@ -607,12 +738,17 @@ class SharedHostImage:
 
 def denoise_tiled_distributed_host(img_host: torch.Tensor, model, cs: int, ucs: int, ol: int = DEFAULT_OVERLAP,
                                    batch: Optional[int] = None, group=None, dst: int = 0, out=None,
-                                   band_fn: Optional[Callable] = None) -> Optional[torch.Tensor]:
+                                   band_fn: Optional[Callable] = None,
+                                   phases: Optional[list] = None) -> Optional[torch.Tensor]:
     """Multi-GPU host-buffer entry: every rank holds the same CPU image (pinned for full PCIe speed),
     uploads only the rows its crop range reads and stitches its band on its GPU.
 
-    * ``out`` a ``SharedHostImage``: neighbours exchange the seam rows over NCCL, then every rank copies
-      the rows it owns straight into the shared host image — N PCIe links in parallel, no gather.
+    * ``out`` a ``SharedHostImage``: every rank copies the rows it owns (``owned_rows_up``) straight into the
+      shared host image — N PCIe links in parallel, no gather.  The rows of its band an earlier rank owns (its
+      part of the grid row the two crop ranges share) are final after its first step(s) and go to that rank's
+      GPU by peer DMA (``PeerSeams``) while the remaining crops run; the owner adds them to its own partial
+      sums after its last step — the step that produces those rows — and downloads them with that step's rows.
+      ``phases`` (a list) receives (name, host time) marks of the call's own blocking points.
     * ``out`` a plain CPU tensor or None: bands are gathered to rank ``dst`` over NCCL and copied to host
       there (one PCIe link).
 
@@ -629,36 +765,110 @@ def denoise_tiled_distributed_host(img_host: torch.Tensor, model, cs: int, ucs: 
         if out.shape != (3, H, W):
             raise ValueError(f"shared output is {out.shape}, image is {(3, H, W)}")
         extents = band_extents(W, H, cs, ucs, ol, ranges)
-        own = owned_rows(extents, H)
+        own = owned_rows_up(extents, H)
         y0, y1 = extents[rank]
         o0, o1 = own[rank]
-        # own rows that earlier ranks' bands also touch are only final after the seam exchange
-        lo = min(o1, max([o0] + [extents[r][1] for r in range(rank) if extents[r][1] > extents[r][0]]))
-        band = full = None
-        if ce > cb:
-            if band_fn is None:
-                if batch is None:
-                    batch = default_batch(ce - cb, cs, _nx(W, ucs, ol))
-                # H2D | forward | stitch | D2H of rows [lo, o1) pipelined inside the library; the stream we
-                # continue on is ordered after its compute stream
-                full = host_range(model, img_host, out.tensor, cs, ucs, ol, batch, cb, ce, lo, o1)
-                band = full[:, y0:y1, :]
-            else:
+        sends, recvs = seam_plan(extents, own, rank)
+        # own rows that later ranks' bands also touch are only final after their partial sums were added
+        hi = max(o0, min([o1] + [a for _, a, _ in recvs]))
+        seq = out._seq + 1  # the image this call produces
+        import time as _time
+
+        def mark(name):
+            if phases is not None:
+                phases.append((name, _time.perf_counter()))
+
+        mark("start")
+        if band_fn is not None:  # CPU (gloo) emulation: blocking hand-over at the end
+            band = None
+            if ce > cb:
                 band, by0, by1 = band_fn(img_host, cb, ce)
                 assert (by0, by1) == (y0, y1)
-                out.tensor[:, lo:o1, :].copy_(band[:, lo - y0:o1 - y0, :])
-        exchange_seams(band, extents, own, rank, group)
-        if lo > o0:
-            for c in range(3):
-                out.tensor[c, o0:lo].copy_(band[c, o0 - y0:lo - y0], non_blocking=True)
-        if band_fn is None and ce > cb:
+            exchange_seams_up(band, extents, own, rank, group)
+            if o1 > o0:
+                out.tensor[:, o0:o1, :].copy_(band[:, o0 - y0:o1 - y0, :])
+        else:
+            dev = model._device if getattr(model, "_handle", None) else next(model.parameters()).device
+            max_rows = max([b - a for r in range(world) for _, a, b in seam_plan(extents, own, r)[0]] + [1])
+            ps = _peer_seams(W, max_rows, dev, group)  # collective on first use: every rank, also one without crops
+        if band_fn is not None:
+            pass
+        elif ce > cb:
+            if batch is None:
+                batch = default_batch(ce - cb, cs, _nx(W, ucs, ol))
+            if ("side", str(dev)) not in _peer_cache:
+                _peer_cache[("side", str(dev))] = torch.cuda.Stream(device=dev)
+                _peer_cache[("token", str(dev))] = torch.zeros(1, device=dev)
+            side = _peer_cache[("side", str(dev))]
+            # H2D | forward | stitch | D2H of rows [o0, hi) pipelined inside the library
+            full = host_range(model, img_host, out.tensor, cs, ucs, ol, batch, cb, ce, o0, hi)
+            mark("enqueued")
+            lib, h = _capi.lib(), model.native_handle()
+            # Hand-over: the rows of this band that earlier ranks own — its part of the grid row it shares with the
+            # previous rank — become final step by step (all but the last `ol` rows after the first step); each
+            # chunk goes to its owner's receive area by peer DMA on a side stream that only waits for that step.
+            chunks = []  # (event, rows handed over so far)
+            if sends:
+                for r, _, _ in sends:  # the owner must be done with image seq-2, which used the same slot
+                    out.wait_flag(r, 0, seq - 2)
+                nst = C.c_int()
+                rd = (C.c_int * 1024)()
+                _capi.check(lib.nind_host_rows_done(h, rd, 1024, C.byref(nst)))
+                prev, total = y0, 0
+                for k in range(nst.value):
+                    todo = [(r, a, max(a, prev), min(b, rd[k])) for r, a, b in sends if min(b, rd[k]) > max(a, prev)]
+                    if todo:
+                        with torch.cuda.device(dev):
+                            _capi.check(lib.nind_host_join_rows(h, rd[k], C.c_void_p(side.cuda_stream)))
+                        for r, a, c0, c1 in todo:
+                            copy_planes(ps.view(r, seq, rank, c1 - a)[:, c0 - a:], full[:, c0:c1], side)
+                            total += c1 - c0
+                        ev = torch.cuda.Event()
+                        ev.record(side)
+                        chunks.append((ev, total))
+                    prev = max(prev, rd[k])
+            # Receive side, in rank order: add what the later ranks hand over as it arrives (their counters say how
+            # many rows have landed) and download the own rows below `hi` as far as they are final.
+            state = []  # per sender: [rank, a, b, rows before this range in the sender's hand-over order, added]
+            for r, a, b in recvs:
+                before = sum(bb - aa for _, aa, bb in seam_plan(extents, own, r)[0] if aa < a)
+                state.append([r, a, b, before, 0])
+            landed = hi   # own rows [o0, landed) are on their way to the shared host image
+            cur, spins, t_spin = 0, 0, _time.perf_counter()
+            while chunks or cur < len(state) or landed < o1:
+                spins += 1
+                if (spins & 0xFFF) == 0 and _time.perf_counter() - t_spin > 60.0:
+                    raise RuntimeError("denoise_tiled_distributed_host: a neighbour's rows did not arrive within 60 s")
+                if chunks and chunks[0][0].query():
+                    out.seam_rows_sent(seq, chunks.pop(0)[1])
+                    if not chunks:
+                        mark("handed_over")
+                if cur < len(state):
+                    r, a, b, before, added = state[cur]
+                    have = min(b - a, max(0, out.seam_rows_of(r, seq) - before))
+                    if have > added:
+                        add_rows(full[:, a + added:a + have], ps.view(rank, seq, r, have)[:, added:])
+                        state[cur][4] = have
+                        if have == b - a:
+                            cur += 1
+                            if cur == len(state):
+                                mark("received")
+                final = min([o1] + [st[1] + st[4] for st in state[cur:]])
+                if final > landed:
+                    for c in range(3):
+                        out.tensor[c, landed:final].copy_(full[c, landed:final], non_blocking=True)
+                    landed = final
+            if not sends:
+                mark("handed_over")
             _capi.check(_capi.lib().nind_host_sync(model.native_handle()))
-            torch.cuda.current_stream(model._device).synchronize()
+            torch.cuda.current_stream(dev).synchronize()
+            mark("rows_landed")
         # every rank's rows have landed in the shared image: arrival counters in the segment itself (no NCCL
         # barrier); only the rank that returns the image waits
         out.arrive()
         if rank == dst:
             out.wait_all()
+        mark("all_arrived")
         return out.tensor if rank == dst else None
     if band_fn is None:
         dev = model._device if getattr(model, "_handle", None) else next(model.parameters()).device

@@ -100,3 +100,31 @@ def test_owned_rows_partition_the_image():
                 assert o0 >= y0 and (o1 <= y1 or o1 == o0)   # a rank only owns rows of its own band
                 rows[o0:o1] += 1
             assert (rows == 1).all()
+
+
+def test_owned_rows_up_partition_and_seam_plan_is_consistent():
+    """Ownership of the host-buffer entry (the EARLIER rank owns the grid row two ranges share): a partition of the
+    image rows inside each owner's band; every send has exactly one matching receive; rows are only handed to
+    earlier ranks, so a rank's hand-over is ready after its first step(s)."""
+    for world in (1, 2, 3, 5, 8, 19, 40):
+        for (w, h, cs, ucs, ol) in ((101, 83, 40, 28, 4), (600, 400, 56, 40, 6), (64, 300, 72, 40, 2)):
+            ranges = nb.shard_ranges(nb.n_crops(w, h, cs, ucs, ol), world)
+            ext = nb.band_extents(w, h, cs, ucs, ol, ranges)
+            own = nb.owned_rows_up(ext, h)
+            rows = np.zeros(h, dtype=np.int32)
+            for (o0, o1), (y0, y1) in zip(own, ext):
+                assert o1 == o0 or (o0 >= y0 and o1 <= y1)
+                rows[o0:o1] += 1
+            assert (rows == 1).all()
+            plans = [nb.seam_plan(ext, own, r) for r in range(world)]
+            sends = sorted((r, dst, a, b) for r, (s, _) in enumerate(plans) for dst, a, b in s)
+            recvs = sorted((src, r, a, b) for r, (_, rc) in enumerate(plans) for src, a, b in rc)
+            assert sends == recvs
+            assert all(dst < src for src, dst, _, _ in sends)
+            covered = np.zeros(h, dtype=np.int32)   # every band row is either owned or handed to its owner
+            for r, (y0, y1) in enumerate(ext):
+                mine = np.zeros(h, dtype=bool)
+                mine[own[r][0]:own[r][1]] = True
+                for _, a, b in plans[r][0]:
+                    mine[a:b] = True
+                assert mine[y0:y1].all()

@@ -4,6 +4,7 @@ Tolerances (BASELINE.json north_star): crop indexing and stitch geometry bit-exa
 max abs error <= 2e-2 and PSNR difference <= 0.05 dB versus the fp32 reference on 0..1 data.  Because
 default-initialised weights give a tiny output range (sigma_out ~ 0.007) every pixel test
 also bounds the error RELATIVE to the output's standard deviation."""
+import ctypes as C
 import math
 import os
 
@@ -385,9 +386,11 @@ def test_throughput_mode_matches_single_image_path(utnet):
 @pytest.mark.gpu
 @pytest.mark.parametrize("world", [2, 3, 5])
 def test_host_range_pipeline_composes_to_the_whole_image(utnet, world):
-    """nind_tiled_denoise_host_range: the per-rank share of the multi-GPU host entry, run here rank after
-    rank on one GPU with the seam exchange done locally, gives the single-GPU image; rows [lo, o1) arrive
-    in the host image straight from the pipeline."""
+    """nind_tiled_denoise_host_range + nind_host_join_rows: the per-rank share of the multi-GPU host entry, run here
+    rank after rank on one GPU (last rank first, so that every hand-over exists when its owner needs it) with the
+    ownership and seam plan of denoise_tiled_distributed_host, gives the single-GPU image; rows [o0, hi) arrive in
+    the host image straight from the pipeline, and the rows an earlier rank owns are final on a side stream that
+    only waited for the step that completes them."""
     from nind_denoise_b200.tiler import host_range
     rng = np.random.default_rng(21)
     H, W, cs, ucs, ol = 610, 455, 120, 96, 6
@@ -395,30 +398,31 @@ def test_host_range_pipeline_composes_to_the_whole_image(utnet, world):
     ref = nb.denoise_tiled_host(img, utnet, cs, ucs, ol, batch=7)
     ranges = nb.shard_ranges(nb.n_crops(W, H, cs, ucs, ol), world)
     ext = nb.band_extents(W, H, cs, ucs, ol, ranges)
-    own = nb.owned_rows(ext, H)
+    own = nb.owned_rows_up(ext, H)
     out = torch.full((3, H, W), float("nan")).pin_memory()
-    bands = []
-    for r, (cb, ce) in enumerate(ranges):
+    side = torch.cuda.Stream()
+    handed = {}   # (sender, owner) -> rows
+    for r in reversed(range(world)):
+        cb, ce = ranges[r]
         if ce <= cb:
-            bands.append(None)
             continue
         o0, o1 = own[r]
-        lo = min(o1, max([o0] + [ext[q][1] for q in range(r) if ext[q][1] > ext[q][0]]))
-        full = host_range(utnet, img, out, cs, ucs, ol, 6, cb, ce, lo, o1)
+        sends, recvs = nb.seam_plan(ext, own, r)
+        hi = max(o0, min([o1] + [a for _, a, _ in recvs]))
+        full = host_range(utnet, img, out, cs, ucs, ol, 6, cb, ce, o0, hi)
+        if sends:
+            _capi.check(_capi.lib().nind_host_join_rows(utnet.native_handle(), max(b for _, _, b in sends),
+                                                        C.c_void_p(side.cuda_stream)))
+            with torch.cuda.stream(side):
+                for q, a, b in sends:
+                    handed[(r, q)] = full[:, a:b].clone()
+            side.synchronize()
+        for q, a, b in recvs:   # rank order
+            full[:, a:b] += handed[(q, r)]
+        out[:, hi:o1] = full[:, hi:o1].cpu()
         _capi.check(_capi.lib().nind_host_sync(utnet.native_handle()))
         torch.cuda.synchronize()
-        bands.append(full[:, ext[r][0]:ext[r][1], :].clone())
-        assert not torch.isnan(out[:, lo:o1]).any()
-        # seam rows [o0, lo): what exchange_seams does between ranks
-        if lo > o0:
-            acc = torch.zeros((3, lo - o0, W), device="cuda")
-            for q in range(r + 1):
-                if bands[q] is None:
-                    continue
-                a, b = max(ext[q][0], o0), min(ext[q][1], lo)
-                if b > a:
-                    acc[:, a - o0:b - o0] += bands[q][:, a - ext[q][0]:b - ext[q][0]]
-            out[:, o0:lo] = acc.cpu()
+        assert not torch.isnan(out[:, o0:o1]).any()
     assert not torch.isnan(out).any()
     assert float((out - ref).abs().max()) <= 1e-6
 

@@ -1,8 +1,8 @@
-"""torchrun --nproc-per-node N tools/dist_phases_host.py [cs ucs]: per-rank phase break-down of the multi-GPU
-host-buffer entry (denoise_tiled_distributed_host with a SharedHostImage): enqueue, pipeline (H2D | forward | stitch
-| D2H of the rows no earlier rank touches), seam exchange, seam-row D2H, closing synchronisation.  Phases are
-separated by stream synchronisations (which serialise what would otherwise overlap: read the table as an upper
-bound per phase, next to the un-instrumented total printed last)."""
+"""torchrun --nproc-per-node N tools/dist_phases_host.py [cs ucs]: per-rank timeline of the multi-GPU host-buffer
+entry (denoise_tiled_distributed_host with a SharedHostImage), from the call's OWN blocking points (its `phases`
+marks; no extra synchronisation is added): enqueue of the H2D | forward | stitch | D2H pipeline, hand-over of the
+rows an earlier rank owns (peer DMA after the first step), arrival of the later rank's rows, all own rows landed in
+the shared host image (pipeline + add + tail D2H), every rank arrived (rank 0 only waits)."""
 import os
 import sys
 import time
@@ -12,8 +12,7 @@ import torch.distributed as dist
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import nind_denoise_b200 as nb  # noqa: E402
-from nind_denoise_b200 import _capi  # noqa: E402
-from nind_denoise_b200.tiler import _nx, default_batch, host_range  # noqa: E402
+from nind_denoise_b200.tiler import _nx, default_batch  # noqa: E402
 
 cs, ucs = (int(sys.argv[1]), int(sys.argv[2])) if len(sys.argv) > 2 else (248, 224)
 ol, W, H = 6, 6000, 4000
@@ -30,71 +29,53 @@ ranges = nb.shard_ranges(n, world)
 cb, ce = ranges[rank]
 batch = default_batch(ce - cb, cs, _nx(W, ucs, ol))
 ext = nb.band_extents(W, H, cs, ucs, ol, ranges)
-own = nb.owned_rows(ext, H)
+own = nb.owned_rows_up(ext, H)
+sends, recvs = nb.seam_plan(ext, own, rank)
 shared = nb.SharedHostImage((3, H, W))
-y0, y1 = ext[rank]
-o0, o1 = own[rank]
-lo = min(o1, max([o0] + [ext[r][1] for r in range(rank) if ext[r][1] > ext[r][0]]))
-lib = _capi.lib()
+NAMES = ["enqueued", "handed_over", "received", "rows_landed", "all_arrived"]
 
 
-def instrumented():
-    t = [time.perf_counter()]
-    full = host_range(model, img_host, shared.tensor, cs, ucs, ol, batch, cb, ce, lo, o1)
-    band = full[:, y0:y1, :]
-    t.append(time.perf_counter())                       # enqueue (CPU)
-    torch.cuda.current_stream().synchronize()
-    t.append(time.perf_counter())                       # compute + stitch (joined on the torch stream)
-    _capi.check(lib.nind_host_sync(model.native_handle()))
-    t.append(time.perf_counter())                       # pipelined D2H tail
-    nb.exchange_seams(band, ext, own, rank)
-    torch.cuda.current_stream().synchronize()
-    t.append(time.perf_counter())                       # seam exchange
-    if lo > o0:
-        for c in range(3):
-            shared.tensor[c, o0:lo].copy_(band[c, o0 - y0:lo - y0], non_blocking=True)
-    torch.cuda.current_stream().synchronize()
-    t.append(time.perf_counter())                       # seam rows D2H
-    dist.barrier()
-    t.append(time.perf_counter())                       # closing barrier
-    return [1e3 * (b - a) for a, b in zip(t, t[1:])]
+def run(phases=None):
+    nb.denoise_tiled_distributed_host(img_host, model, cs, ucs, ol, batch=batch, out=shared, phases=phases)
 
 
 for _ in range(3):
-    instrumented()
-torch.cuda.synchronize(); dist.barrier()
-acc = None
-reps = 6
+    run()
+reps = 8
+acc = [0.0] * len(NAMES)
 for _ in range(reps):
-    torch.cuda.synchronize(); dist.barrier()
-    p = instrumented()
-    acc = p if acc is None else [a + b for a, b in zip(acc, p)]
-mine = torch.tensor([a / reps for a in acc] + [float(ce - cb), float(lo - o0), float(o1 - lo)], device=dev)
+    torch.cuda.synchronize(); dist.barrier(); torch.cuda.synchronize()
+    ph = []
+    run(ph)
+    t0 = ph[0][1]
+    d = dict(ph)
+    last = t0
+    for i, k in enumerate(NAMES):
+        last = d.get(k, last)
+        acc[i] += 1e3 * (last - t0)
+mine = torch.tensor([a / reps for a in acc] + [float(ce - cb), float(sum(b - a for _, a, b in sends)),
+                                               float(sum(b - a for _, a, b in recvs)), float(own[rank][1] - own[rank][0])],
+                    device=dev)
 allp = [torch.zeros_like(mine) for _ in range(world)]
 dist.all_gather(allp, mine)
 if rank == 0:
-    print(f"world {world} cs {cs}: {n} crops, batch {batch}; ms per phase (each phase ends with a synchronisation)")
-    print("rank crops seam_rows piped_rows | enqueue  compute  d2h_tail  exchange  seam_d2h  barrier | sum")
+    print(f"world {world} cs {cs}: {n} crops, batch {batch}; ms since the start of the call (host clock, no added syncs)")
+    print("rank crops rows_sent rows_recv rows_owned | enqueued  handed_over  received  rows_landed  all_arrived")
     for r, v in enumerate(allp):
         v = v.tolist()
-        print(f"{r:4d} {int(v[6]):5d} {int(v[7]):9d} {int(v[8]):10d} | " + "  ".join(f"{x:7.3f}" for x in v[:6]) + f" | {sum(v[:6]):6.3f}")
-
-
-def plain():
-    nb.denoise_tiled_distributed_host(img_host, model, cs, ucs, ol, batch=batch, out=shared)
-
+        print(f"{r:4d} {int(v[5]):5d} {int(v[6]):9d} {int(v[7]):9d} {int(v[8]):10d} | " + "  ".join(f"{x:10.3f}" for x in v[:5]))
 
 for _ in range(2):
-    plain()
+    run()
 torch.cuda.synchronize(); dist.barrier(); torch.cuda.synchronize()
 t0 = time.perf_counter()
 for _ in range(reps):
-    plain()
+    run()
 torch.cuda.synchronize(); dist.barrier(); torch.cuda.synchronize()
 ms = torch.tensor([(time.perf_counter() - t0) / reps * 1e3], device=dev)
 dist.all_reduce(ms, op=dist.ReduceOp.MAX)
 if rank == 0:
-    print(f"un-instrumented total: {ms.item():.3f} ms per image -> {24.0 / ms.item() * 1e3:.0f} MP/s")
+    print(f"back-to-back total: {ms.item():.3f} ms per image -> {24.0 / ms.item() * 1e3:.0f} MP/s")
 shared.close()
 dist.barrier()
 dist.destroy_process_group()
