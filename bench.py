@@ -338,6 +338,9 @@ def main():
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
+        # one process per GPU: run on (and allocate the pinned host buffers from) the GPU's own NUMA node
+        if os.environ.get("NIND_NO_NUMA_BIND") is None:
+            nb.bind_host_to_gpu(local)
         dist.init_process_group("nccl", device_id=dev)
     wl = workload(args.cs)
     cs, ucs, ol = wl["cs"], wl["ucs"], wl["ol"]

@@ -8,8 +8,8 @@ runs in hand-written CUDA kernels behind the C ABI in include/nind_b200.h (libni
 from .networks import UNet, UtNet, register  # noqa: F401
 from .tiler import (CS_UNET, CS_UTNET, UCS_UNET, UCS_UTNET, assemble_bands, crop_table, denoise_tiled,  # noqa: F401
                     denoise_images_host, denoise_tiled_distributed, denoise_tiled_distributed_host, denoise_tiled_host, gather_crops, n_crops, shard_ranges,
-                    stitch_crops, OneImageDS, SharedHostImage, PeerGather, plan_steps, tiled_step, add_rows, band_extents, denoise_whole_image, pad_whole_image, owned_rows, exchange_seams, owned_rows_up, seam_plan, exchange_seams_up, PeerSeams)
+                    stitch_crops, OneImageDS, SharedHostImage, PeerGather, plan_steps, tiled_step, add_rows, band_extents, denoise_whole_image, pad_whole_image, owned_rows, exchange_seams, owned_rows_up, seam_plan, exchange_seams_up, PeerSeams, bind_host_to_gpu)
 
 __all__ = ["UtNet", "UNet", "register", "denoise_tiled", "denoise_tiled_host", "denoise_images_host", "denoise_tiled_distributed", "denoise_tiled_distributed_host",
            "crop_table", "n_crops", "shard_ranges", "assemble_bands", "gather_crops", "stitch_crops", "OneImageDS",
-           "SharedHostImage", "PeerGather", "plan_steps", "tiled_step", "add_rows", "band_extents", "denoise_whole_image", "pad_whole_image", "owned_rows", "exchange_seams", "owned_rows_up", "seam_plan", "exchange_seams_up", "PeerSeams"]
+           "SharedHostImage", "PeerGather", "plan_steps", "tiled_step", "add_rows", "band_extents", "denoise_whole_image", "pad_whole_image", "owned_rows", "exchange_seams", "owned_rows_up", "seam_plan", "exchange_seams_up", "PeerSeams", "bind_host_to_gpu"]

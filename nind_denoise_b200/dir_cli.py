@@ -177,6 +177,8 @@ def denoise_dir(in_paths: Sequence[str], out_paths: Sequence[str], model, cs: in
 def _replica(rank: int, args, model_path: str, work, results):
     """One process per GPU: pulls (index, in, out, baseline) items from the shared queue until it is empty."""
     torch.cuda.set_device(rank)
+    from .tiler import bind_host_to_gpu
+    bind_host_to_gpu(rank)  # this replica's pinned buffers and decode threads next to its GPU's PCIe root port
     model = load_model(_Args(args, model_path), torch.device("cuda", rank))
     while True:
         items = []

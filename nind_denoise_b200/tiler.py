@@ -640,6 +640,34 @@ def host_range(model, img_host: torch.Tensor, out_host: torch.Tensor, cs: int, u
         return torch.as_tensor(_DevicePtr(d_out.value, (3, H, W)), device=model._device)
 
 
+def bind_host_to_gpu(device_index: int) -> Optional[List[int]]:
+    """Pin the calling process to the CPUs of the NUMA node GPU ``device_index`` hangs off (sysfs ``local_cpulist`` of
+    its PCI function), so that the host buffers it allocates AFTERWARDS (first touch) and the thread that feeds the
+    GPU sit next to its PCIe root port.  One process per GPU (torchrun) does not do this by itself.  Returns the CPU
+    list, or None when the topology cannot be read (then nothing is changed)."""
+    import os
+
+    try:
+        bus = torch.cuda.get_device_properties(device_index).pci_bus_id
+        dom = torch.cuda.get_device_properties(device_index).pci_domain_id
+        dev = torch.cuda.get_device_properties(device_index).pci_device_id
+        path = f"/sys/bus/pci/devices/{dom:04x}:{bus:02x}:{dev:02x}.0/local_cpulist"
+        cpus: List[int] = []
+        for part in open(path).read().strip().split(","):
+            if "-" in part:
+                a, b = part.split("-")
+                cpus.extend(range(int(a), int(b) + 1))
+            elif part:
+                cpus.append(int(part))
+        cpus = sorted(set(cpus) & os.sched_getaffinity(0))
+        if not cpus:
+            return None
+        os.sched_setaffinity(0, cpus)
+        return cpus
+    except Exception:
+        return None
+
+
 class SharedHostImage:
     """A [3,H,W] fp32 host image in ONE shared-memory segment mapped by every rank of ``group`` (ranks of a
     node), page-locked on each rank: the multi-GPU host entry lets every GPU copy the rows it owns straight
@@ -679,6 +707,12 @@ class SharedHostImage:
         self._flags = whole[data_bytes:].view(torch.int64)
         if rank == src:
             self._flags.zero_()
+        # First touch: every rank writes the slice of rows it will (roughly) own before anyone page-locks the segment,
+        # so that those pages are allocated on ITS NUMA node (ownership is by contiguous row ranges in rank order).
+        if len(self.shape) == 3:
+            hh = self.shape[1]
+            self.tensor[:, hh * rank // self._world:hh * (rank + 1) // self._world].zero_()
+        dist.barrier(group)
         self._seq = 0
         self.pinned = False
         if pin and torch.cuda.is_available():

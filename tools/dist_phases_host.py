@@ -19,6 +19,8 @@ ol, W, H = 6, 6000, 4000
 local = int(os.environ.get("LOCAL_RANK", "0"))
 torch.cuda.set_device(local)
 dev = torch.device("cuda", local)
+if os.environ.get("NIND_NO_NUMA_BIND") is None:
+    print(f"rank {local}: bound to {len(nb.bind_host_to_gpu(local) or [])} CPUs of the GPU's NUMA node", flush=True)
 dist.init_process_group("nccl", device_id=dev)
 rank, world = dist.get_rank(), dist.get_world_size()
 torch.manual_seed(0)
