@@ -135,6 +135,7 @@ struct nind_net {
   std::vector<int> rows_done;         // band rows [y0, rows_done[k]) are final after step k (last enqueue)
   cudaEvent_t ev_join = nullptr;
   int flat = -1;
+  int wide = -1;   // 128-byte staging rows in the TMA-store epilogue: -1 auto (store-bound layers), 0 off, 1 wherever legal
   int pair64 = 1;  // pixel-pair mode for the C_out = 64 3x3 layers (validated on B200, profiles/r02_pair_mode_first_light.log)
   int host_first = -1, host_last = -1;  // crops in the first / last pipeline step (-1: one grid row)
   // options
@@ -463,6 +464,7 @@ struct PlanBuilder {
     s.max_ctas = net->max_ctas;
     s.cg = net->cg;
     s.dual = net->dual;
+    s.wide = net->wide;
     s.flat = net->flat == 1 ? 2 : net->flat;  // 1 = on every layer where it is legal
     if (L.n_total >= 256) s.n_tile = net->n_tile_deep;
     maybe_pair(s, L, in, in_coff);
@@ -504,6 +506,7 @@ struct PlanBuilder {
     s.max_ctas = net->max_ctas;
     s.cg = net->cg;
     s.dual = net->dual;
+    s.wide = net->wide;
     maybe_pair(s, L, in, 0);
     if (rc) return;
     Step st;
@@ -908,6 +911,8 @@ int nind_set_option(nind_net* net, const char* key, int value) {
     return 0;
   } else if (k == "dual_issuer") {  // two MMA issuer warps on alternate tiles (0 | 1)
     net->dual = value ? 1 : 0;
+  } else if (k == "wide_store") {  // 128-byte epilogue staging rows: -1 auto, 0 off, 1 wherever legal
+    net->wide = value;
   } else if (k == "flat") {  // flat (1-D) tiles on narrow maps: -1 auto, 0 off, 1 wherever legal
     net->flat = value;
   } else {

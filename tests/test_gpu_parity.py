@@ -258,7 +258,9 @@ def test_kernel_variants_agree():
     for name, opts in (("default", {}), ("unfused_pool", {"fuse_pool": 0}), ("no_pair", {"pair64": 0}),
                        ("cta1", {"cta_group": 1}),
                        ("cta2", {"cta_group": 2}), ("n128", {"n_tile_deep": 128}),
-                       ("flat_off", {"flat": 0}), ("flat_all", {"flat": 1})):
+                       ("flat_off", {"flat": 0}), ("flat_all", {"flat": 1}),
+                       ("wide_off", {"wide_store": 0}), ("wide_all", {"wide_store": 1}),
+                       ("single_issuer", {"dual_issuer": 0})):
         m = nb.UtNet().to(dev()).eval()
         m.load_state_dict(sd)
         for k, v in opts.items():
@@ -275,6 +277,10 @@ def test_kernel_variants_agree():
     # flat (1-D) tiles only change which pixels share a tile, not any pixel's summation order
     assert np.array_equal(outs["flat_off"], outs["default"])
     assert np.array_equal(outs["flat_all"], outs["default"])
+    # the staging layout of the TMA-store epilogue (64-byte halves / 128-byte rows) and the number of MMA issuer
+    # warps do not touch the arithmetic at all
+    for k in ("wide_off", "wide_all", "single_issuer"):
+        assert np.array_equal(outs[k], outs["default"]), k
 
 
 def test_cli_shim_roundtrip(tmp_path, golden_networks):
