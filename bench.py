@@ -536,7 +536,7 @@ def main():
         # crops this rank ran, over the CUDA-event time of its conv launches
         conv_fl_alg = flops_crop * (ce - cb)
         achieved = conv_fl_alg / (conv_ms * 1e-3) / 1e12 if conv_ms > 0 else 0.0
-        traffic, traffic_note = ncu_traffic(cs, batch)
+        traffic, traffic_note = ncu_traffic(cs, -(-(ce - cb) // k_steps))  # the forwards are balanced: 4 x 133 crops
         roof = {"bound": "tensor", "kernel": "nind::igemm_kernel<N_TILE, TPS, CG, C8, PM> (all conv layers)",
                 "achieved": achieved, "peak": pk["sustained"], "unit": "TFLOP/s", "frac": achieved / pk["sustained"],
                 "frac_of_burst": achieved / pk["burst"], "peak_source": pk["source"] + " (bf16_tflops_sustained)",
