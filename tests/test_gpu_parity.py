@@ -129,6 +129,54 @@ def test_utnet_forward_config1(utnet, golden_networks):
         check_pixels(y, golden_networks[f"utnet_out_{cs}"], f"UtNet cs={cs} vs reference golden")
 
 
+def test_utnet_forward_cs264_and_104(utnet):
+    """SURVEY 8d config 1 'also run 264' (the next legal size above 256) and the smallest legal crop, against the
+    oracle (the reference classes equal the oracle exactly, tests/test_oracle_golden.py)."""
+    sd = on.init_state_dict("UtNet", seed=0)
+    for cs in (264, 104):
+        torch.manual_seed(cs)
+        x = torch.rand(1, 3, cs, cs)
+        with torch.no_grad():
+            ref = on.utnet_forward(sd, x).numpy()[0]
+        y = utnet(x.to(dev())).cpu().numpy()[0]
+        check_pixels(y, ref, f"UtNet cs={cs} vs oracle")
+
+
+LAYER_SHAPES = [
+    # taps cin n_total B Hs Ws a bo epi [n_tile ws ctas cg flat pair pool]: the layer shapes of UtNet at small sizes
+    "9 8 64 2 44 52 0 0 0",                      # first layer (8-channel hi/lo input)
+    "9 64 64 2 42 50 0 0 0 0 -1 0 0 -1 1 1",     # convs1.2: pixel-pair mode + fused pool
+    "9 64 64 2 44 52 0 0 2 0 -1 0 0 -1 1 0",     # tconvs4.2 + fused 1x1 head (pixel-pair mode)
+    "9 64 64 2 44 52 0 0 0 0 -1 0 0 -1 0 0",     # the same layer in the plain 3x3 form
+    "9 128 64 2 44 52 0 0 0",                    # tconvs4.0
+    "9 64 128 2 40 40 0 0 0 0 -1 0 0 -1 0 1",    # convs2.0 .. with fused pool
+    "9 128 128 2 40 40 0 0 0",
+    "9 256 128 2 36 36 0 0 0",
+    "9 128 256 2 30 30 0 0 0",
+    "9 256 256 3 28 28 0 0 0",
+    "9 512 256 2 28 28 0 0 0",
+    "9 256 512 3 14 14 0 0 0",
+    "9 512 512 4 14 14 0 0 0",                   # flat tiles
+    "1 128 256 2 41 37 0 0 1",                   # 2x2/s2 up-convs: depth-to-space epilogue, odd sizes
+    "1 256 512 2 30 30 0 0 1",
+    "1 512 1024 2 14 14 0 0 1",
+    "1 1024 2048 2 6 6 0 0 1",
+]
+
+
+@pytest.mark.parametrize("shape", LAYER_SHAPES)
+def test_each_layer_shape_against_a_naive_convolution(shape):
+    """Per-layer parity (SURVEY 8c protocol step 2): every layer shape of the network through `igemm_kernel`, alone,
+    against a plain CUDA-core fp32 convolution over the same bf16 inputs (tools/probe, built by
+    __graft_entry__.build() from the library's own kernel objects): isolates a kernel bug from bf16 drift through
+    23 layers.  The probe also checks that nothing is written outside the destination's interior."""
+    import subprocess
+    probe = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools", "probe")
+    assert os.path.exists(probe), "tools/probe is missing: run __graft_entry__.build()"
+    r = subprocess.run([probe, "conv"] + shape.split(), capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0 and "-> PASS" in r.stdout, r.stdout[-1500:] + r.stderr[-500:]
+
+
 def test_utnet_batch_and_rect(utnet):
     sd = on.init_state_dict("UtNet", seed=0)
     torch.manual_seed(3)
