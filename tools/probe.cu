@@ -3,6 +3,7 @@
 // convolution.  Each invocation runs ONE test so that a trap in one cannot mask the others.
 //
 //   probe desc <r0> <sbo_bytes> <bo_mode>
+//   probe tmem                                TMEM -> register read throughput per tcgen05.ld shape
 //   probe hbm [GiB]                          read / write / copy ceilings of plain kernels
 //   probe conv <taps> <cin> <n_total> <B> <Hs> <Ws> <a_mode> <bo_mode> <epi> [n_tile] [ws] [ctas]
 //
@@ -624,6 +625,113 @@ static int run_hbm(double gib) {
   return 0;
 }
 
+// ------------------------------------------------------------------ TMEM read throughput (probe tmem)
+// How fast can the epilogue warps drain accumulators?  One CTA per SM, W warps (4, 8 or 16: 1, 2 or 4 per TMEM lane
+// quarter), each loops tcgen05.ld of 4 KB + tcgen05.wait::ld over its quarter.  SHAPE 0: 32x32b.x32 (32 lanes x 32
+// columns, what the epilogue uses), 1: 32x32b.x16 x 2, 2: 16x256b.x8 x 2 halves (16 lanes x 64 columns each),
+// 3: 16x128b.x16 x 2 halves.  DEPTH = loads in flight before each wait.
+#define TM_REGS32(v) "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), \
+  "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), \
+  "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), \
+  "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+#define TM_FMT32 "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}"
+template <int SHAPE>
+__device__ __forceinline__ void tm_load4k(uint32_t taddr, uint32_t (&v)[32]) {
+  if (SHAPE == 0) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 " TM_FMT32 ", [%32];" : TM_REGS32(v) : "r"(taddr) : "memory");
+  } else if (SHAPE == 1) {
+    uint32_t(&a)[16] = reinterpret_cast<uint32_t(&)[16]>(v[0]);
+    uint32_t(&b)[16] = reinterpret_cast<uint32_t(&)[16]>(v[16]);
+    tmem_ld_32x32(taddr, a);
+    tmem_ld_32x32(taddr + 16, b);
+  } else if (SHAPE == 2) {  // two 16-lane halves x 32 columns each (x4 = 16 regs)
+    asm volatile("tcgen05.ld.sync.aligned.16x256b.x4.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+                   "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+                 : "r"(taddr) : "memory");
+    asm volatile("tcgen05.ld.sync.aligned.16x256b.x4.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+                 : "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+                   "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+                 : "r"(taddr + (16u << 16)) : "memory");
+  } else {  // 16x128b.x8: 16 lanes x 32 columns, 16 regs; two halves
+    asm volatile("tcgen05.ld.sync.aligned.16x128b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+                   "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+                 : "r"(taddr) : "memory");
+    asm volatile("tcgen05.ld.sync.aligned.16x128b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+                 : "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+                   "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+                 : "r"(taddr + (16u << 16)) : "memory");
+  }
+}
+
+template <int SHAPE, int DEPTH>
+__global__ void __launch_bounds__(512, 1) tmem_read_kernel(int iters, long long* clk, uint32_t* sink) {
+  __shared__ uint32_t slot;
+  const int warp = threadIdx.x >> 5;
+  if (warp == 0) {
+    tmem_alloc(smem_u32(&slot), 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t base = slot + (static_cast<uint32_t>((warp & 3) * 32) << 16);
+  uint32_t acc = 0;
+  __syncthreads();
+  const long long t0 = clock64();
+  for (int it = 0; it < iters; ++it) {
+    uint32_t v[DEPTH][32];
+#pragma unroll
+    for (int d = 0; d < DEPTH; ++d) tm_load4k<SHAPE>(base + ((it * DEPTH + d) * 32 & 511 & ~31), v[d]);
+    tmem_wait_ld();
+#pragma unroll
+    for (int d = 0; d < DEPTH; ++d)
+#pragma unroll
+      for (int j = 0; j < 32; ++j) acc ^= v[d][j];
+  }
+  const long long t1 = clock64();
+  if (acc == 0x12345u) *sink = acc;
+  if (threadIdx.x == 0) clk[blockIdx.x] = t1 - t0;
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(slot, 512);
+}
+
+template <int SHAPE, int DEPTH>
+static void run_tmem_one(const char* name, int warps, long long* dclk, uint32_t* sink, int sms) {
+  const int iters = 2000;
+  tmem_read_kernel<SHAPE, DEPTH><<<sms, warps * 32>>>(iters, dclk, sink);
+  CK(cudaDeviceSynchronize());
+  tmem_read_kernel<SHAPE, DEPTH><<<sms, warps * 32>>>(iters, dclk, sink);
+  CK(cudaDeviceSynchronize());
+  std::vector<long long> h(sms);
+  CK(cudaMemcpy(h.data(), dclk, sms * 8, cudaMemcpyDeviceToHost));
+  double avg = 0;
+  for (auto c : h) avg += (double)c;
+  avg /= sms;
+  printf("tmem %-22s depth %d  %2d warps: %7.1f B/clk/SM  (%.0f clk per 4 KB load per warp)\n", name, DEPTH, warps,
+         (double)warps * iters * DEPTH * 4096.0 / avg, avg / (iters * DEPTH));
+}
+
+static int run_tmem() {
+  int sms = 0;
+  CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0));
+  long long* dclk;
+  uint32_t* sink;
+  CK(cudaMalloc(&dclk, sms * 8));
+  CK(cudaMalloc(&sink, 4));
+  for (int warps : {4, 8, 16}) {
+    run_tmem_one<0, 1>("32x32b.x32", warps, dclk, sink, sms);
+    run_tmem_one<0, 2>("32x32b.x32", warps, dclk, sink, sms);
+    run_tmem_one<1, 1>("32x32b.x16 x2", warps, dclk, sink, sms);
+    run_tmem_one<2, 1>("16x256b.x4 x2", warps, dclk, sink, sms);
+    run_tmem_one<2, 2>("16x256b.x4 x2", warps, dclk, sink, sms);
+    run_tmem_one<3, 1>("16x128b.x8 x2", warps, dclk, sink, sms);
+  }
+  return 0;
+}
+
 int main(int argc, char** argv) {
   if (argc < 2) { printf("usage: probe desc|conv ...\n"); return 2; }
   if (!strcmp(argv[1], "desc")) {
@@ -635,6 +743,7 @@ int main(int argc, char** argv) {
     return run_desc0(atoi(argv[2]), atoi(argv[3]), atoi(argv[4]), atoi(argv[5]));
   }
   if (!strcmp(argv[1], "conv")) return run_conv(argc, argv);
+  if (!strcmp(argv[1], "tmem")) return run_tmem();
   if (!strcmp(argv[1], "hbm")) return run_hbm(argc > 2 ? atof(argv[2]) : 4.0);
   return 2;
 }
