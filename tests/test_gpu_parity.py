@@ -157,7 +157,8 @@ LAYER_SHAPES = [
     "9 512 256 2 28 28 0 0 0",
     "9 256 512 3 14 14 0 0 0",
     "9 512 512 4 14 14 0 0 0",                   # flat tiles
-    "1 128 256 2 41 37 0 0 1",                   # 2x2/s2 up-convs: depth-to-space epilogue, odd sizes
+    "1 128 256 2 41 37 0 0 1",                   # 2x2/s2 up-convs: depth-to-space epilogue, odd sizes (flat tiles)
+    "1 128 256 2 40 48 0 0 1",                   # the same layer on 16x8 tiles: TMA stores, one box per 4 rows
     "1 256 512 2 30 30 0 0 1",
     "1 512 1024 2 14 14 0 0 1",
     "1 1024 2048 2 6 6 0 0 1",
