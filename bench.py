@@ -85,19 +85,53 @@ def ncu_traffic(cs, batch):
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled during the timed region (B200_PROFILING.md)."""
+    """SM clock and clock-event (throttle) reasons sampled during the timed region (B200_PROFILING.md's clocks line).
+
+    Read through NVML in this process — the library `nvidia-smi` itself reads, two calls per sample every 100 ms —
+    because a looping `nvidia-smi --query-gpu=... -lms 100` next to the bench occasionally stalls the GPU for tens of
+    milliseconds (one 60 ms step among sixty 36 ms ones with it, none without: per-step stamps under
+    NIND_BENCH_DIAG=1).  Falls back to the `nvidia-smi` loop when pynvml cannot be imported."""
 
     Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    NAMES = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
 
     def __init__(self, index=0):
-        self.rows, self.proc, self.index = [], None, index
+        self.rows, self.proc, self.index, self.nvml, self.stop_flag, self.source = [], None, index, None, False, None
+
+    def _nvml_loop(self):
+        n = self.nvml
+        bits = [n.nvmlClocksThrottleReasonHwSlowdown, n.nvmlClocksThrottleReasonHwThermalSlowdown,
+                n.nvmlClocksThrottleReasonSwThermalSlowdown, n.nvmlClocksThrottleReasonSwPowerCap]
+        while not self.stop_flag:
+            try:
+                sm = n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM)
+                r = n.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle)
+                self.rows.append([time.time(), str(sm), str(self.sm_max)] +
+                                 ["Active" if r & b else "Not Active" for b in bits])
+            except Exception:
+                pass
+            time.sleep(0.1)
 
     def start(self):
         try:
+            import pynvml
+            pynvml.nvmlInit()
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = int(vis.split(",")[self.index]) if vis and all(v.strip().isdigit() for v in vis.split(",")) else self.index
+            self.handle = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.sm_max = pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM)
+            self.nvml, self.source = pynvml, "nvml"
+            self.t = threading.Thread(target=self._nvml_loop, daemon=True)
+            self.t.start()
+            return
+        except Exception:
+            self.nvml = None
+        try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.source = "nvidia-smi"
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
         except Exception:
@@ -108,25 +142,28 @@ class ClockSampler:
             self.rows.append([time.time()] + [c.strip() for c in line.split(",")])
 
     def stop(self, t0=None, t1=None):
-        if not self.proc:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        if not self.proc and not self.nvml:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi / NVML unavailable"]}
         time.sleep(0.15)
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=2)
-        except Exception:
-            self.proc.kill()
+        if self.nvml:
+            self.stop_flag = True
+            self.t.join(timeout=1)
+        else:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                self.proc.kill()
         # keep the samples taken inside the timed region (the sampler is started before the warm-up so that
-        # nvidia-smi's start-up / NVML initialisation cannot stall the timed launches)
+        # its start-up / NVML initialisation cannot stall the timed launches)
         rows = [r[1:] for r in self.rows if len(r) >= 7 and (t0 is None or t0 - 0.05 <= r[0] <= t1 + 0.15)]
         if not rows:
             rows = [r[1:] for r in self.rows[-3:] if len(r) >= 7]
         sm = [float(r[0]) for r in rows if r[0].replace(".", "").isdigit()]
         mx = [float(r[1]) for r in rows if r[1].replace(".", "").isdigit()]
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = sorted({names[i] for r in rows for i in range(4) if r[2 + i].startswith("Active")})
+        reasons = sorted({self.NAMES[i] for r in rows for i in range(4) if r[2 + i].startswith("Active")})
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": reasons, "samples": len(sm)}
+                "reasons": reasons, "samples": len(sm), "source": self.source}
 
 
 def sample_crops(nx, ny, k):
@@ -434,16 +471,29 @@ def main():
     sync_all()
     t_start = time.time()
     torch.cuda.profiler.start()  # no-op unless run under `ncu --profile-from-start off` (tools/run_ncu_r2.sh)
+    marks = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
     e0.record()
-    for _ in range(args.steps):
+    for i in range(args.steps):
         out = step()
+        marks[i].record()   # per-step stamps (no synchronisation): a stall shows up as one long step
     e1.record()
     sync_all()
     torch.cuda.profiler.stop()
     t_end = time.time()
     ms = max_over_ranks(e0.elapsed_time(e1))
+    step_ms = [a.elapsed_time(b) for a, b in zip([e0] + marks[:-1], marks)]
     launches = lib.nind_kernel_launches() - l0
     clocks = sampler.stop(t_start, t_end) if rank == 0 else None
+    if os.environ.get("NIND_BENCH_DIAG") and rank == 0:
+        print("diag: per-step ms with the clock sampler running: " + " ".join(f"{v:.2f}" for v in step_ms), file=sys.stderr)
+        m2 = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
+        m2[0].record()
+        for i in range(args.steps):
+            step()
+            m2[i + 1].record()
+        torch.cuda.synchronize()
+        print("diag: per-step ms after the sampler was stopped:      " +
+              " ".join(f"{a.elapsed_time(b):.2f}" for a, b in zip(m2, m2[1:])), file=sys.stderr)
 
     # ---- end to end through the host-buffer entry point (N = 1) / host image in + out (N > 1)
     # N > 1: one shared, page-locked host image that every rank writes the rows it owns into (N PCIe links)
