@@ -527,6 +527,43 @@ def test_dir_cli_matches_single_image_path(tmp_path):
 
 
 @pytest.mark.gpu
+def test_dir_cli_two_gpus_match_one(tmp_path):
+    """dir_cli --gpus 2 (one replica process per GPU fed from one file queue — what replaces denoise_dir.py:76-103's
+    per-image subprocesses on a multi-GPU box) writes the same files and the same testres.json scores as --gpus 1.
+    Skipped on a one-GPU box."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    import json
+
+    import cv2
+    from nind_denoise_b200 import dir_cli
+
+    rng = np.random.default_rng(33)
+    noisy = tmp_path / "set_a"
+    noisy.mkdir()
+    names = [f"NIND_a_ISO{iso}.tif" for iso in (400, 800, 1600, 3200, 6400)]
+    for name in names + ["NIND_a_ISO100.tif"]:
+        cv2.imwrite(str(noisy / name), (rng.random((150, 190, 3)) * 65535).astype(np.uint16))
+    outs = {}
+    for gpus in (1, 2):
+        mdir = tmp_path / f"model_g{gpus}"
+        mdir.mkdir()
+        model_path = str(mdir / "generator_3.pt")
+        torch.save(on.init_state_dict("UtNet", seed=0), model_path)
+        rc = dir_cli.main(["--noisy_dir", str(noisy), "--result_dir", str(tmp_path / f"out{gpus}"), "--network", "UtNet",
+                           "--model_path", model_path, "--cs", "120", "--ucs", "96", "--gpus", str(gpus)])
+        assert rc == 0
+        d = tmp_path / f"out{gpus}" / f"model_g{gpus}"
+        assert sorted(os.listdir(d)) == sorted(names)
+        outs[gpus] = ({n: cv2.imread(str(d / n), cv2.IMREAD_UNCHANGED) for n in names},
+                      json.load(open(mdir / "testres.json"))["3"])
+    for n in names:
+        assert np.array_equal(outs[1][0][n], outs[2][0][n]), n
+    for k, v in outs[1][1].items():
+        assert abs(v - outs[2][1][k]) <= 1e-7, k
+
+
+@pytest.mark.gpu
 def test_whole_image_mode(utnet):
     """--whole_image (denoise_image.py:91-97,110-128,255-256): one forward over the mirror-padded image."""
     sd = on.init_state_dict("UtNet", seed=0)
