@@ -527,6 +527,60 @@ def test_dir_cli_matches_single_image_path(tmp_path):
 
 
 @pytest.mark.gpu
+def test_cli_jpeg_in_jpeg_out_and_whole_image(tmp_path):
+    """The remaining file conventions of denoise_image.py through the CLI shim: an 8-bit JPEG in (np_imgops.py:19-22:
+    /255) and a .jpg out (pt_helpers.py:36-40: clip(0,1), 8 bit) on the tiled path, and --whole_image --pad with a
+    16-bit .png out, both against the oracle pushed through the same cv2 encoder."""
+    import cv2
+    from nind_denoise_b200 import cli
+
+    sd = {k: v.clone() for k, v in on.init_state_dict("UtNet", seed=0).items()}
+    sd["tconvs4.4.bias"] = sd["tconvs4.4.bias"] + 0.5     # output inside the displayable range
+    model_path = str(tmp_path / "generator_1.pt")
+    torch.save(sd, model_path)
+    rng = np.random.default_rng(61)
+    yy, xx = np.meshgrid(np.linspace(0, 1, 230), np.linspace(0, 1, 260), indexing="ij")
+    smooth = np.stack([0.5 + 0.4 * np.sin(5 * xx), 0.5 + 0.4 * np.cos(4 * yy), 0.5 + 0.3 * np.sin(3 * xx + 2 * yy)], -1)
+    src = str(tmp_path / "in.jpg")
+    cv2.imwrite(src, np.clip((smooth + rng.normal(0, 0.03, smooth.shape)) * 255, 0, 255).astype(np.uint8))
+    img = cli.img_path_to_np_flt(src)                      # what the reference reads from that file: RGB CHW / 255
+    assert img.dtype == np.float32 and img.shape == (3, 230, 260) and img.max() <= 1.0
+
+    def fwd(c):
+        return on.utnet_forward(sd, torch.from_numpy(c).unsqueeze(0))[0].numpy()
+
+    # tiled, .jpg out
+    out_jpg = str(tmp_path / "out.jpg")
+    assert cli.main(["--network", "UtNet", "--model_path", model_path, "--input", src, "--output", out_jpg,
+                     "--cs", "120", "--ucs", "96", "--exif_method", "noexif"]) == 0
+    with torch.no_grad():
+        ref = og.denoise_tiled(img, fwd, 120, 96, 6)
+    exp8 = (np.clip(ref, 0, 1) * 255 + 0.5).astype(np.uint8)                       # pt_helpers.py:36-38
+    exp_path = str(tmp_path / "expected.jpg")
+    cv2.imwrite(exp_path, cv2.cvtColor(np.ascontiguousarray(exp8.transpose(1, 2, 0)), cv2.COLOR_RGB2BGR))
+    got, exp = cv2.imread(out_jpg), cv2.imread(exp_path)
+    assert got.shape == exp.shape == (230, 260, 3) and got.dtype == np.uint8
+    # a pixel whose value sits on an 8-bit rounding boundary may differ by one level before encoding
+    # (and the JPEG encoder spreads such a flip over its 8x8 block)
+    d = np.abs(got.astype(np.int32) - exp.astype(np.int32))
+    assert d.max() <= 4 and d.mean() <= 0.25, (int(d.max()), float(d.mean()))
+
+    # whole image, 16-bit .png out
+    small = str(tmp_path / "small.png")
+    cv2.imwrite(small, (rng.random((104, 136, 3)) * 65535).astype(np.uint16))
+    out_png = str(tmp_path / "whole.png")
+    assert cli.main(["--network", "UtNet", "--model_path", model_path, "--input", small, "--output", out_png,
+                     "--whole_image", "--pad", "8", "--cs", "120", "--ucs", "96", "--exif_method", "noexif"]) == 0
+    im2 = cli.img_path_to_np_flt(small)
+    with torch.no_grad():
+        y = fwd(og.whole_image_input(im2, 8))[:, 8:-8, 8:-8]
+    exp16 = (np.clip(y, 0, 1) * 65535).round().astype(np.int64)
+    got16 = cv2.cvtColor(cv2.imread(out_png, cv2.IMREAD_UNCHANGED), cv2.COLOR_BGR2RGB).transpose(2, 0, 1).astype(np.int64)
+    assert got16.shape == exp16.shape
+    assert np.abs(got16 - exp16).max() <= 0.25 * float(y.std()) * 65535 + 1
+
+
+@pytest.mark.gpu
 def test_dir_cli_two_gpus_match_one(tmp_path):
     """dir_cli --gpus 2 (one replica process per GPU fed from one file queue — what replaces denoise_dir.py:76-103's
     per-image subprocesses on a multi-GPU box) writes the same files and the same testres.json scores as --gpus 1.
