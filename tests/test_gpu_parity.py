@@ -172,8 +172,14 @@ def test_each_layer_shape_against_a_naive_convolution(shape):
     __graft_entry__.build() from the library's own kernel objects): isolates a kernel bug from bf16 drift through
     23 layers.  The probe also checks that nothing is written outside the destination's interior."""
     import subprocess
-    probe = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools", "probe")
-    assert os.path.exists(probe), "tools/probe is missing: run __graft_entry__.build()"
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    probe = os.path.join(root, "tools", "probe")
+    if not os.path.exists(probe):   # normally built by __graft_entry__.build(); nvcc is on the GPU image too
+        import sys
+        sys.path.insert(0, root)
+        import __graft_entry__
+        __graft_entry__.build()
+    assert os.path.exists(probe), "tools/probe is missing and could not be built (__graft_entry__.build())"
     r = subprocess.run([probe, "conv"] + shape.split(), capture_output=True, text=True, timeout=120)
     assert r.returncode == 0 and "-> PASS" in r.stdout, r.stdout[-1500:] + r.stderr[-500:]
 
